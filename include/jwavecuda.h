@@ -1,0 +1,141 @@
+/* jwavecuda.h -- C ABI of libjwavecuda.so: the B200 (sm_100a) wavelet filter-bank engine that sits
+ * behind JWave-Pro's BasicTransform API for three transforms:
+ *
+ *   MODWT  (a-trous circular convolution)   replaces  transforms/MODWTTransform.java:256-306 forwardMODWT,
+ *                                                      :337-375 inverseMODWT (direct method :677-716)
+ *   FWT    (decimated periodic pyramid)     replaces  transforms/FastWaveletTransform.java:71-101,119-153
+ *                                                      + transforms/wavelets/Wavelet.java:236-303
+ *   WPT    (full packet tree)               replaces  transforms/WaveletPacketTransform.java:73-124,141-191
+ *
+ * (paths relative to /root/reference/src/main/java/jwave/).  The reference has no FFI of its own; these
+ * entry points are what its Java subclasses CudaMODWTTransform / CudaFastWaveletTransform /
+ * CudaWaveletPacketTransform bind through Panama FFM (java/…/JwcNative.java), and what the
+ * Python ctypes mirror in jwave-pro_b200/ binds for the tests.
+ *
+ * Conventions
+ *  - plain C, no CUDA/torch types; every size is int64_t or int; all arrays are IEEE fp64, row-major, dense.
+ *  - return value: 0 = JWC_OK, negative = error (jwc_last_error() gives the text, thread-local).
+ *    Nothing here aborts, exits or throws across the boundary.
+ *  - There is NO CPU fallback: every transform runs as CUDA kernels; without a usable device
+ *    jwc_create() returns NULL.
+ *  - Batches: `batch` independent signals of length n each; signal b starts at in + b*n.
+ *  - A context may be used from several host threads at once (calls are re-entrant; scratch memory is
+ *    stream-ordered per call).  Filters are passed per call; the library keeps no filter state.
+ */
+#ifndef JWAVECUDA_H
+#define JWAVECUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define JWC_API __attribute__((visibility("default")))
+#else
+#define JWC_API
+#endif
+
+typedef struct jwc_ctx jwc_ctx;
+
+enum {
+  JWC_OK = 0,
+  JWC_ERR_INVALID = -1,     /* bad argument (NULL pointer, n < 1, level out of range, L > JWC_MAX_TAPS ...) */
+  JWC_ERR_CUDA = -2,        /* a CUDA runtime call failed; text in jwc_last_error() */
+  JWC_ERR_NOMEM = -3,       /* device or pinned allocation failed */
+  JWC_ERR_UNSUPPORTED = -4  /* shape outside what the build supports */
+};
+
+/* flags (bit-or) */
+#define JWC_FLAG_EXACT 1u         /* unfused multiply/add in the reference's summation order: results are
+                                     bit-identical to the JVM arithmetic (slower kernels).  Default uses FMA;
+                                     then |err| <= 1e-12*max|x| versus the reference. */
+#define JWC_FLAG_FORCE_GENERIC 2u /* one kernel per level, no tile fusion (debug / cross-check) */
+
+#define JWC_MAX_TAPS 64           /* longest filter accepted (reference max on the path: Daubechies20 = 40) */
+#define JWC_MODWT_MAX_LEVEL 13    /* transforms/MODWTTransform.java:111 MAX_DECOMPOSITION_LEVEL */
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+
+/* devices: CUDA ordinals the context may use (host-buffer calls shard the batch over all of them, by
+ * signal, no collective); devices == NULL or ndev <= 0 means "the current device only". */
+JWC_API jwc_ctx* jwc_create(const int* devices, int ndev);
+JWC_API void jwc_destroy(jwc_ctx* ctx);
+JWC_API int jwc_num_devices(const jwc_ctx* ctx);
+JWC_API int jwc_device_ordinal(const jwc_ctx* ctx, int slot);
+JWC_API const char* jwc_last_error(void);
+JWC_API const char* jwc_version(void);
+/* number of CUDA kernels this context has launched so far (all slots) */
+JWC_API uint64_t jwc_launch_count(const jwc_ctx* ctx);
+/* tuning knobs for sweeps ("modwt_tile", "modwt_threads", ...); unknown key -> JWC_ERR_INVALID */
+JWC_API int jwc_set_tuning(jwc_ctx* ctx, const char* key, int value);
+JWC_API int jwc_get_tuning(const jwc_ctx* ctx, const char* key, int* value);
+
+/* ---- memory helpers (pinned host staging = what the Java side wraps in MemorySegments) --------------- */
+JWC_API void* jwc_alloc_pinned(size_t bytes);
+JWC_API void jwc_free_pinned(void* p);
+JWC_API void* jwc_alloc_device(jwc_ctx* ctx, int slot, size_t bytes);
+JWC_API void jwc_free_device(jwc_ctx* ctx, int slot, void* p);
+JWC_API int jwc_copy_to_device(jwc_ctx* ctx, int slot, void* dst_dev, const void* src_host, size_t bytes);
+JWC_API int jwc_copy_to_host(jwc_ctx* ctx, int slot, void* dst_host, const void* src_dev, size_t bytes);
+JWC_API int jwc_synchronize(jwc_ctx* ctx);
+
+/* ---- MODWT ------------------------------------------------------------------------------------------
+ * g, h: the level-1 MODWT filters g~ = (scalingDeCom/||.||)/sqrt2, h~ = (waveletDeCom/||.||)/sqrt2
+ *       (MODWTTransform.java:462-475), L taps each; level-j upsampling (:618-630) is implicit.
+ * forward:  x [batch][n]  ->  coeffs [batch][levels+1][n], rows W_1..W_J, V_J   (:298-303, flat form :406-416)
+ *           W_j[t] = sum_m h[m] V_{j-1}[(t - m 2^(j-1)) mod n],  V_j likewise with g           (:677-690)
+ * inverse:  coeffs -> x,  V_{j-1}[t] = sum_m g[m] V_j[(t + m 2^(j-1)) mod n] + sum_m h[m] W_j[...]  (:703-716, :363-369)
+ * Any n >= 1 (not only 2^p); 1 <= levels <= min(13, floor(log2 n)) as the reference enforces (:257-282) --
+ * the library itself only requires levels >= 1 and (L-1)*2^(levels-1) representable; callers validate.
+ * Host-pointer variants shard the batch over the context's devices and pipeline H2D / kernels / D2H.   */
+JWC_API int jwc_modwt_forward(jwc_ctx* ctx, const double* x, double* coeffs, int64_t batch, int64_t n, int levels,
+                              const double* g, const double* h, int L, unsigned flags);
+JWC_API int jwc_modwt_inverse(jwc_ctx* ctx, const double* coeffs, double* x, int64_t batch, int64_t n, int levels,
+                              const double* g, const double* h, int L, unsigned flags);
+/* device-pointer variants: buffers live on device `slot` of the context; `stream` is a cudaStream_t
+ * (NULL = the context's own stream for that slot); asynchronous with respect to the host. */
+JWC_API int jwc_modwt_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_x, double* d_coeffs,
+                                  int64_t batch, int64_t n, int levels, const double* g, const double* h, int L,
+                                  unsigned flags);
+JWC_API int jwc_modwt_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_coeffs, double* d_x,
+                                  int64_t batch, int64_t n, int levels, const double* g, const double* h, int L,
+                                  unsigned flags);
+
+/* ---- FWT --------------------------------------------------------------------------------------------
+ * lo, hi: scalingDeCom / waveletDeCom for forward, scalingReCon / waveletReCon for inverse (Wavelet.java:178-219).
+ * n must be 2^p, 0 <= levels <= p (FastWaveletTransform.java:74-83); levels = 0 copies.
+ * forward: in [batch][n] -> out [batch][n] in the reference's in-place layout [A_J | D_J | ... | D_1]
+ *          one step on a length-h prefix: lo[i] = sum_j x[(2i+j) mod h] lo[j], hi likewise (Wavelet.java:236-260)
+ * inverse: synthesis out[(2i+j) mod h] += c[i] lo[j] + c[i+h/2] hi[j] (Wavelet.java:277-303), h = 2n/2^levels .. n */
+JWC_API int jwc_fwt_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, int levels,
+                            const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, int levels,
+                            const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                int64_t batch, int64_t n, int levels, const double* lo, const double* hi, int L,
+                                unsigned flags);
+JWC_API int jwc_fwt_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                int64_t batch, int64_t n, int levels, const double* lo, const double* hi, int L,
+                                unsigned flags);
+
+/* ---- WPT --------------------------------------------------------------------------------------------
+ * Same step, applied to every aligned block of length h = n/2^l at level l (WaveletPacketTransform.java:98-120,
+ * :167-187); leaves in natural (Paley) order.  n = 2^p, 0 <= levels <= p. */
+JWC_API int jwc_wpt_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, int levels,
+                            const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, int levels,
+                            const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                int64_t batch, int64_t n, int levels, const double* lo, const double* hi, int L,
+                                unsigned flags);
+JWC_API int jwc_wpt_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                int64_t batch, int64_t n, int levels, const double* lo, const double* hi, int L,
+                                unsigned flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JWAVECUDA_H */

@@ -1,0 +1,427 @@
+// jwc_api.cu -- the extern "C" boundary of libjwavecuda.so (include/jwavecuda.h): context, memory helpers,
+// argument validation, dispatch (fused tile kernels when the shape allows, generic kernels otherwise -- both CUDA,
+// there is no CPU path), and the host-buffer pipeline that shards a batch over the context's devices.
+#include <cstdarg>
+#include <cstring>
+#include <thread>
+
+#include "jwc_internal.cuh"
+
+namespace jwc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int ordinal) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != ordinal) ok = (cudaSetDevice(ordinal) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+enum class Op { ModwtFwd, ModwtInv, FwtFwd, FwtInv, WptFwd, WptInv };
+
+bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+int ilog2(int64_t n) {
+  int p = 0;
+  while (((int64_t)1 << (p + 1)) <= n) p++;
+  return p;
+}
+
+int validate(Op op, const void* in, const void* out, int64_t batch, int64_t n, int levels, const double* f0,
+             const double* f1, int L) {
+  JWC_REQUIRE(in != nullptr && out != nullptr, "input/output pointer is NULL");
+  JWC_REQUIRE(f0 != nullptr && f1 != nullptr, "filter pointer is NULL");
+  JWC_REQUIRE(batch >= 0, "batch must be >= 0 (got %lld)", (long long)batch);
+  JWC_REQUIRE(n >= 1, "signal length must be >= 1 (got %lld)", (long long)n);
+  JWC_REQUIRE(n < ((int64_t)1 << 40), "signal length %lld too large", (long long)n);
+  JWC_REQUIRE(L >= 1 && L <= JWC_MAX_TAPS, "filter length %d outside 1..%d", L, JWC_MAX_TAPS);
+  if (op == Op::ModwtFwd || op == Op::ModwtInv) {
+    JWC_REQUIRE(levels >= 1 && levels <= 40, "MODWT level %d out of range", levels);
+  } else {
+    JWC_REQUIRE(is_pow2(n), "given array length is not 2^p (got %lld)", (long long)n);
+    JWC_REQUIRE(levels >= 0 && levels <= ilog2(n), "given level %d is out of range for given array of length %lld",
+                levels, (long long)n);
+  }
+  return JWC_OK;
+}
+
+void load_filters(FilterPair& fp, const double* f0, const double* f1, int L) {
+  memset(&fp, 0, sizeof(fp));
+  memcpy(fp.f0, f0, sizeof(double) * (size_t)L);
+  memcpy(fp.f1, f1, sizeof(double) * (size_t)L);
+}
+
+// One transform on device-resident buffers of slot `dev`, enqueued on `st`.
+int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, const double* d_in, double* d_out,
+               int64_t batch, int64_t n, int levels, const FilterPair& fp, int L, unsigned flags) {
+  if (batch == 0) return JWC_OK;
+  const bool exact = (flags & JWC_FLAG_EXACT) != 0;
+  const bool generic = exact || (flags & JWC_FLAG_FORCE_GENERIC) != 0 || ctx->tune.force_generic != 0;
+  int rc = JWC_ERR_UNSUPPORTED;
+  if (!generic) {
+    switch (op) {
+      case Op::ModwtFwd: rc = fast_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L); break;
+      case Op::ModwtInv: rc = fast_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L); break;
+      case Op::FwtFwd: rc = fast_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
+      case Op::FwtInv: rc = fast_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
+      case Op::WptFwd: rc = fast_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, true); break;
+      case Op::WptInv: rc = fast_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, true); break;
+    }
+    if (rc != JWC_ERR_UNSUPPORTED) return rc;
+  }
+  switch (op) {
+    case Op::ModwtFwd: return generic_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, exact);
+    case Op::ModwtInv: return generic_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, exact);
+    case Op::FwtFwd: return generic_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false, exact);
+    case Op::FwtInv: return generic_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false, exact);
+    case Op::WptFwd: return generic_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, true, exact);
+    case Op::WptInv: return generic_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, true, exact);
+  }
+  return JWC_ERR_INVALID;
+}
+
+void io_sizes(Op op, int64_t n, int levels, int64_t* in_per, int64_t* out_per) {
+  *in_per = n;
+  *out_per = n;
+  if (op == Op::ModwtFwd) *out_per = (int64_t)(levels + 1) * n;
+  if (op == Op::ModwtInv) *in_per = (int64_t)(levels + 1) * n;
+}
+
+// Host-buffer pipeline on ONE slot: chunks of signals, double-buffered device staging, H2D / kernels / D2H on three
+// streams chained by events.  Called on its own host thread per slot when the context spans several devices.
+int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, int64_t batch, int64_t n, int levels,
+                  const FilterPair& fp, int L, unsigned flags) {
+  if (batch == 0) return JWC_OK;
+  const DeviceSlot& dev = ctx->slots[slot];
+  DeviceGuard guard(dev.ordinal);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", dev.ordinal); return JWC_ERR_CUDA; }
+  int64_t in_per, out_per;
+  io_sizes(op, n, levels, &in_per, &out_per);
+  const int64_t per_sig_bytes = (in_per + out_per) * (int64_t)sizeof(double);
+  int64_t chunk_mb = ctx->tune.h2d_chunk_mb > 0 ? ctx->tune.h2d_chunk_mb : 512;
+  int64_t chunk = (chunk_mb << 20) / per_sig_bytes;
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  const int nbuf = (chunk < batch) ? 2 : 1;
+
+  cudaStream_t sc = dev.stream, si = dev.copy_in, so = dev.copy_out;
+  double* d_in[2] = {nullptr, nullptr};
+  double* d_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {}, ev_alloc = nullptr;
+  int rc = JWC_OK;
+  auto fail = [&](cudaError_t e, const char* what) {
+    set_error("%s failed: %s", what, cudaGetErrorString(e));
+    rc = JWC_ERR_CUDA;
+  };
+  cudaError_t e;
+  for (int i = 0; i < nbuf && rc == JWC_OK; i++) {
+    if ((e = cudaMallocAsync((void**)&d_in[i], (size_t)(chunk * in_per) * sizeof(double), sc)) != cudaSuccess ||
+        (e = cudaMallocAsync((void**)&d_out[i], (size_t)(chunk * out_per) * sizeof(double), sc)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("device staging allocation of %lld MiB failed: %s",
+                (long long)((chunk * (in_per + out_per) * 8) >> 20), cudaGetErrorString(e));
+      rc = JWC_ERR_NOMEM;
+    }
+    if (rc == JWC_OK && ((e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming)) != cudaSuccess ||
+                         (e = cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming)) != cudaSuccess ||
+                         (e = cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming)) != cudaSuccess))
+      fail(e, "cudaEventCreate");
+  }
+  if (rc == JWC_OK && (e = cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming)) != cudaSuccess)
+    fail(e, "cudaEventCreate");
+  if (rc == JWC_OK) {
+    // staging was allocated in stream order on sc: the copy streams must not touch it earlier
+    if ((e = cudaEventRecord(ev_alloc, sc)) != cudaSuccess || (e = cudaStreamWaitEvent(si, ev_alloc, 0)) != cudaSuccess ||
+        (e = cudaStreamWaitEvent(so, ev_alloc, 0)) != cudaSuccess)
+      fail(e, "stream ordering");
+  }
+  int64_t c = 0;
+  for (int64_t b0 = 0; b0 < batch && rc == JWC_OK; b0 += chunk, c++) {
+    const int64_t nb = (batch - b0 < chunk) ? batch - b0 : chunk;
+    const int k = (int)(c % nbuf);
+    if (c >= nbuf) {
+      // d_in[k] is free once the kernels of chunk c-nbuf ran; d_out[k] once its D2H finished
+      if ((e = cudaStreamWaitEvent(si, ev_k[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
+      if ((e = cudaStreamWaitEvent(sc, ev_out[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
+    }
+    if ((e = cudaMemcpyAsync(d_in[k], in + b0 * in_per, (size_t)(nb * in_per) * sizeof(double), cudaMemcpyHostToDevice,
+                             si)) != cudaSuccess) { fail(e, "cudaMemcpyAsync(H2D)"); break; }
+    if ((e = cudaEventRecord(ev_in[k], si)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
+    if ((e = cudaStreamWaitEvent(sc, ev_in[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
+    rc = run_device(ctx, dev, sc, op, d_in[k], d_out[k], nb, n, levels, fp, L, flags);
+    if (rc != JWC_OK) break;
+    if ((e = cudaEventRecord(ev_k[k], sc)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
+    if ((e = cudaStreamWaitEvent(so, ev_k[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
+    if ((e = cudaMemcpyAsync(out + b0 * out_per, d_out[k], (size_t)(nb * out_per) * sizeof(double),
+                             cudaMemcpyDeviceToHost, so)) != cudaSuccess) { fail(e, "cudaMemcpyAsync(D2H)"); break; }
+    if ((e = cudaEventRecord(ev_out[k], so)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
+  }
+  // drain, then release staging in stream order on sc
+  cudaError_t e1 = cudaStreamSynchronize(si), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(so);
+  if (rc == JWC_OK) {
+    if (e1 != cudaSuccess) fail(e1, "cudaStreamSynchronize(copy_in)");
+    else if (e2 != cudaSuccess) fail(e2, "cudaStreamSynchronize(compute)");
+    else if (e3 != cudaSuccess) fail(e3, "cudaStreamSynchronize(copy_out)");
+  }
+  for (int i = 0; i < 2; i++) {
+    if (d_in[i]) cudaFreeAsync(d_in[i], sc);
+    if (d_out[i]) cudaFreeAsync(d_out[i], sc);
+    if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+    if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+    if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+  }
+  if (ev_alloc) cudaEventDestroy(ev_alloc);
+  return rc;
+}
+
+int run_host(jwc_ctx* ctx, Op op, const double* in, double* out, int64_t batch, int64_t n, int levels,
+             const double* f0, const double* f1, int L, unsigned flags) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  int rc = validate(op, in, out, batch, n, levels, f0, f1, L);
+  if (rc != JWC_OK) return rc;
+  FilterPair fp;
+  load_filters(fp, f0, f1, L);
+  int64_t in_per, out_per;
+  io_sizes(op, n, levels, &in_per, &out_per);
+  const int nd = (int)ctx->slots.size();
+  if (nd == 1 || batch < 2) return run_host_slot(ctx, 0, op, in, out, batch, n, levels, fp, L, flags);
+  // shard by signal: contiguous blocks, no data-path collective
+  std::vector<std::thread> th;
+  std::vector<int> rcs(nd, JWC_OK);
+  std::vector<std::string> errs(nd);
+  for (int s = 0; s < nd; s++) {
+    const int64_t b0 = batch * s / nd, b1 = batch * (s + 1) / nd;
+    th.emplace_back([=, &rcs, &errs, &fp]() {
+      rcs[s] = run_host_slot(ctx, s, op, in + b0 * in_per, out + b0 * out_per, b1 - b0, n, levels, fp, L, flags);
+      if (rcs[s] != JWC_OK) errs[s] = g_err;
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int s = 0; s < nd; s++)
+    if (rcs[s] != JWC_OK) {
+      set_error("device slot %d: %s", s, errs[s].c_str());
+      return rcs[s];
+    }
+  return JWC_OK;
+}
+
+int run_dev(jwc_ctx* ctx, int slot, void* stream, Op op, const double* d_in, double* d_out, int64_t batch, int64_t n,
+            int levels, const double* f0, const double* f1, int L, unsigned flags) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  JWC_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), "device slot %d out of range", slot);
+  int rc = validate(op, d_in, d_out, batch, n, levels, f0, f1, L);
+  if (rc != JWC_OK) return rc;
+  FilterPair fp;
+  load_filters(fp, f0, f1, L);
+  const DeviceSlot& dev = ctx->slots[slot];
+  DeviceGuard guard(dev.ordinal);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", dev.ordinal); return JWC_ERR_CUDA; }
+  cudaStream_t st = stream ? (cudaStream_t)stream : dev.stream;
+  return run_device(ctx, dev, st, op, d_in, d_out, batch, n, levels, fp, L, flags);
+}
+
+}  // namespace
+}  // namespace jwc
+
+using namespace jwc;
+
+extern "C" {
+
+JWC_API const char* jwc_last_error(void) { return g_err; }
+JWC_API const char* jwc_version(void) { return "jwavecuda 0.1 (sm_100a)"; }
+
+JWC_API jwc_ctx* jwc_create(const int* devices, int ndev) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    (void)cudaGetLastError();
+    set_error("no CUDA device available (libjwavecuda has no CPU fallback)");
+    return nullptr;
+  }
+  std::vector<int> ords;
+  if (devices == nullptr || ndev <= 0) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    ords.push_back(cur);
+  } else {
+    for (int i = 0; i < ndev; i++) {
+      if (devices[i] < 0 || devices[i] >= count) {
+        set_error("device ordinal %d out of range (0..%d)", devices[i], count - 1);
+        return nullptr;
+      }
+      ords.push_back(devices[i]);
+    }
+  }
+  jwc_ctx* ctx = new jwc_ctx();
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int o : ords) {
+    DeviceSlot s;
+    s.ordinal = o;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(o) != cudaSuccess || cudaGetDeviceProperties(&prop, o) != cudaSuccess) {
+      set_error("cannot open device %d: %s", o, cudaGetErrorString(cudaGetLastError()));
+      cudaSetDevice(prev);
+      jwc_destroy(ctx);
+      return nullptr;
+    }
+    if (prop.major < 10) {
+      set_error("device %d is sm_%d%d; libjwavecuda is built for sm_100a (B200) only", o, prop.major, prop.minor);
+      cudaSetDevice(prev);
+      jwc_destroy(ctx);
+      return nullptr;
+    }
+    s.sm_count = prop.multiProcessorCount;
+    s.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cannot create streams on device %d: %s", o, cudaGetErrorString(cudaGetLastError()));
+      cudaSetDevice(prev);
+      jwc_destroy(ctx);
+      return nullptr;
+    }
+    // keep freed scratch in the pool instead of returning it to the driver after every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, o) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    ctx->slots.push_back(s);
+  }
+  cudaSetDevice(prev);
+  return ctx;
+}
+
+JWC_API void jwc_destroy(jwc_ctx* ctx) {
+  if (!ctx) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (auto& s : ctx->slots) {
+    cudaSetDevice(s.ordinal);
+    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    if (s.copy_in) { cudaStreamSynchronize(s.copy_in); cudaStreamDestroy(s.copy_in); }
+    if (s.copy_out) { cudaStreamSynchronize(s.copy_out); cudaStreamDestroy(s.copy_out); }
+  }
+  cudaSetDevice(prev);
+  delete ctx;
+}
+
+JWC_API int jwc_num_devices(const jwc_ctx* ctx) { return ctx ? (int)ctx->slots.size() : 0; }
+JWC_API int jwc_device_ordinal(const jwc_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return -1;
+  return ctx->slots[slot].ordinal;
+}
+JWC_API uint64_t jwc_launch_count(const jwc_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+static int* tuning_field(jwc_ctx* ctx, const char* key) {
+  if (!ctx || !key) return nullptr;
+  Tuning& t = ctx->tune;
+  if (!strcmp(key, "modwt_tile")) return &t.modwt_tile;
+  if (!strcmp(key, "modwt_threads")) return &t.modwt_threads;
+  if (!strcmp(key, "modwt_group")) return &t.modwt_group;
+  if (!strcmp(key, "dwt_tile")) return &t.dwt_tile;
+  if (!strcmp(key, "dwt_threads")) return &t.dwt_threads;
+  if (!strcmp(key, "dwt_group")) return &t.dwt_group;
+  if (!strcmp(key, "h2d_chunk_mb")) return &t.h2d_chunk_mb;
+  if (!strcmp(key, "force_generic")) return &t.force_generic;
+  return nullptr;
+}
+JWC_API int jwc_set_tuning(jwc_ctx* ctx, const char* key, int value) {
+  int* f = tuning_field(ctx, key);
+  if (!f) { set_error("unknown tuning key '%s'", key ? key : "(null)"); return JWC_ERR_INVALID; }
+  *f = value;
+  return JWC_OK;
+}
+JWC_API int jwc_get_tuning(const jwc_ctx* ctx, const char* key, int* value) {
+  int* f = tuning_field(const_cast<jwc_ctx*>(ctx), key);
+  if (!f || !value) { set_error("unknown tuning key '%s'", key ? key : "(null)"); return JWC_ERR_INVALID; }
+  *value = *f;
+  return JWC_OK;
+}
+
+JWC_API void* jwc_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+JWC_API void jwc_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+JWC_API void* jwc_alloc_device(jwc_ctx* ctx, int slot, size_t bytes) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) { set_error("bad context/slot"); return nullptr; }
+  DeviceGuard guard(ctx->slots[slot].ordinal);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+JWC_API void jwc_free_device(jwc_ctx* ctx, int slot, void* p) {
+  if (!ctx || !p || slot < 0 || slot >= (int)ctx->slots.size()) return;
+  DeviceGuard guard(ctx->slots[slot].ordinal);
+  cudaFree(p);
+}
+JWC_API int jwc_copy_to_device(jwc_ctx* ctx, int slot, void* dst, const void* src, size_t bytes) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) { set_error("bad context/slot"); return JWC_ERR_INVALID; }
+  DeviceGuard guard(ctx->slots[slot].ordinal);
+  cudaStream_t st = ctx->slots[slot].stream;
+  JWC_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+  JWC_CUDA_CHECK(cudaStreamSynchronize(st));
+  return JWC_OK;
+}
+JWC_API int jwc_copy_to_host(jwc_ctx* ctx, int slot, void* dst, const void* src, size_t bytes) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) { set_error("bad context/slot"); return JWC_ERR_INVALID; }
+  DeviceGuard guard(ctx->slots[slot].ordinal);
+  cudaStream_t st = ctx->slots[slot].stream;
+  JWC_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+  JWC_CUDA_CHECK(cudaStreamSynchronize(st));
+  return JWC_OK;
+}
+JWC_API int jwc_synchronize(jwc_ctx* ctx) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  for (auto& s : ctx->slots) {
+    DeviceGuard guard(s.ordinal);
+    JWC_CUDA_CHECK(cudaStreamSynchronize(s.copy_in));
+    JWC_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    JWC_CUDA_CHECK(cudaStreamSynchronize(s.copy_out));
+  }
+  return JWC_OK;
+}
+
+#define JWC_DEFINE(name, OP)                                                                                        \
+  JWC_API int jwc_##name(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, int levels,         \
+                         const double* f0, const double* f1, int L, unsigned flags) {                               \
+    return run_host(ctx, OP, in, out, batch, n, levels, f0, f1, L, flags);                                          \
+  }                                                                                                                 \
+  JWC_API int jwc_##name##_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,             \
+                               int64_t batch, int64_t n, int levels, const double* f0, const double* f1, int L,     \
+                               unsigned flags) {                                                                    \
+    return run_dev(ctx, slot, stream, OP, d_in, d_out, batch, n, levels, f0, f1, L, flags);                         \
+  }
+
+JWC_DEFINE(modwt_forward, Op::ModwtFwd)
+JWC_DEFINE(modwt_inverse, Op::ModwtInv)
+JWC_DEFINE(fwt_forward, Op::FwtFwd)
+JWC_DEFINE(fwt_inverse, Op::FwtInv)
+JWC_DEFINE(wpt_forward, Op::WptFwd)
+JWC_DEFINE(wpt_inverse, Op::WptInv)
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// jwc_internal.cuh -- shared declarations of libjwavecuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/jwavecuda.h"
+
+namespace jwc {
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define JWC_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      jwc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return JWC_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+#define JWC_REQUIRE(cond, ...)       \
+  do {                               \
+    if (!(cond)) {                   \
+      jwc::set_error(__VA_ARGS__);   \
+      return JWC_ERR_INVALID;        \
+    }                                \
+  } while (0)
+
+// ---- filters travel as kernel parameters (constant bank): statically indexed taps become
+//      immediate constant operands of DFMA, dynamically indexed ones an LDC.
+struct FilterPair {
+  double f0[JWC_MAX_TAPS];  // MODWT: g~   FWT/WPT: scaling (low-pass) filter of the direction
+  double f1[JWC_MAX_TAPS];  // MODWT: h~   FWT/WPT: wavelet (high-pass) filter of the direction
+};
+
+struct Tuning {
+  int modwt_tile = 0;       // 0 = auto
+  int modwt_threads = 0;
+  int modwt_group = 0;      // max levels fused per pass, 0 = auto
+  int dwt_tile = 0;
+  int dwt_threads = 0;
+  int dwt_group = 0;
+  int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
+  int force_generic = 0;
+};
+
+struct DeviceSlot {
+  int ordinal = 0;
+  cudaStream_t stream = nullptr;      // compute stream of the slot (used when the caller passes NULL)
+  cudaStream_t copy_in = nullptr;     // host-pipeline H2D stream
+  cudaStream_t copy_out = nullptr;    // host-pipeline D2H stream
+  int sm_count = 0;
+  int max_smem_optin = 0;
+};
+
+}  // namespace jwc
+
+struct jwc_ctx {
+  std::vector<jwc::DeviceSlot> slots;
+  std::atomic<uint64_t> launches{0};
+  jwc::Tuning tune;
+  std::mutex mu;
+};
+
+namespace jwc {
+
+// Stream-ordered scratch: cudaMallocAsync/cudaFreeAsync on the call's stream, so concurrent calls on one
+// context never share workspace (re-entrancy requirement of SURVEY.md section 8b "threading").
+struct Scratch {
+  cudaStream_t stream;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  double* get(size_t n_doubles) {
+    void* p = nullptr;
+    if (n_doubles == 0) n_doubles = 1;
+    if (cudaMallocAsync(&p, n_doubles * sizeof(double), stream) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    ptrs.push_back(p);
+    return static_cast<double*>(p);
+  }
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, stream);
+  }
+};
+
+// ---- generic (any shape, one level per launch) kernels: jwc_generic.cu ---------------------------------
+int generic_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
+                          int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact);
+int generic_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
+                          int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact);
+// tree = false: FWT (only the length-h prefix is transformed each level); tree = true: WPT (every block).
+int generic_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact);
+int generic_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact);
+
+// ---- fused tile kernels: jwc_modwt_fast.cu / jwc_dwt_fast.cu --------------------------------------------
+// each returns JWC_ERR_UNSUPPORTED (without setting an error) when the shape is outside its fast path.
+int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
+                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
+                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree);
+int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree);
+
+inline void count_launch(jwc_ctx* ctx, uint64_t k = 1) { ctx->launches.fetch_add(k, std::memory_order_relaxed); }
+
+template <bool EXACT>
+__device__ __forceinline__ double mac(double acc, double a, double b) {
+  if (EXACT) return __dadd_rn(acc, __dmul_rn(a, b));  // two roundings, like the JVM
+  return fma(a, b, acc);
+}
+
+}  // namespace jwc

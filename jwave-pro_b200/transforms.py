@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference's transform classes for the three GPU transforms.
+
+The reference is Java and this image has no JDK, so the drop-in classes exist twice: as Java sources that bind
+the C ABI through Panama FFM (java/jwave/transforms/cuda/*.java, not compilable here) and as this Python mirror
+with the same class / method names, argument meaning, validation order and error messages, so that the tests
+in tests/ read like the reference's own JUnit tests.  Both sit on the same C ABI (include/jwavecuda.h); neither
+has a CPU path.
+
+Reference (relative to /root/reference/src/main/java/jwave/transforms/):
+  BasicTransform.java:99-157,671-697        abstract 1-D API, isBinary, calcExponent
+  WaveletTransform.java:77-182              full-depth defaults, decompose / recompose
+  FastWaveletTransform.java:71-153          CudaFastWaveletTransform
+  WaveletPacketTransform.java:73-191        CudaWaveletPacketTransform
+  MODWTTransform.java:256-443,452-606,854-912   CudaMODWTTransform
+"""
+import ctypes
+import math
+import threading
+
+import numpy as np
+
+from . import _native
+from .exceptions import IllegalArgumentException, JWaveFailure
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+class BasicTransform:
+    """transforms/BasicTransform.java:42 -- only the 1-D surface the hot path touches."""
+
+    _name = None
+
+    def getName(self):
+        return self._name
+
+    @staticmethod
+    def isBinary(number):
+        # tools/MathToolKit.java:185
+        return number > 0 and (number & (number - 1)) == 0
+
+    def calcExponent(self, number):
+        # BasicTransform.java:687-697 + MathToolKit.getExponent :202 ((int)(ln f / ln 2), exact for 2^0..2^30)
+        if not self.isBinary(number):
+            raise JWaveFailure("BasicTransform#calcExponent - given number is not binary: "
+                               "2^p | pEN .. = 1, 2, 4, 8, 16, 32, .. ")
+        return int(number).bit_length() - 1
+
+
+class WaveletTransform(BasicTransform):
+    """transforms/WaveletTransform.java:42"""
+
+    def __init__(self, wavelet, context=None):
+        self._wavelet = wavelet
+        self._ctx = context
+
+    def getWavelet(self):
+        return self._wavelet
+
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = _native.default_context()
+        return self._ctx
+
+    def _call(self, fn_name, src, dst, batch, n, levels, f0, f1, flags):
+        lib = _native.load()
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        rc = getattr(lib, fn_name)(self._context().handle, src.ctypes.data, dst.ctypes.data, batch, n, levels,
+                                   _ptr(f0), _ptr(f1), len(f0), flags)
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (fn_name, rc, _native.last_error()))
+
+    def _call_dev(self, fn_name, d_src, d_dst, batch, n, levels, f0, f1, flags, stream=0, slot=0):
+        """Device-resident variant: d_src / d_dst are raw device addresses (e.g. torch.Tensor.data_ptr())."""
+        lib = _native.load()
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        rc = getattr(lib, fn_name + "_dev")(self._context().handle, slot, ctypes.c_void_p(stream or None),
+                                            ctypes.c_void_p(d_src), ctypes.c_void_p(d_dst), batch, n, levels,
+                                            _ptr(f0), _ptr(f1), len(f0), flags)
+        if rc != 0:
+            raise RuntimeError("%s_dev failed (%d): %s" % (fn_name, rc, _native.last_error()))
+
+    # ---- full-depth defaults (WaveletTransform.java:77-112) --------------------------------------------------
+    def forward(self, arrTime, level=None):
+        if level is None:
+            if not self.isBinary(len(arrTime)):
+                raise JWaveFailure("WaveletTransform#forward - given array length is not 2^p | p E N ... = "
+                                   "1, 2, 4, 8, 16, 32, .. please use the Ancient Egyptian Decomposition for any "
+                                   "other array length!")
+            level = self.calcExponent(len(arrTime))
+        return self._forward_level(arrTime, level)
+
+    def reverse(self, arrHilb, level=None):
+        if level is None:
+            if not self.isBinary(len(arrHilb)):
+                raise JWaveFailure("WaveletTransform#reverse - given array length is not 2^p | p E N ... = "
+                                   "1, 2, 4, 8, 16, 32, .. please use the Ancient Egyptian Decomposition for any "
+                                   "other array length!")
+            level = self.calcExponent(len(arrHilb))
+        return self._reverse_level(arrHilb, level)
+
+    def decompose(self, arrTime):
+        # WaveletTransform.java:136-147
+        length = len(arrTime)
+        levels = self.calcExponent(length)
+        return np.stack([self.forward(arrTime, p) for p in range(levels + 1)])
+
+    def recompose(self, matDeComp, level):
+        # WaveletTransform.java:173-182
+        if level < 0 or level >= len(matDeComp):
+            raise JWaveFailure("WaveletTransform#recompose - given level is out of range")
+        return self.reverse(matDeComp[level], level)
+
+
+class _CudaPyramidBase(WaveletTransform):
+    """Shared by FWT and WPT: same validation (FastWaveletTransform.java:74-83, WaveletPacketTransform.java:76-84)."""
+
+    _fn = None      # "jwc_fwt" / "jwc_wpt"
+    _cls = None     # class name used in the reference's messages
+
+    def _check(self, length, level, direction):
+        if not self.isBinary(length):
+            raise JWaveFailure("%s#%s - given array length is not 2^p | p E N ... = 1, 2, 4, 8, 16, 32, .. "
+                               "please use the Ancient Egyptian Decomposition for any other array length!"
+                               % (self._cls, direction))
+        if level < 0 or level > self.calcExponent(length):
+            raise JWaveFailure("%s#%s - given level is out of range for given array" % (self._cls, direction))
+
+    def _forward_level(self, arrTime, level, flags=0):
+        x = _as_f64(arrTime)
+        self._check(len(x), level, "forward")
+        out = np.empty_like(x)
+        self._call(self._fn + "_forward", x, out, 1, len(x), level, self._wavelet.getScalingDeComposition(),
+                   self._wavelet.getWaveletDeComposition(), flags)
+        return out
+
+    def _reverse_level(self, arrHilb, level, flags=0):
+        c = _as_f64(arrHilb)
+        self._check(len(c), level, "reverse")
+        out = np.empty_like(c)
+        self._call(self._fn + "_inverse", c, out, 1, len(c), level, self._wavelet.getScalingReConstruction(),
+                   self._wavelet.getWaveletReConstruction(), flags)
+        return out
+
+    # ---- batched entry points (rows = independent signals), host buffers -------------------------------------
+    def forwardBatch(self, matTime, level=None, flags=0, out=None):
+        X = _as_f64(matTime)
+        B, N = X.shape
+        if level is None:
+            level = self.calcExponent(N)
+        self._check(N, level, "forward")
+        out = np.empty_like(X) if out is None else out
+        self._call(self._fn + "_forward", X, out, B, N, level, self._wavelet.getScalingDeComposition(),
+                   self._wavelet.getWaveletDeComposition(), flags)
+        return out
+
+    def reverseBatch(self, matHilb, level=None, flags=0, out=None):
+        C = _as_f64(matHilb)
+        B, N = C.shape
+        if level is None:
+            level = self.calcExponent(N)
+        self._check(N, level, "reverse")
+        out = np.empty_like(C) if out is None else out
+        self._call(self._fn + "_inverse", C, out, B, N, level, self._wavelet.getScalingReConstruction(),
+                   self._wavelet.getWaveletReConstruction(), flags)
+        return out
+
+    # ---- device-resident (benchmarks, pipelines that keep data in HBM) ------------------------------------
+    def forwardDevice(self, d_in, d_out, batch, n, level, stream=0, flags=0, slot=0):
+        self._check(n, level, "forward")
+        self._call_dev(self._fn + "_forward", d_in, d_out, batch, n, level, self._wavelet.getScalingDeComposition(),
+                       self._wavelet.getWaveletDeComposition(), flags, stream, slot)
+
+    def reverseDevice(self, d_in, d_out, batch, n, level, stream=0, flags=0, slot=0):
+        self._check(n, level, "reverse")
+        self._call_dev(self._fn + "_inverse", d_in, d_out, batch, n, level, self._wavelet.getScalingReConstruction(),
+                       self._wavelet.getWaveletReConstruction(), flags, stream, slot)
+
+
+class CudaFastWaveletTransform(_CudaPyramidBase):
+    """Drop-in for transforms/FastWaveletTransform.java (same _name, :52)."""
+
+    _fn = "jwc_fwt"
+    _cls = "FastWaveletTransform"
+
+    def __init__(self, wavelet, context=None):
+        super().__init__(wavelet, context)
+        self._name = "Fast Wavelet Transform"
+
+
+class CudaWaveletPacketTransform(_CudaPyramidBase):
+    """Drop-in for transforms/WaveletPacketTransform.java (same _name, :54)."""
+
+    _fn = "jwc_wpt"
+    _cls = "WaveletPacketTransform"
+
+    def __init__(self, wavelet, context=None):
+        super().__init__(wavelet, context)
+        self._name = "Wavelet Packet Transform"
+
+
+class CudaMODWTTransform(WaveletTransform):
+    """Drop-in for transforms/MODWTTransform.java."""
+
+    MAX_DECOMPOSITION_LEVEL = 13  # MODWTTransform.java:111
+
+    def __init__(self, wavelet, context=None):
+        super().__init__(wavelet, context)
+        self._name = "MODWT"
+        self._lock = threading.Lock()
+        self._g = None
+        self._h = None
+
+    @staticmethod
+    def getMaxDecompositionLevel():
+        return CudaMODWTTransform.MAX_DECOMPOSITION_LEVEL
+
+    # ---- filter preparation (MODWTTransform.java:452-484, normalize :599-606) --------------------------------
+    def initializeFilterCache(self):
+        if self._g is None:
+            with self._lock:
+                if self._g is None:
+                    def normalize(f):
+                        f = np.array(f, dtype=np.float64)
+                        energy = 0.0
+                        for c in f:
+                            energy += float(c) * float(c)
+                        norm = math.sqrt(energy)
+                        if norm > 1e-12:
+                            f = f / norm
+                        return f
+                    sf = math.sqrt(2.0)
+                    h = normalize(self._wavelet.getWaveletDeComposition()) / sf
+                    self._g = normalize(self._wavelet.getScalingDeComposition()) / sf
+                    self._h = h
+
+    def clearFilterCache(self):
+        # MODWTTransform.java:556-569: the GPU path keeps no per-level upsampled filters (the stride is implicit in
+        # the kernels); only the two base filters are cached.
+        with self._lock:
+            self._g = None
+            self._h = None
+
+    def precomputeFilters(self, maxLevel):
+        # MODWTTransform.java:578-590
+        if maxLevel > self.MAX_DECOMPOSITION_LEVEL:
+            raise IllegalArgumentException("MODWTTransform#precomputeFilters - maximum supported decomposition level "
+                                           "is %d, requested: %d" % (self.MAX_DECOMPOSITION_LEVEL, maxLevel))
+        self.initializeFilterCache()
+
+    def _filters(self):
+        self.initializeFilterCache()
+        g, h = self._g, self._h
+        if g is None or h is None:      # cleared by another thread between the two statements
+            return self._filters()
+        return g, h
+
+    # ---- forwardMODWT / inverseMODWT (MODWTTransform.java:256-306, 337-375) ----------------------------------
+    def _check_levels(self, maxLevel, N):
+        if maxLevel < 1:
+            raise IllegalArgumentException("MODWTTransform#forwardMODWT - decomposition level must be at least 1, "
+                                           "requested: %d" % maxLevel)
+        if maxLevel > self.MAX_DECOMPOSITION_LEVEL:
+            raise IllegalArgumentException("MODWTTransform#forwardMODWT - maximum supported decomposition level is "
+                                           "%d, requested: %d" % (self.MAX_DECOMPOSITION_LEVEL, maxLevel))
+        if N is None or N == 0:
+            return False
+        theoretical = int(N).bit_length() - 1
+        if maxLevel > theoretical:
+            raise IllegalArgumentException("Decomposition level %d exceeds theoretical limit %d for signal length %d"
+                                           % (maxLevel, theoretical, N))
+        return True
+
+    def forwardMODWT(self, data, maxLevel, flags=0):
+        N = 0 if data is None else len(data)
+        if not self._check_levels(maxLevel, N):
+            return [np.empty(0) for _ in range(maxLevel + 1)]
+        x = _as_f64(data)
+        g, h = self._filters()
+        out = np.empty((maxLevel + 1, N))
+        self._call("jwc_modwt_forward", x, out, 1, N, maxLevel, g, h, flags)
+        return out
+
+    def inverseMODWT(self, coefficients, flags=0):
+        if coefficients is None or len(coefficients) == 0:
+            return np.empty(0)
+        maxLevel = len(coefficients) - 1
+        if maxLevel <= 0:
+            return np.empty(0)
+        c = _as_f64(coefficients)
+        N = c.shape[1]
+        if N == 0:
+            return np.empty(0)
+        g, h = self._filters()
+        x = np.empty(N)
+        self._call("jwc_modwt_inverse", c, x, 1, N, maxLevel, g, h, flags)
+        return x
+
+    # ---- flattened 1-D interface (MODWTTransform.java:389-443, 854-912) --------------------------------------
+    def forward(self, arrTime, level=None):
+        if arrTime is None or len(arrTime) == 0:
+            return np.empty(0)
+        if level is None:
+            level = self.calcExponent(len(arrTime))       # :858 (throws JWaveFailure for non-2^p)
+            return self.forwardMODWT(arrTime, level).reshape(-1)
+        if not self.isBinary(len(arrTime)):
+            raise JWaveFailure("MODWTTransform#forward - given array length is not 2^p | p E N ... = "
+                               "1, 2, 4, 8, 16, 32, .. ")
+        maxLevel = self.calcExponent(len(arrTime))
+        if level < 0 or level > maxLevel:
+            raise JWaveFailure("MODWTTransform#forward - given level is out of range for given array")
+        if level > self.MAX_DECOMPOSITION_LEVEL:
+            raise JWaveFailure("MODWTTransform#forward - maximum supported decomposition level is %d, requested: %d"
+                               % (self.MAX_DECOMPOSITION_LEVEL, level))
+        return self.forwardMODWT(arrTime, level).reshape(-1)
+
+    def reverse(self, arrHilb, level=None):
+        if arrHilb is None or len(arrHilb) == 0:
+            return np.empty(0)
+        total = len(arrHilb)
+        if level is None:
+            # :888-897 -- smallest 2^p N with total % N == 0 and total/N - 1 <= log2 N
+            N = 0
+            levels = 0
+            for testN in range(1, total + 1):
+                if total % testN == 0:
+                    testLevels = total // testN - 1
+                    if testLevels >= 0 and self.isBinary(testN) and testLevels <= self.calcExponent(testN):
+                        N, levels = testN, testLevels
+                        break
+            if N == 0:
+                raise JWaveFailure("MODWTTransform#reverse - Invalid flattened coefficient array length. "
+                                   "Cannot determine original signal dimensions.")
+        else:
+            levels = level
+            N = total // (level + 1)
+            if not self.isBinary(N):
+                raise JWaveFailure("MODWTTransform#reverse - Invalid coefficient array for given level")
+            if total != N * (level + 1):
+                raise JWaveFailure("MODWTTransform#reverse - Coefficient array length does not match expected size "
+                                   "for given level")
+        return self.inverseMODWT(_as_f64(arrHilb).reshape(levels + 1, N))
+
+    # ---- batched host-buffer entry points ------------------------------------------------------------------
+    def forwardMODWTBatch(self, matTime, maxLevel, flags=0, out=None):
+        X = _as_f64(matTime)
+        B, N = X.shape
+        self._check_levels(maxLevel, N)
+        g, h = self._filters()
+        out = np.empty((B, maxLevel + 1, N)) if out is None else out
+        self._call("jwc_modwt_forward", X, out, B, N, maxLevel, g, h, flags)
+        return out
+
+    def inverseMODWTBatch(self, coeffs, flags=0, out=None):
+        C = _as_f64(coeffs)
+        B, J1, N = C.shape
+        g, h = self._filters()
+        out = np.empty((B, N)) if out is None else out
+        self._call("jwc_modwt_inverse", C, out, B, N, J1 - 1, g, h, flags)
+        return out
+
+    # ---- device-resident ----------------------------------------------------------------------------------------
+    def forwardMODWTDevice(self, d_x, d_coeffs, batch, n, maxLevel, stream=0, flags=0, slot=0):
+        self._check_levels(maxLevel, n)
+        g, h = self._filters()
+        self._call_dev("jwc_modwt_forward", d_x, d_coeffs, batch, n, maxLevel, g, h, flags, stream, slot)
+
+    def inverseMODWTDevice(self, d_coeffs, d_x, batch, n, maxLevel, stream=0, flags=0, slot=0):
+        g, h = self._filters()
+        self._call_dev("jwc_modwt_inverse", d_coeffs, d_x, batch, n, maxLevel, g, h, flags, stream, slot)

@@ -1,0 +1,157 @@
+"""oracle/c_oracle.py -- TEST INFRASTRUCTURE: ctypes loader for oracle/libjwave_oracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libjwave_oracle.so")
+_lib = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "jwave_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B" if force else "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.jwo_batch.argtypes = [ctypes.c_int, _dp, _dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                   _dp, _dp, ctypes.c_int, ctypes.c_int]
+        _lib.jwo_batch.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def build_orthonormal(scaling):
+    s = _c(scaling)
+    w = np.empty_like(s)
+    lib().jwo_build_orthonormal(_p(s), ctypes.c_int(len(s)), _p(w))
+    return w
+
+
+def modwt_filters(scaling, wavelet):
+    s, w = _c(scaling), _c(wavelet)
+    g, h = np.empty_like(s), np.empty_like(s)
+    lib().jwo_modwt_filters(_p(s), _p(w), ctypes.c_int(len(s)), _p(g), _p(h))
+    return g, h
+
+
+def upsample(f, level):
+    f = _c(f)
+    M = (len(f) - 1) * (1 << max(level - 1, 0)) + 1
+    out = np.empty(M)
+    n = lib().jwo_upsample(_p(f), ctypes.c_int(len(f)), ctypes.c_int(level), _p(out))
+    return out[:n]
+
+
+def circular_convolve(x, f, adjoint=False):
+    x, f = _c(x), _c(f)
+    out = np.empty_like(x)
+    fn = lib().jwo_circular_convolve_adjoint if adjoint else lib().jwo_circular_convolve
+    fn(_p(x), ctypes.c_int(len(x)), _p(f), ctypes.c_int(len(f)), _p(out))
+    return out
+
+
+def modwt_forward(x, J, g, h, dense=False, fft=False):
+    x, g, h = _c(x), _c(g), _c(h)
+    N = len(x)
+    out = np.empty((J + 1, N))
+    if fft:
+        rc = lib().jwo_modwt_forward_fft(_p(x), ctypes.c_int(N), ctypes.c_int(J), _p(g), _p(h), ctypes.c_int(len(g)), _p(out))
+    else:
+        rc = lib().jwo_modwt_forward(_p(x), ctypes.c_int(N), ctypes.c_int(J), _p(g), _p(h), ctypes.c_int(len(g)), _p(out),
+                                     ctypes.c_int(1 if dense else 0))
+    assert rc == 0, rc
+    return out
+
+
+def modwt_inverse(coeffs, g, h, dense=False, fft=False):
+    c, g, h = _c(coeffs), _c(g), _c(h)
+    J, N = c.shape[0] - 1, c.shape[1]
+    x = np.empty(N)
+    if fft:
+        rc = lib().jwo_modwt_inverse_fft(_p(c), ctypes.c_int(N), ctypes.c_int(J), _p(g), _p(h), ctypes.c_int(len(g)), _p(x))
+    else:
+        rc = lib().jwo_modwt_inverse(_p(c), ctypes.c_int(N), ctypes.c_int(J), _p(g), _p(h), ctypes.c_int(len(g)), _p(x),
+                                     ctypes.c_int(1 if dense else 0))
+    assert rc == 0, rc
+    return x
+
+
+def wavelet_forward(x, length, s, w):
+    x, s, w = _c(x), _c(s), _c(w)
+    out = np.empty(length)
+    lib().jwo_wavelet_forward(_p(x), ctypes.c_int(length), _p(s), _p(w), ctypes.c_int(len(s)), _p(out))
+    return out
+
+
+def wavelet_reverse(c, length, sr, wr):
+    c, sr, wr = _c(c), _c(sr), _c(wr)
+    out = np.empty(length)
+    lib().jwo_wavelet_reverse(_p(c), ctypes.c_int(length), _p(sr), _p(wr), ctypes.c_int(len(sr)), _p(out))
+    return out
+
+
+def _tree(fn, x, level, f0, f1):
+    x, f0, f1 = _c(x), _c(f0), _c(f1)
+    out = np.empty_like(x)
+    rc = fn(_p(x), ctypes.c_int(len(x)), ctypes.c_int(level), _p(f0), _p(f1), ctypes.c_int(len(f0)), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+def fwt_forward(x, level, s, w):
+    return _tree(lib().jwo_fwt_forward, x, level, s, w)
+
+
+def fwt_reverse(c, level, sr, wr):
+    return _tree(lib().jwo_fwt_reverse, c, level, sr, wr)
+
+
+def wpt_forward(x, level, s, w):
+    return _tree(lib().jwo_wpt_forward, x, level, s, w)
+
+
+def wpt_reverse(c, level, sr, wr):
+    return _tree(lib().jwo_wpt_reverse, c, level, sr, wr)
+
+
+OPS = {"modwt_fwd": 0, "modwt_inv": 1, "modwt_fwd_fft": 2, "modwt_inv_fft": 3,
+       "fwt_fwd": 4, "fwt_rev": 5, "wpt_fwd": 6, "wpt_rev": 7}
+
+
+def batch(op, x, level, f0, f1, nthreads=1):
+    """x: (batch, N) (or (batch, level+1, N) for MODWT inverse). Returns the batched result."""
+    x, f0, f1 = _c(x), _c(f0), _c(f1)
+    code = OPS[op]
+    if code in (1, 3):
+        B, N = x.shape[0], x.shape[2]
+        out = np.empty((B, N))
+    elif code in (0, 2):
+        B, N = x.shape
+        out = np.empty((B, level + 1, N))
+    else:
+        B, N = x.shape
+        out = np.empty((B, N))
+    rc = lib().jwo_batch(code, _p(x), _p(out), B, N, level, _p(f0), _p(f1), len(f0), nthreads)
+    assert rc == 0, rc
+    return out

@@ -1,0 +1,179 @@
+"""CPU-only: pin the oracle (C and numpy restatements) to the reference's own known-answer tests."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import splitmix_uniform
+from oracle import np_oracle
+
+
+@pytest.fixture(scope="module")
+def W(jw):
+    return jw.wavelets
+
+
+def test_table_checksums(W):
+    # (sum, sum of squares) of the reference tables
+    exp = {"Daubechies4": (1.4142135623730947, 0.99999999999906619),
+           "Daubechies8": (1.4142135623730954, 1.0000000000022773),
+           "Daubechies20": (1.4142135623730949, 0.99999999999757472),
+           "Symlet8": (1.4142135623730951, 0.99999999999993094)}
+    for cls, (s, s2) in exp.items():
+        t = W.create(cls).getScalingDeComposition()
+        assert math.fsum(t) == pytest.approx(s, abs=2e-16)
+        assert math.fsum(v * v for v in t) == pytest.approx(s2, abs=2e-16)
+    d4 = W.Daubechies4().getScalingDeComposition()
+    assert d4[0] == -0.010597401784997278 and d4[-1] == 0.23037781330885523
+    d20 = W.Daubechies20().getScalingDeComposition()
+    assert d20[0] == -2.998836489615753e-10 and d20[-1] == 0.0007799536136659112
+    assert len(W.ALL_CLASSES) == 44
+
+
+def test_haar_filters_fixture(W, kats, oracle):
+    h = W.Haar1()
+    k = kats["haar_filters"]
+    np.testing.assert_allclose(h.getScalingDeComposition(), k["dec_lo"], atol=1e-10)
+    np.testing.assert_allclose(h.getWaveletDeComposition(), k["dec_hi"], atol=1e-10)
+    # (filter_haar_rec_*.txt exist but no reference test loads them; rec_hi there follows another sign convention
+    #  than Haar1.java:61-68, whose reconstruction filters are copies of the decomposition filters.)
+    np.testing.assert_allclose(h.getScalingReConstruction(), k["rec_lo"], atol=1e-10)
+    assert np.array_equal(h.getWaveletReConstruction(), h.getWaveletDeComposition())
+    # the three derived filters follow Wavelet._buildOrthonormalSpace in all restatements
+    for cls in W.ALL_CLASSES:
+        w = W.create(cls)
+        s = w.getScalingDeComposition()
+        assert np.array_equal(oracle.build_orthonormal(s), w.getWaveletDeComposition())
+        assert np.array_equal(np_oracle.build_orthonormal(s), w.getWaveletDeComposition())
+
+
+def test_modwt_haar_known_values(W, kats, oracle):
+    k = kats["modwt_haar_level1"]
+    h = W.Haar1()
+    for mod in (oracle, np_oracle):
+        g, hh = mod.modwt_filters(h.getScalingDeComposition(), h.getWaveletDeComposition())
+        np.testing.assert_allclose(g, [0.5, 0.5], atol=1e-15)
+        np.testing.assert_allclose(hh, [0.5, -0.5], atol=1e-15)
+        c = mod.modwt_forward(np.array(k["input"]), 1, g, hh)
+        np.testing.assert_allclose(c[0], k["D1"], atol=1e-9)
+        np.testing.assert_allclose(c[1], k["A1"], atol=1e-9)
+    c = oracle.modwt_forward(np.array(k["input"]), 1, g, hh, dense=True)
+    np.testing.assert_allclose(c[0], k["D1"], atol=1e-9)
+    c = oracle.modwt_forward(np.array(k["input"]), 1, g, hh, fft=True)
+    np.testing.assert_allclose(c[0], k["D1"], atol=1e-9)
+    np.testing.assert_allclose(c[1], k["A1"], atol=1e-9)
+
+
+def test_adjoint_is_matrix_transpose(kats, oracle):
+    k = kats["adjoint_transpose"]
+    np.testing.assert_allclose(oracle.circular_convolve(k["signal"], k["filter"]), k["direct"], atol=1e-10)
+    np.testing.assert_allclose(oracle.circular_convolve(k["signal"], k["filter"], adjoint=True), k["adjoint"], atol=1e-10)
+
+
+def test_haar_fwt_level1_fixture(W, kats, oracle):
+    k = kats["haar_fwt_level1"]
+    h = W.Haar1()
+    for mod in (oracle, np_oracle):
+        out = mod.fwt_forward(np.array(k["input"]), 1, h.getScalingDeComposition(), h.getWaveletDeComposition())
+        np.testing.assert_allclose(out[:4], k["approx"], atol=1e-10)
+        np.testing.assert_allclose(out[4:], k["detail"], atol=1e-10)
+
+
+def _ladder(n, p):
+    e = np.zeros(n)
+    e[: n >> p] = 2.0 ** (p / 2.0)
+    return e
+
+
+@pytest.mark.parametrize("n", [4, 64])
+def test_all_ones_ladders_every_wavelet(W, oracle, n):
+    """SteppingTest.java:37-314 / DecomposeTest.java:30-170: FWT and WPT of all-ones, every level, tolerance 1e-8."""
+    ones = np.ones(n)
+    for w in W.create2arr():
+        s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+        sr, wr = w.getScalingReConstruction(), w.getWaveletReConstruction()
+        for p in range(int(math.log2(n)) + 1):
+            for fwd, rev in ((oracle.fwt_forward, oracle.fwt_reverse), (oracle.wpt_forward, oracle.wpt_reverse)):
+                c = fwd(ones, p, s, wv)
+                np.testing.assert_allclose(c, _ladder(n, p), atol=1e-8, err_msg="%s level %d" % (w.getName(), p))
+                np.testing.assert_allclose(rev(c, p, sr, wr), ones, atol=1e-8)
+
+
+def test_c_and_numpy_restatements_agree_bitwise(W, oracle):
+    rng_x = splitmix_uniform(11, (256,))
+    for cls in ["Haar1", "Daubechies2", "Daubechies4", "Daubechies8", "Daubechies20", "Symlet8", "Coiflet3"]:
+        w = W.create(cls)
+        s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+        g1, h1 = oracle.modwt_filters(s, wv)
+        g2, h2 = np_oracle.modwt_filters(s, wv)
+        assert np.array_equal(g1, g2) and np.array_equal(h1, h2)
+        for J in (1, 3, 5):
+            a = oracle.modwt_forward(rng_x, J, g1, h1)
+            b = np_oracle.modwt_forward(rng_x, J, g1, h1)
+            assert np.array_equal(a, b), (cls, J)
+            assert np.array_equal(oracle.modwt_inverse(a, g1, h1), np_oracle.modwt_inverse(a, g1, h1))
+        for lvl in (1, 4, 8):
+            assert np.array_equal(oracle.fwt_forward(rng_x, lvl, s, wv), np_oracle.fwt_forward(rng_x, lvl, s, wv))
+            assert np.array_equal(oracle.wpt_forward(rng_x, lvl, s, wv), np_oracle.wpt_forward(rng_x, lvl, s, wv))
+            assert np.array_equal(oracle.fwt_reverse(rng_x, lvl, s, wv), np_oracle.fwt_reverse(rng_x, lvl, s, wv))
+            assert np.array_equal(oracle.wpt_reverse(rng_x, lvl, s, wv), np_oracle.wpt_reverse(rng_x, lvl, s, wv))
+
+
+def test_dense_and_sparse_direct_convolution_identical(W, oracle):
+    """The literal O(N*M) loops over the zero-stuffed filters (MODWTTransform.java:677-716) and the loops that skip
+    the structural zeros give the same bits; includes filter-longer-than-signal (sym8 on 8 samples,
+    MODWTFFTConvolutionTest.java:42-56) and non-2^p lengths (MODWTInverseTest.java:20-92)."""
+    for cls, n, J in [("Symlet8", 8, 3), ("Daubechies4", 100, 6), ("Daubechies20", 288, 8), ("Haar1", 1000, 9)]:
+        w = W.create(cls)
+        g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+        x = splitmix_uniform(n, (n,))
+        a = oracle.modwt_forward(x, J, g, h, dense=True)
+        b = oracle.modwt_forward(x, J, g, h, dense=False)
+        assert np.array_equal(a, b)
+        assert np.array_equal(oracle.modwt_inverse(a, g, h, dense=True), oracle.modwt_inverse(a, g, h, dense=False))
+        up = oracle.upsample(g, J)
+        assert len(up) == (len(g) - 1) * 2 ** (J - 1) + 1 and np.count_nonzero(up) <= len(g)
+
+
+def test_oracle_properties_like_reference_tests(W, oracle):
+    """MODWTInverseTest.java:20-115, MODWTTransformTest.java:74-89, PropertyBasedTest.java:316-357."""
+    for cls in ["Haar1", "Daubechies4", "Daubechies6", "Symlet8"]:
+        w = W.create(cls)
+        g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+        for n in (64, 100, 288, 512, 1000):
+            x = splitmix_uniform(n + 7, (n,))
+            J = 3
+            c = oracle.modwt_forward(x, J, g, h)
+            xr = oracle.modwt_inverse(c, g, h)
+            assert np.mean((x - xr) ** 2) < 1e-10
+            assert abs(np.sum(c ** 2) - np.sum(x ** 2)) < 1e-9 * np.sum(x ** 2) + 1e-9
+            shifted = oracle.modwt_forward(np.roll(x, 5), J, g, h)
+            np.testing.assert_allclose(shifted, np.roll(c, 5, axis=1), atol=1e-12)
+
+
+def test_fft_path_matches_direct_path(W, oracle):
+    """MODWTFFTConvolutionTest.java: direct vs FFT agree to 1e-8 (the FFT path is the timed CPU baseline only)."""
+    w = W.Daubechies4()
+    g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+    x = splitmix_uniform(3, (1024,))
+    a = oracle.modwt_forward(x, 3, g, h)
+    b = oracle.modwt_forward(x, 3, g, h, fft=True)
+    np.testing.assert_allclose(a, b, atol=1e-8)
+    np.testing.assert_allclose(oracle.modwt_inverse(a, g, h, fft=True), x, atol=1e-8)
+
+
+def test_batch_driver_threads(W, oracle):
+    w = W.Daubechies4()
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    g, h = oracle.modwt_filters(s, wv)
+    X = splitmix_uniform(5, (6, 128))
+    c1 = oracle.batch("modwt_fwd", X, 3, g, h, nthreads=1)
+    c4 = oracle.batch("modwt_fwd", X, 3, g, h, nthreads=4)
+    assert np.array_equal(c1, c4)
+    for b in range(6):
+        assert np.array_equal(c1[b], oracle.modwt_forward(X[b], 3, g, h))
+    assert np.allclose(oracle.batch("modwt_inv", c1, 3, g, h, nthreads=3), X, atol=1e-10)
+    f = oracle.batch("fwt_fwd", X, 7, s, wv, nthreads=2)
+    assert np.array_equal(f[2], oracle.fwt_forward(X[2], 7, s, wv))
+    p = oracle.batch("wpt_fwd", X, 4, s, wv, nthreads=2)
+    assert np.array_equal(p[5], oracle.wpt_forward(X[5], 4, s, wv))
