@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3haar|c3db8|c4|c5]
+
+A "step" is one pass of the hot path over one batch of synthetic input: forward + inverse of the named
+transform.  Default workload = BASELINE.json configs[1] ("c2"): batched MODWT Daubechies4 J=6 forward+inverse on
+4,096 signals x 65,536 fp64 samples per GPU (weak scaling: every rank owns its own 4,096 signals, sharded by signal,
+no collective on the data path).  `value` = sample-transforms per second summed over all ranks, counting
+batch*N samples for the forward and batch*N for the inverse of every step, inputs resident in HBM.
+
+Prints ONE JSON line (see the task contract): metric/value/unit, roofline (forward kernel: algorithmic bytes
+8*(J+2) per sample / CUDA-event duration vs MEASURED_PEAKS.json), cpu_baseline (the oracle's restatement of the
+reference's default FFT-convolution MODWT on the host cores, bounded sample), e2e (same metric through the
+host-buffer C ABI with pinned host memory, copies inside the timed region), clocks, gpu_launches.
+
+--impl reference times the reference's own CPU algorithm (oracle port: FFT-convolution MODWT exactly as
+MODWTTransform.java:752-837 + FastFourierTransform.java:172-212; no JVM exists here) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    #  name: (kind, wavelet class, levels, batch per GPU, n)
+    "c2": ("modwt", "Daubechies4", 6, 4096, 65536),
+    "c5": ("modwt", "Daubechies20", 8, 8192, 65536),     # total 8,192 series -> per GPU 8192 / N (strong) in BASELINE; here per GPU
+    "c3haar": ("fwt", "Haar1", 20, 1024, 1 << 20),
+    "c3db8": ("fwt", "Daubechies8", 20, 1024, 1 << 20),
+    "c4": ("wpt", "Symlet8", 6, 512, 65536),
+}
+
+
+def workload_desc(name, kind, cls, levels, batch, n):
+    return "%s: batched %s %s J=%d forward+inverse, %d signals x %d fp64 samples per GPU" % (
+        name, kind.upper(), cls, levels, batch, n)
+
+
+def algorithmic_bytes_per_sample(kind, levels):
+    # MODWT fwd or inv 8*(J+2) B/sample; FWT / WPT 16 B/sample
+    return 8 * (levels + 2) if kind == "modwt" else 16
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_time(kind, cls, levels, n, nsig, threads, repeats=1):
+    """Time the oracle's restatement of the reference's CPU path on `nsig` signals with `threads` host threads.
+    MODWT uses the reference's default FFT convolution (AUTO picks FFT for every BASELINE config)."""
+    import jwave_pro_b200 as jw
+    from jwave_pro_b200.synth import splitmix_uniform
+    from oracle import c_oracle as oracle
+    w = jw.wavelets.create(cls)
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    X = splitmix_uniform(0x5EED0002, (nsig, n))
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if kind == "modwt":
+            g, h = oracle.modwt_filters(s, wv)
+            c = oracle.batch("modwt_fwd_fft", X, levels, g, h, nthreads=threads)
+            oracle.batch("modwt_inv_fft", c, levels, g, h, nthreads=threads)
+        else:
+            c = oracle.batch(kind + "_fwd", X, levels, s, wv, nthreads=threads)
+            oracle.batch(kind + "_rev", c, levels, w.getScalingReConstruction(), w.getWaveletReConstruction(),
+                         nthreads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def run_reference(args, kind, cls, levels, batch, n, rank, world):
+    """--impl reference: rank 0 alone works; other ranks exit 0."""
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    # bounded sample per step: a few signals per core, so K+W steps finish in minutes
+    probe = cpu_reference_time(kind, cls, levels, n, cores, cores)
+    target = 6.0  # seconds per step
+    nsig = int(max(cores, min(batch, cores * max(1, round(target / max(probe, 1e-3))))))
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_reference_time(kind, cls, levels, n, nsig, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = 2.0 * nsig * n / (ms * 1e-3) / 1e9
+    sample = "%d signals x %d samples per step (of %d), forward+inverse, %d threads, one signal per thread" % (
+        nsig, n, batch, cores)
+    line = {
+        "impl": "reference", "metric": "MODWT/FWT/WPT Gsamples/s (forward+inverse sample-transforms per second)",
+        "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_desc(args.workload, kind, cls, levels, batch, n),
+                   "note": "CPU arm: C restatement (oracle/jwave_oracle.c, -O2 -ffp-contract=off) of the reference's "
+                           "default path (FFT-convolution MODWT; no JVM in this image), bounded sample per step"},
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override signals per GPU (debug; invalidates the headline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", default="", help="comma list key=value passed to jwc_set_tuning")
+    ap.add_argument("--flags", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("note: warmup < 3 breaks the timing rules; use only for smoke runs", file=sys.stderr)
+
+    kind, cls, levels, batch, n = WORKLOADS[args.workload]
+    if args.batch > 0:
+        batch = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        return run_reference(args, kind, cls, levels, batch, n, rank, world)
+
+    import torch
+    import jwave_pro_b200 as jw
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        devices = [local_rank]
+    else:
+        # plain `python bench.py --gpus N` (no torchrun): one process drives N devices, one stream each
+        devices = list(range(max(1, args.gpus)))
+        torch.cuda.set_device(devices[0])
+    n_gpus = world if distributed else len(devices)
+
+    ctx = jw.Context(devices)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        ctx.set_tuning(k, int(v))
+    w = jw.wavelets.create(cls)
+    if kind == "modwt":
+        tr = jw.CudaMODWTTransform(w, context=ctx)
+    elif kind == "fwt":
+        tr = jw.CudaFastWaveletTransform(w, context=ctx)
+    else:
+        tr = jw.CudaWaveletPacketTransform(w, context=ctx)
+
+    # ---- synthetic inputs, resident in HBM (uniform(-1,1), seeded per rank) ---------------------------------
+    out_rows = levels + 1 if kind == "modwt" else 1
+    bufs = []
+    for slot, d in enumerate(devices):
+        with torch.cuda.device(d):
+            gen = torch.Generator(device="cuda:%d" % d)
+            gen.manual_seed(0x5EED0002 + rank * 16 + slot)
+            x = torch.rand((batch, n), dtype=torch.float64, device="cuda:%d" % d, generator=gen) * 2.0 - 1.0
+            c = torch.empty((batch, out_rows * n), dtype=torch.float64, device="cuda:%d" % d)
+            xr = torch.empty_like(x)
+            bufs.append((x, c, xr, torch.cuda.current_stream(d)))
+
+    def fwd(slot):
+        x, c, xr, st = bufs[slot]
+        if kind == "modwt":
+            tr.forwardMODWTDevice(x.data_ptr(), c.data_ptr(), batch, n, levels, stream=st.cuda_stream, flags=args.flags,
+                                  slot=slot)
+        else:
+            tr.forwardDevice(x.data_ptr(), c.data_ptr(), batch, n, levels, stream=st.cuda_stream, flags=args.flags,
+                             slot=slot)
+
+    def inv(slot):
+        x, c, xr, st = bufs[slot]
+        if kind == "modwt":
+            tr.inverseMODWTDevice(c.data_ptr(), xr.data_ptr(), batch, n, levels, stream=st.cuda_stream,
+                                  flags=args.flags, slot=slot)
+        else:
+            tr.reverseDevice(c.data_ptr(), xr.data_ptr(), batch, n, levels, stream=st.cuda_stream, flags=args.flags,
+                             slot=slot)
+
+    def sync_all():
+        for d in devices:
+            torch.cuda.synchronize(d)
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for s in range(len(devices)):
+            fwd(s)
+            inv(s)
+    sync_all()
+    # correctness of the timed path itself: round trip must hold
+    pr = max(float((b[2] - b[0]).abs().max()) for b in bufs) if args.warmup > 0 else 0.0
+
+    # ---- timed region ---------------------------------------------------------------------------------------------
+    clock = ClockSampler(devices[0]) if rank == 0 else None
+    ev = []
+    launches0 = ctx.launch_count()
+    sync_all()
+    for s, d in enumerate(devices):
+        with torch.cuda.device(d):
+            st = bufs[s][3]
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+            e[0].record(st)
+            ev.append(e)
+    for k in range(args.steps):
+        for s, d in enumerate(devices):
+            with torch.cuda.device(d):
+                fwd(s)
+                ev[s][2 * k + 1].record(bufs[s][3])
+                inv(s)
+                ev[s][2 * k + 2].record(bufs[s][3])
+    sync_all()
+    launches = ctx.launch_count() - launches0
+    clocks = clock.stop() if clock else None
+    total_ms = max(e[0].elapsed_time(e[-1]) for e in ev)
+    fwd_ms = max(sum(e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(args.steps)) for e in ev) / args.steps
+    inv_ms = max(sum(e[2 * k + 1].elapsed_time(e[2 * k + 2]) for k in range(args.steps)) for e in ev) / args.steps
+    if distributed:
+        t = torch.tensor([total_ms, fwd_ms, inv_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, fwd_ms, inv_ms = [float(v) for v in t.tolist()]
+    ms_per_step = total_ms / args.steps
+    samples_per_step = 2.0 * batch * n * n_gpus
+    value = samples_per_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (forward) ------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    bps = algorithmic_bytes_per_sample(kind, levels)
+    fwd_gbs = bps * batch * n / (fwd_ms * 1e-3) / 1e9
+    inv_gbs = bps * batch * n / (inv_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak,
+                "traffic": None, "kernel": "%s forward" % kind, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bps * batch * n, "avg_ms": fwd_ms,
+                "inverse": {"achieved": inv_gbs, "frac": inv_gbs / peak, "avg_ms": inv_ms}}
+
+    # ---- e2e: the same metric through the host-buffer C ABI (pinned host memory, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        eb = min(batch, 256) * len(devices)
+        hx = torch.empty((eb, n), dtype=torch.float64).pin_memory()
+        hx.copy_(torch.cat([b[0][:eb // len(devices)].cpu() for b in bufs]))
+        hc = torch.empty((eb, out_rows * n), dtype=torch.float64).pin_memory()
+        hr = torch.empty((eb, n), dtype=torch.float64).pin_memory()
+        ectx = jw.Context(devices)
+        if kind == "modwt":
+            et = jw.CudaMODWTTransform(w, context=ectx)
+            X, C, R = hx.numpy(), hc.numpy().reshape(eb, out_rows, n), hr.numpy()
+            step = lambda: (et.forwardMODWTBatch(X, levels, out=C), et.inverseMODWTBatch(C, out=R))  # noqa: E731
+        else:
+            et = (jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform)(w, context=ectx)
+            X, C, R = hx.numpy(), hc.numpy(), hr.numpy()
+            step = lambda: (et.forwardBatch(X, levels, out=C), et.reverseBatch(C, levels, out=R))  # noqa: E731
+        step()
+        esteps = max(2, min(args.steps, 5))
+        if distributed:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            step()
+        e_ms = (time.perf_counter() - t0) * 1e3 / esteps
+        if distributed:
+            t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        assert float(np.max(np.abs(R - X))) <= 1e-10
+        io = (1 + out_rows) * eb * n * 8 * (world if distributed else 1)
+        e2e = {"value": 2.0 * eb * n * (world if distributed else 1) / (e_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+               "h2d_bytes_per_step": io, "d2h_bytes_per_step": io, "ms_per_step": e_ms,
+               "batch_per_gpu": eb // len(devices), "note": "jwc_*_forward + jwc_*_inverse on pinned host buffers, %d signals per GPU "
+               "per step (bounded so pinned staging stays small); PCIe-bound" % eb}
+        ectx.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        probe = cpu_reference_time(kind, cls, levels, n, cores, cores)
+        nsig = int(max(cores, min(batch, cores * max(1, round(12.0 / max(probe, 1e-3))))))
+        dt = cpu_reference_time(kind, cls, levels, n, nsig, cores)
+        cpu = {"value": 2.0 * nsig * n / dt / 1e9, "unit": "Gsamples/s", "cores": cores, "kind": "port",
+               "sample": "%d of %d signals x %d samples, forward+inverse, %d threads (one signal per thread); C "
+                         "restatement of the reference's %s" % (nsig, batch, n, cores,
+                                                                "FFT-convolution MODWT" if kind == "modwt" else kind.upper())}
+
+    if rank == 0:
+        line = {
+            "metric": "MODWT/FWT/WPT Gsamples/s (forward+inverse sample-transforms per second)",
+            "value": value, "unit": "Gsamples/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload, kind, cls, levels, batch, n),
+                       "l2": "inputs larger than L2 (%.1f GiB read per direction vs 126 MB L2)" % (
+                           (out_rows if kind == "modwt" else 1) * batch * n * 8 / 2 ** 30),
+                       "sharding": "by signal, no collective", "tune": args.tune, "flags": args.flags,
+                       "round_trip_max_err": pr},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,100 @@
+"""CPU-only: validation order, exception types and message substrings of the host mirror
+(reference tests MODWT1DInterfaceTest.java:108-137, MODWTTheoreticalLimitTest.java:40-56,
+MODWTLevelLimitTest.java:20-87, ParallelWPTTest.java:128-151).  None of these reach the native library."""
+import numpy as np
+import pytest
+
+
+def test_modwt_forward_level_checks(jw):
+    t = jw.CudaMODWTTransform(jw.wavelets.Daubechies4())
+    x = np.ones(64)
+    with pytest.raises(jw.IllegalArgumentException, match="at least 1"):
+        t.forwardMODWT(x, 0)
+    with pytest.raises(jw.IllegalArgumentException, match="maximum supported decomposition level is 13"):
+        t.forwardMODWT(x, 14)
+    with pytest.raises(jw.IllegalArgumentException, match="exceeds theoretical limit 6 for signal length 64"):
+        t.forwardMODWT(x, 7)
+    # order: level checks come before the null/empty check (MODWTTransform.java:257-273)
+    with pytest.raises(jw.IllegalArgumentException, match="at least 1"):
+        t.forwardMODWT(None, 0)
+    rows = t.forwardMODWT(None, 3)
+    assert len(rows) == 4 and all(len(r) == 0 for r in rows)
+    rows = t.forwardMODWT([], 2)
+    assert len(rows) == 3
+    assert jw.CudaMODWTTransform.getMaxDecompositionLevel() == 13
+    # floor(log2 N) for non powers of two (MODWTLog2CalculationTest.java:90-121)
+    with pytest.raises(jw.IllegalArgumentException, match="theoretical limit 6 for signal length 100"):
+        t.forwardMODWT(np.ones(100), 7)
+
+
+def test_modwt_inverse_degenerate_inputs(jw):
+    t = jw.CudaMODWTTransform(jw.wavelets.Haar1())
+    assert len(t.inverseMODWT(None)) == 0
+    assert len(t.inverseMODWT([])) == 0
+    assert len(t.inverseMODWT([[1.0, 2.0]])) == 0   # < 2 rows (MODWTTransform.java:342-346)
+
+
+def test_modwt_flat_interface_errors(jw):
+    t = jw.CudaMODWTTransform(jw.wavelets.Haar1())
+    assert len(t.forward([], 2)) == 0 and len(t.forward(None)) == 0 and len(t.reverse([], 1)) == 0
+    with pytest.raises(jw.JWaveFailure, match=r"2\^p"):
+        t.forward(np.ones(7), 2)
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        t.forward(np.ones(8), -1)
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        t.forward(np.ones(8), 4)
+    with pytest.raises(jw.IllegalArgumentException, match="at least 1"):
+        t.forward(np.ones(8), 0)          # passes the JWaveFailure checks, then forwardMODWT's
+    with pytest.raises(jw.JWaveFailure, match="maximum supported"):
+        t.forward(np.ones(1 << 14), 14)
+    with pytest.raises(jw.JWaveFailure, match="Invalid coefficient array"):
+        t.reverse(np.ones(21), 2)         # 21 / 3 = 7 is not 2^p
+    with pytest.raises(jw.JWaveFailure, match="does not match"):
+        t.reverse(np.ones(25), 2)         # 25 // 3 = 8 but 8*3 != 25
+    with pytest.raises(jw.IllegalArgumentException):
+        t.forward(np.ones(1 << 14))       # level-less forward on N > 8192: J = 14 > 13, unchecked (A.6)
+    with pytest.raises(jw.JWaveFailure):
+        t.forward(np.ones(12))            # calcExponent on a non power of two
+
+
+def test_fwt_wpt_shape_errors(jw):
+    for cls, name in ((jw.CudaFastWaveletTransform, "Fast Wavelet Transform"),
+                      (jw.CudaWaveletPacketTransform, "Wavelet Packet Transform")):
+        t = cls(jw.wavelets.Daubechies4())
+        assert t.getName() == name
+        with pytest.raises(jw.JWaveFailure, match=r"2\^p"):
+            t.forward(np.ones(17), 2)
+        with pytest.raises(jw.JWaveFailure, match=r"2\^p"):
+            t.forward(np.ones(17))
+        with pytest.raises(jw.JWaveFailure, match="given level is out of range for given array"):
+            t.forward(np.ones(8), 10)
+        with pytest.raises(jw.JWaveFailure, match="given level is out of range for given array"):
+            t.reverse(np.ones(8), -1)
+        with pytest.raises(jw.JWaveFailure, match=r"2\^p"):
+            t.forward(np.ones(0))
+        with pytest.raises(jw.JWaveFailure, match="out of range"):
+            t.recompose(np.ones((4, 8)), 4)
+
+
+def test_modwt_base_filters_match_oracle(jw, oracle):
+    for cls in jw.wavelets.ALL_CLASSES:
+        w = jw.wavelets.create(cls)
+        t = jw.CudaMODWTTransform(w)
+        t.initializeFilterCache()
+        g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+        assert np.array_equal(t._g, g) and np.array_equal(t._h, h)
+        t.clearFilterCache()
+        assert t._g is None
+        t.precomputeFilters(5)
+        assert np.array_equal(t._g, g)
+    with pytest.raises(jw.IllegalArgumentException):
+        jw.CudaMODWTTransform(jw.wavelets.Haar1()).precomputeFilters(14)
+
+
+def test_getters_return_copies(jw):
+    w = jw.wavelets.Symlet8()
+    a = w.getScalingDeComposition()
+    a[0] = 99.0
+    assert w.getScalingDeComposition()[0] != 99.0
+    assert w.getMotherWavelength() == 16 and w.getTransformWavelength() == 2
+    assert jw.wavelets.create("Daubechies 20").getMotherWavelength() == 40

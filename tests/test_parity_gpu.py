@@ -1,0 +1,344 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the reference's KATs.
+
+Bars (BASELINE.json north_star): max|err| <= 1e-12 * max|x| for the default (FMA) kernels, perfect reconstruction
+<= 1e-10; in JWC_FLAG_EXACT mode (unfused mul/add in the reference's order) the result must equal the oracle
+bit for bit.  Nothing here reads /root/reference.
+"""
+import math
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import chirp, splitmix_uniform
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12   # north_star parity tolerance, relative to max|x|
+PR_TOL = 1e-10
+
+
+def _maxerr(a, b, x):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) / max(float(np.max(np.abs(x))), 1e-300)
+
+
+def _modwt_oracle(oracle, w, X, J, nthreads=8):
+    g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+    return oracle.batch("modwt_fwd", X, J, g, h, nthreads=nthreads), (g, h)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference KATs on the GPU
+# ----------------------------------------------------------------------------------------------------------------
+
+def test_kat_modwt_haar(jw, gpu_ctx, kats):
+    k = kats["modwt_haar_level1"]
+    t = jw.CudaMODWTTransform(jw.wavelets.Haar1())
+    for flags in (0, jw.FLAG_EXACT, jw.FLAG_FORCE_GENERIC):
+        c = t.forwardMODWT(k["input"], 1, flags=flags)
+        np.testing.assert_allclose(c[0], k["D1"], atol=1e-9)
+        np.testing.assert_allclose(c[1], k["A1"], atol=1e-9)
+        np.testing.assert_allclose(t.inverseMODWT(c, flags=flags), k["input"], atol=1e-9)
+
+
+def test_kat_haar_fwt_fixture(jw, gpu_ctx, kats):
+    k = kats["haar_fwt_level1"]
+    out = jw.CudaFastWaveletTransform(jw.wavelets.Haar1()).forward(k["input"], 1)
+    np.testing.assert_allclose(out[:4], k["approx"], atol=1e-10)
+    np.testing.assert_allclose(out[4:], k["detail"], atol=1e-10)
+
+
+@pytest.mark.parametrize("n", [4, 64])
+def test_kat_all_ones_ladders(jw, gpu_ctx, n):
+    """SteppingTest.java:37-314 for the 44 in-scope wavelets: includes filters far longer than the signal (L=40, n=4)."""
+    ones = np.ones(n)
+    for w in jw.wavelets.create2arr():
+        for T in (jw.CudaFastWaveletTransform, jw.CudaWaveletPacketTransform):
+            t = T(w)
+            for p in range(int(math.log2(n)) + 1):
+                e = np.zeros(n)
+                e[: n >> p] = 2.0 ** (p / 2.0)
+                c = t.forward(ones, p)
+                np.testing.assert_allclose(c, e, atol=1e-8, err_msg="%s %s level %d" % (T.__name__, w.getName(), p))
+                np.testing.assert_allclose(t.reverse(c, p), ones, atol=1e-8)
+            d = t.decompose(ones)
+            np.testing.assert_allclose(t.recompose(d, int(math.log2(n))), ones, atol=1e-8)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# exact mode: bit-identical to the oracle
+# ----------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cls,n,J", [("Haar1", 8, 3), ("Symlet8", 8, 3), ("Daubechies4", 1024, 3),
+                                     ("Daubechies4", 100, 6), ("Daubechies6", 288, 5), ("Daubechies20", 1000, 9),
+                                     ("Coiflet5", 500, 8), ("Daubechies20", 64, 6), ("Symlet20", 4096, 12)])
+def test_exact_modwt_bitwise(jw, gpu_ctx, oracle, cls, n, J):
+    w = jw.wavelets.create(cls)
+    t = jw.CudaMODWTTransform(w)
+    X = splitmix_uniform(n * 31 + J, (3, n))
+    ref, (g, h) = _modwt_oracle(oracle, w, X, J)
+    got = t.forwardMODWTBatch(X, J, flags=jw.FLAG_EXACT)
+    assert np.array_equal(got, ref)
+    back = t.inverseMODWTBatch(got, flags=jw.FLAG_EXACT)
+    assert np.array_equal(back, oracle.batch("modwt_inv", ref, J, g, h, nthreads=4))
+    assert np.max(np.abs(back - X)) < PR_TOL
+
+
+@pytest.mark.parametrize("cls", ["Haar1", "Daubechies2", "Daubechies4", "Daubechies8", "Daubechies20", "Symlet8",
+                                 "Coiflet1", "Coiflet5"])
+@pytest.mark.parametrize("n", [2, 4, 16, 64, 1024])
+def test_exact_fwt_wpt_bitwise(jw, gpu_ctx, oracle, cls, n):
+    w = jw.wavelets.create(cls)
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    X = splitmix_uniform(n + len(s), (2, n))
+    p = int(math.log2(n))
+    for lvl in sorted({0, 1, p // 2, p}):
+        for T, fo, ro in ((jw.CudaFastWaveletTransform, "fwt_fwd", "fwt_rev"),
+                          (jw.CudaWaveletPacketTransform, "wpt_fwd", "wpt_rev")):
+            t = T(w)
+            ref = oracle.batch(fo, X, lvl, s, wv)
+            got = t.forwardBatch(X, lvl, flags=jw.FLAG_EXACT)
+            assert np.array_equal(got, ref), (T.__name__, cls, n, lvl)
+            rref = oracle.batch(ro, ref, lvl, s, wv)
+            rgot = t.reverseBatch(got, lvl, flags=jw.FLAG_EXACT)
+            assert np.array_equal(rgot, rref), (T.__name__, cls, n, lvl, "reverse")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# default kernels vs the oracle at the BASELINE configurations (a subset of signals at the full length)
+# ----------------------------------------------------------------------------------------------------------------
+
+def _inputs(seed, batch, n):
+    X = splitmix_uniform(seed, (batch, n))
+    X[batch // 2:] = chirp(batch - batch // 2, n)   # random + chirp, SURVEY.md section 8d
+    return X
+
+
+@pytest.mark.parametrize("cls,n,J,batch", [
+    ("Daubechies4", 1024, 3, 1),        # C1 (the reference's own CPU-runnable case)
+    ("Daubechies4", 65536, 6, 6),       # C2 shape
+    ("Daubechies20", 65536, 8, 4),      # C5 shape
+    ("Symlet8", 65536, 6, 3),
+    ("Haar1", 65536, 13, 2),            # deepest level the reference allows
+    ("Daubechies4", 8192, 13, 2),
+    ("Daubechies20", 8192, 13, 1),      # (L-1)*2^12 = 159744 > n: the filter wraps many times
+    ("Daubechies8", 4096, 5, 37),       # ragged batch
+    ("Daubechies4", 100, 6, 5),         # not a power of two (MODWTInverseTest.java:20-92)
+    ("Daubechies6", 1000, 9, 3),
+    ("Daubechies4", 65538, 6, 2),       # even but not a multiple of anything convenient
+    ("Daubechies4", 40000, 7, 3),
+    ("Daubechies4", 65537, 4, 2),       # odd length
+    ("Symlet8", 8, 3, 2),               # filter longer than the signal (MODWTFFTConvolutionTest.java:42-56)
+])
+def test_modwt_matches_oracle(jw, gpu_ctx, oracle, cls, n, J, batch):
+    w = jw.wavelets.create(cls)
+    t = jw.CudaMODWTTransform(w)
+    X = _inputs(n + J, batch, n)
+    ref, (g, h) = _modwt_oracle(oracle, w, X, J)
+    got = t.forwardMODWTBatch(X, J)
+    assert _maxerr(got, ref, X) <= TOL
+    gen = t.forwardMODWTBatch(X, J, flags=jw.FLAG_FORCE_GENERIC)
+    assert _maxerr(gen, ref, X) <= TOL
+    back = t.inverseMODWTBatch(ref)
+    assert _maxerr(back, oracle.batch("modwt_inv", ref, J, g, h, nthreads=8), X) <= TOL
+    assert _maxerr(t.inverseMODWTBatch(got), X, X) <= PR_TOL
+    # single-signal API and flat 1-D API agree with the batch API
+    one = t.forwardMODWT(X[0], J)
+    assert np.array_equal(one, got[0])
+    if jw.BasicTransform.isBinary(n):
+        flat = t.forward(X[0], J)
+        assert np.array_equal(flat, got[0].reshape(-1))
+        assert _maxerr(t.reverse(flat, J), X[0], X[0]) <= PR_TOL
+
+
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+@pytest.mark.parametrize("cls,n,lvl,batch", [
+    ("Haar1", 1 << 20, 20, 2),          # C3
+    ("Daubechies8", 1 << 20, 20, 2),    # C3
+    ("Symlet8", 65536, 6, 4),           # C4
+    ("Daubechies20", 65536, 16, 2),
+    ("Daubechies4", 1 << 17, 9, 3),
+    ("Coiflet3", 2048, 11, 9),
+    ("Daubechies8", 4096, 3, 33),
+    ("Daubechies20", 32, 5, 3),
+    ("Daubechies4", 2, 1, 2),
+    ("Haar1", 1, 0, 3),
+])
+def test_fwt_wpt_match_oracle(jw, gpu_ctx, oracle, kind, cls, n, lvl, batch):
+    if kind == "wpt" and n >= (1 << 20):
+        lvl = 8   # a 20-level packet tree of 2^20 samples costs the CPU oracle too long
+    w = jw.wavelets.create(cls)
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    t = (jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform)(w)
+    X = _inputs(n + lvl, batch, n)
+    ref = oracle.batch(kind + "_fwd", X, lvl, s, wv, nthreads=8)
+    got = t.forwardBatch(X, lvl)
+    assert _maxerr(got, ref, X) <= TOL
+    gen = t.forwardBatch(X, lvl, flags=jw.FLAG_FORCE_GENERIC)
+    assert _maxerr(gen, ref, X) <= TOL
+    rref = oracle.batch(kind + "_rev", ref, lvl, s, wv, nthreads=8)
+    assert _maxerr(t.reverseBatch(ref, lvl), rref, X) <= TOL
+    assert _maxerr(t.reverseBatch(got, lvl), X, X) <= PR_TOL
+    assert np.array_equal(t.forward(X[0], lvl), got[0])
+    # every intermediate level is reachable, like the reference's stepping API
+    for l2 in sorted({0, 1, lvl // 2}):
+        if l2 <= lvl:
+            r2 = oracle.batch(kind + "_fwd", X[:1], l2, s, wv)
+            assert _maxerr(t.forwardBatch(X[:1], l2), r2, X) <= TOL
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host pipeline, threads, degenerate batches
+# ----------------------------------------------------------------------------------------------------------------
+
+def test_host_pipeline_many_chunks(jw, oracle):
+    ctx = jw.Context()
+    ctx.set_tuning("h2d_chunk_mb", 1)   # forces many double-buffered chunks
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaMODWTTransform(w, context=ctx)
+    X = _inputs(77, 41, 8192)
+    ref, (g, h) = _modwt_oracle(oracle, w, X, 5)
+    got = t.forwardMODWTBatch(X, 5)
+    assert _maxerr(got, ref, X) <= TOL
+    assert _maxerr(t.inverseMODWTBatch(got), X, X) <= PR_TOL
+    f = jw.CudaFastWaveletTransform(w, context=ctx)
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    assert _maxerr(f.forwardBatch(X, 13), oracle.batch("fwt_fwd", X, 13, s, wv, nthreads=8), X) <= TOL
+    assert ctx.launch_count() > 0
+    ctx.close()
+
+
+def test_empty_batch_and_bad_arguments(jw, gpu_ctx):
+    from jwave_pro_b200 import _native
+    t = jw.CudaMODWTTransform(jw.wavelets.Haar1())
+    out = t.forwardMODWTBatch(np.empty((0, 64)), 3)
+    assert out.shape == (0, 4, 64)
+    lib = _native.load()
+    x = np.ones(8)
+    o = np.empty(16)
+    g = np.array([0.5, 0.5])
+    dp = _native._dp
+    rc = lib.jwc_modwt_forward(gpu_ctx.handle, x.ctypes.data, o.ctypes.data, 1, 8, 0, g.ctypes.data_as(dp),
+                               g.ctypes.data_as(dp), 2, 0)
+    assert rc == -1 and b"level" in lib.jwc_last_error()
+    rc = lib.jwc_fwt_forward(gpu_ctx.handle, x.ctypes.data, o.ctypes.data, 1, 7, 1, g.ctypes.data_as(dp),
+                             g.ctypes.data_as(dp), 2, 0)
+    assert rc == -1 and b"2^p" in lib.jwc_last_error()
+    rc = lib.jwc_fwt_forward(gpu_ctx.handle, x.ctypes.data, o.ctypes.data, 1, 8, 4, g.ctypes.data_as(dp),
+                             g.ctypes.data_as(dp), 2, 0)
+    assert rc == -1 and b"out of range" in lib.jwc_last_error()
+    rc = lib.jwc_fwt_forward(gpu_ctx.handle, None, o.ctypes.data, 1, 8, 1, g.ctypes.data_as(dp),
+                             g.ctypes.data_as(dp), 2, 0)
+    assert rc == -1
+    rc = lib.jwc_wpt_forward(gpu_ctx.handle, x.ctypes.data, o.ctypes.data, 1, 8, 1, g.ctypes.data_as(dp),
+                             g.ctypes.data_as(dp), 65, 0)
+    assert rc == -1 and b"filter length" in lib.jwc_last_error()
+
+
+def test_thread_safety_shared_instance(jw, gpu_ctx, oracle):
+    """MODWTThreadSafetyTest.java:24-104: 10 threads x iterations on ONE instance, clearFilterCache every 10th."""
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaMODWTTransform(w)
+    x = splitmix_uniform(9, (512,))
+    g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+    ref = oracle.modwt_forward(x, 4, g, h)
+    errs = []
+
+    def work(tid):
+        try:
+            for it in range(30):
+                c = t.forwardMODWT(x, 4)
+                if np.max(np.abs(c - ref)) > 1e-10:
+                    errs.append((tid, it))
+                if it % 10 == 0:
+                    t.clearFilterCache()
+        except Exception as e:   # noqa: BLE001
+            errs.append((tid, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(10)]
+    [x_.start() for x_ in th]
+    [x_.join() for x_ in th]
+    assert not errs, errs[:3]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# full BASELINE sizes, device-resident: size-independent properties (round trip, linearity, shift invariance)
+# ----------------------------------------------------------------------------------------------------------------
+
+def _torch_inputs(torch, batch, n, seed):
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    return torch.rand((batch, n), dtype=torch.float64, device="cuda", generator=gen) * 2.0 - 1.0
+
+
+@pytest.mark.parametrize("cls,n,J,batch", [("Daubechies4", 65536, 6, 4096), ("Daubechies20", 65536, 8, 1024)])
+def test_modwt_full_size_properties(jw, gpu_ctx, oracle, cls, n, J, batch):
+    import torch
+    w = jw.wavelets.create(cls)
+    t = jw.CudaMODWTTransform(w)
+    st = torch.cuda.current_stream().cuda_stream
+    x = _torch_inputs(torch, batch, n, 1234)
+    c = torch.empty((batch, J + 1, n), dtype=torch.float64, device="cuda")
+    t.forwardMODWTDevice(x.data_ptr(), c.data_ptr(), batch, n, J, stream=st)
+    xr = torch.empty_like(x)
+    t.inverseMODWTDevice(c.data_ptr(), xr.data_ptr(), batch, n, J, stream=st)
+    torch.cuda.synchronize()
+    assert float((xr - x).abs().max()) <= PR_TOL
+    # energy: sum of squares of all coefficients == energy of the signal (MODWTTransformTest.java:74-89)
+    e_x = (x * x).sum(dim=1)
+    e_c = (c * c).sum(dim=(1, 2))
+    assert float(((e_c - e_x).abs() / e_x).max()) < 1e-9
+    # spot rows against the oracle: first / last / a few pseudo-random signals
+    rows = sorted({0, 1, batch - 1, batch // 2, (batch * 7) // 13, 3 % batch})
+    X = x[rows].cpu().numpy()
+    ref, _ = _modwt_oracle(oracle, w, X, J)
+    assert _maxerr(c[rows].cpu().numpy(), ref, X) <= TOL
+    # shift invariance: MODWT(roll(x, s)) == roll(MODWT(x), s) (PropertyBasedTest.java:316-357)
+    xs = torch.roll(x[:64], shifts=12345, dims=1).contiguous()
+    cs = torch.empty((64, J + 1, n), dtype=torch.float64, device="cuda")
+    t.forwardMODWTDevice(xs.data_ptr(), cs.data_ptr(), 64, n, J, stream=st)
+    torch.cuda.synchronize()
+    assert float((cs - torch.roll(c[:64], shifts=12345, dims=2)).abs().max()) <= 1e-12
+    # linearity: T(a x + b y) == a T(x) + b T(y)
+    y = _torch_inputs(torch, 64, n, 99)
+    cy = torch.empty_like(cs)
+    t.forwardMODWTDevice(y.data_ptr(), cy.data_ptr(), 64, n, J, stream=st)
+    z = (0.75 * x[:64] - 1.5 * y).contiguous()
+    cz = torch.empty_like(cs)
+    t.forwardMODWTDevice(z.data_ptr(), cz.data_ptr(), 64, n, J, stream=st)
+    torch.cuda.synchronize()
+    assert float((cz - (0.75 * c[:64] - 1.5 * cy)).abs().max()) <= 1e-12
+
+
+@pytest.mark.parametrize("kind,cls,n,lvl,batch", [("fwt", "Haar1", 1 << 20, 20, 1024),
+                                                   ("fwt", "Daubechies8", 1 << 20, 20, 1024),
+                                                   ("wpt", "Symlet8", 65536, 6, 512)])
+def test_fwt_wpt_full_size_properties(jw, gpu_ctx, oracle, kind, cls, n, lvl, batch):
+    import torch
+    w = jw.wavelets.create(cls)
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    t = (jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform)(w)
+    st = torch.cuda.current_stream().cuda_stream
+    x = _torch_inputs(torch, batch, n, 4321)
+    c = torch.empty_like(x)
+    xr = torch.empty_like(x)
+    t.forwardDevice(x.data_ptr(), c.data_ptr(), batch, n, lvl, stream=st)
+    t.reverseDevice(c.data_ptr(), xr.data_ptr(), batch, n, lvl, stream=st)
+    torch.cuda.synchronize()
+    assert float((xr - x).abs().max()) <= PR_TOL
+    e_x = (x * x).sum(dim=1)
+    e_c = (c * c).sum(dim=1)
+    assert float(((e_c - e_x).abs() / e_x).max()) < 1e-9   # orthonormal transform (PropertyBasedTest.java:138-202)
+    rows = sorted({0, batch - 1, batch // 3})
+    X = x[rows].cpu().numpy()
+    ref = oracle.batch(kind + "_fwd", X, lvl, s, wv, nthreads=8)
+    assert _maxerr(c[rows].cpu().numpy(), ref, X) <= TOL
+    y = _torch_inputs(torch, 8, n, 5)
+    cy = torch.empty_like(y)
+    t.forwardDevice(y.data_ptr(), cy.data_ptr(), 8, n, lvl, stream=st)
+    z = (2.0 * x[:8] + 0.5 * y).contiguous()
+    cz = torch.empty_like(y)
+    t.forwardDevice(z.data_ptr(), cz.data_ptr(), 8, n, lvl, stream=st)
+    torch.cuda.synchronize()
+    assert float((cz - (2.0 * c[:8] + 0.5 * cy)).abs().max()) <= 1e-11
