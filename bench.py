@@ -230,7 +230,7 @@ def main():
             x = torch.rand((batch, n), dtype=torch.float64, device="cuda:%d" % d, generator=gen) * 2.0 - 1.0
             c = torch.empty((batch, out_rows * n), dtype=torch.float64, device="cuda:%d" % d)
             xr = torch.empty_like(x)
-            bufs.append((x, c, xr, torch.cuda.current_stream(d)))
+            bufs.append((x, c, xr, torch.cuda.Stream(device=d)))   # explicit stream: kernels AND events go here
 
     def fwd(slot):
         x, c, xr, st = bufs[slot]

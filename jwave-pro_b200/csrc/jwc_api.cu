@@ -333,6 +333,7 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "modwt_tile")) return &t.modwt_tile;
   if (!strcmp(key, "modwt_threads")) return &t.modwt_threads;
   if (!strcmp(key, "modwt_group")) return &t.modwt_group;
+  if (!strcmp(key, "modwt_smem")) return &t.modwt_smem;
   if (!strcmp(key, "dwt_tile")) return &t.dwt_tile;
   if (!strcmp(key, "dwt_threads")) return &t.dwt_threads;
   if (!strcmp(key, "dwt_group")) return &t.dwt_group;

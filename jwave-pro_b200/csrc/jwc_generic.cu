@@ -182,22 +182,24 @@ void fill_offsets(ModwtLevelArgs& a, int level, int L, int64_t n) {
 
 }  // namespace
 
-int generic_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
-                          int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact) {
+int generic_modwt_forward_from(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_v, int64_t v_sig,
+                               int first_level, double* d_coeffs, int64_t batch, int64_t n, int levels,
+                               const FilterPair& f, int L, bool exact) {
   Scratch ws(st);
   double* vbuf[2] = {nullptr, nullptr};
-  if (levels >= 2) {
+  const int todo = levels - first_level + 1;
+  if (todo >= 2) {
     vbuf[0] = ws.get((size_t)batch * n);
     if (!vbuf[0]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
-  if (levels >= 3) {
+  if (todo >= 3) {
     vbuf[1] = ws.get((size_t)batch * n);
     if (!vbuf[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const int64_t cs = (int64_t)(levels + 1) * n;
-  const double* in = d_x;
-  int64_t in_stride = n;
-  for (int j = 1; j <= levels; j++) {
+  const double* in = d_v;
+  int64_t in_stride = v_sig;
+  for (int j = first_level; j <= levels; j++) {
     ModwtLevelArgs a{};
     a.in_v = in;
     a.in_v_stride = in_stride;
@@ -207,7 +209,7 @@ int generic_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
       a.out_v = d_coeffs + (int64_t)levels * n;
       a.out_v_stride = cs;
     } else {
-      a.out_v = vbuf[(j - 1) & 1];
+      a.out_v = vbuf[(j - first_level) & 1];
       a.out_v_stride = n;
     }
     a.n = n;
@@ -223,6 +225,11 @@ int generic_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
     in_stride = a.out_v_stride;
   }
   return JWC_OK;
+}
+
+int generic_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
+                          int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact) {
+  return generic_modwt_forward_from(ctx, dev, st, d_x, n, 1, d_coeffs, batch, n, levels, f, L, exact);
 }
 
 int generic_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,

@@ -42,6 +42,7 @@ struct Tuning {
   int modwt_tile = 0;       // 0 = auto
   int modwt_threads = 0;
   int modwt_group = 0;      // max levels fused per pass, 0 = auto
+  int modwt_smem = 0;       // shared-memory budget per CTA in bytes, 0 = auto
   int dwt_tile = 0;
   int dwt_threads = 0;
   int dwt_group = 0;
@@ -93,6 +94,10 @@ struct Scratch {
 // ---- generic (any shape, one level per launch) kernels: jwc_generic.cu ---------------------------------
 int generic_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
                           int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact);
+// continue a forward MODWT from V_{first_level-1} (d_v, signal stride v_sig) for levels first_level .. levels
+int generic_modwt_forward_from(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_v, int64_t v_sig,
+                               int first_level, double* d_coeffs, int64_t batch, int64_t n, int levels,
+                               const FilterPair& f, int L, bool exact = false);
 int generic_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                           int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact);
 // tree = false: FWT (only the length-h prefix is transformed each level); tree = true: WPT (every block).

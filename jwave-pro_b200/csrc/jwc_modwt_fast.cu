@@ -1,8 +1,520 @@
-// placeholder until the fused kernels land
+// jwc_modwt_fast.cu -- fused multi-level MODWT forward on shared-memory tiles (sm_100a).
+//
+// Computes, for levels j0+1 .. j0+k of every signal (reference: transforms/MODWTTransform.java:290-304 with the direct
+// convolution :677-690, paths relative to /root/reference/src/main/java/jwave/):
+//     W_j[t] = sum_m h~[m] V_{j-1}[(t - m 2^(j-1)) mod N],   V_j[t] = sum_m g~[m] V_{j-1}[(t - m 2^(j-1)) mod N]
+//
+// Data layout / traffic: the input tile (T2 outputs + left halo (L-1)(2^k-1)) is read from HBM ONCE (1-D bulk TMA
+// copy, the circular wrap is done by splitting the copy at the signal boundary), all k levels are computed in shared
+// memory (V ping-pongs between two buffers), each W_j tile is staged in shared memory and leaves through an
+// asynchronous bulk store, so HBM sees one read and k+1 writes per sample: 8(k+2) bytes.
+//
+// Inner loop ("column scheme"): at stride s the tile is a matrix M[row][col], position = row*s + col, and the
+// a-trous filter is a vertical FIR down each column.  One work item = R consecutive rows of one column: it slides a
+// window down the column, R + L - 1 LDS.64 for 2*R*L DFMA (taps are immediate constant-bank operands), so shared
+// memory bandwidth (128 B/clk/SM) stays below the fp64 pipe.  Lanes map to consecutive columns (s >= 16) or to
+// (column, row-block) pairs whose addresses are distinct mod 16 doubles because R is odd -> conflict-free for all s.
 #include "jwc_internal.cuh"
+#include "jwc_modwt_plan.cuh"
+#include "jwc_tma.cuh"
+
 namespace jwc {
-int fast_modwt_forward(jwc_ctx*, const DeviceSlot&, cudaStream_t, const double*, double*, int64_t, int64_t, int,
-                       const FilterPair&, int) { return JWC_ERR_UNSUPPORTED; }
-int fast_modwt_inverse(jwc_ctx*, const DeviceSlot&, cudaStream_t, const double*, double*, int64_t, int64_t, int,
-                       const FilterPair&, int) { return JWC_ERR_UNSUPPORTED; }
+
+namespace {
+
+struct FwdPassArgs {
+  const double* in;   // V_{j0}
+  double* coeffs;     // coefficient block base
+  double* vout;       // V_{j0+k}
+  int64_t in_sig, coeff_sig, vout_sig;
+  int64_t N, Nd;
+  int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
+};
+
+template <int L, int R, bool WITH_W>
+__device__ __forceinline__ void fwd_item(const double* __restrict__ top, int s, const FilterPair& f, double (&av)[R],
+                                         double (&aw)[R]) {
+#pragma unroll
+  for (int q = 0; q < R; q++) { av[q] = 0.0; aw[q] = 0.0; }
+  // rows R-1 down to -(L-1): every accumulator meets its taps in ascending m, the reference's order
+  const double* p = top;
+#pragma unroll
+  for (int i = R - 1; i >= -(L - 1); --i) {
+    const double x = *p;
+    p -= s;
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int m = q - i;
+      if (m >= 0 && m < L) {
+        av[q] = fma(x, f.f0[m], av[q]);
+        if (WITH_W) aw[q] = fma(x, f.f1[m], aw[q]);
+      }
+    }
+  }
 }
+
+template <int L, int R>
+__global__ void __launch_bounds__(512) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
+                                                             const __grid_constant__ FilterPair f) {
+  extern __shared__ __align__(128) double smem[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int P = 1 << a.logP;
+  double* V0 = smem;
+  double* V1 = V0 + a.vcap;
+  double* W0 = V1 + a.vcap;
+  double* W1 = W0 + P * a.T2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(W1 + P * a.T2);
+
+  int64_t bid = blockIdx.x;
+  const int ti = (int)(bid % a.tiles_i);
+  bid /= a.tiles_i;
+  const int pg = (int)(bid % a.groups);
+  const int64_t b = bid / a.groups;
+  const int64_t i0 = (int64_t)ti * a.T2;
+  const int tlen2 = (int)((a.Nd - i0 < a.T2) ? (a.Nd - i0) : a.T2);
+  const int ph0 = pg << a.logP;
+  const int64_t S0 = (int64_t)1 << a.j0;
+  const double* in_b = a.in + b * a.in_sig;
+  double* co_b = a.coeffs + b * a.coeff_sig;
+  double* vo_b = a.vout + b * a.vout_sig;
+  const int rows_in = a.Hp + tlen2;
+
+  // ---- load V_{j0}: decimated rows i0-Hp .. i0+tlen2-1 (circular), P phases each ---------------------------
+  if (a.mode == MODE_BULK) {
+    if (tid == 0) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int64_t g0 = i0 - a.Hp;  // even; Hp <= N guaranteed by the planner
+      ptx::mbar_expect_tx(bar, (uint32_t)rows_in * 8u);
+      if (g0 >= 0) {
+        ptx::bulk_g2s(V0, in_b + g0, (uint32_t)rows_in * 8u, bar);
+      } else {
+        const uint32_t head = (uint32_t)(-g0);
+        ptx::bulk_g2s(V0, in_b + (a.N + g0), head * 8u, bar);
+        ptx::bulk_g2s(V0 + head, in_b, ((uint32_t)rows_in - head) * 8u, bar);
+      }
+    }
+    ptx::mbar_wait(bar, 0);
+  } else if (a.mode == MODE_VEC2) {
+    const int hp2 = P >> 1;  // 16-byte chunks per row
+    const int chunks = rows_in * hp2;
+    for (int q = tid; q < chunks; q += nt) {
+      const int r = q / hp2, pp = (q - r * hp2) * 2;
+      int64_t i = (i0 - a.Hp + r) % a.Nd;
+      if (i < 0) i += a.Nd;
+      ptx::cp_async16(V0 + r * P + pp, in_b + i * S0 + ph0 + pp);
+    }
+    ptx::cp_async_commit_wait_all();
+    __syncthreads();
+  } else {
+    const int total = rows_in * P;
+    for (int e = tid; e < total; e += nt) {
+      const int r = e >> a.logP, p = e & (P - 1);
+      int64_t i = (i0 - a.Hp + r) % a.Nd;
+      if (i < 0) i += a.Nd;
+      V0[e] = in_b[i * S0 + ph0 + p];
+    }
+    __syncthreads();
+  }
+
+  // ---- k fused levels ---------------------------------------------------------------------------------------------
+  const int eW = P * a.Hp;  // first virtual position whose W / final V is an output of this tile
+  for (int jj = 1; jj <= a.k; jj++) {
+    const int sh = a.logP + jj - 1;
+    const int s = 1 << sh;
+    const int hrem = (L - 1) * ((1 << a.k) - (1 << jj));
+    const int e0 = P * (a.Hp - hrem);
+    const int len = P * (hrem + tlen2);
+    const double* vin = (jj & 1) ? V0 : V1;
+    double* vout = (jj & 1) ? V1 : V0;
+    double* wst = (jj & 1) ? W0 : W1;
+    const int rows = (len + s - 1) >> sh;
+    const int nrb = (rows + R - 1) / R;
+    const int items = nrb << sh;
+    for (int w = tid; w < items; w += nt) {
+      const int rb = w >> sh, c = w & (s - 1);
+      const int rel0 = ((rb * R) << sh) + c;
+      const double* top = vin + e0 + rel0 + ((R - 1) << sh);
+      double av[R], aw[R];
+      const bool need_w = (e0 + rel0 + ((R - 1) << sh)) >= eW;   // any row of the item inside the output tile
+      if (need_w) fwd_item<L, R, true>(top, s, f, av, aw);
+      else fwd_item<L, R, false>(top, s, f, av, aw);
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const int rel = rel0 + (q << sh);
+        if (rel < len) {
+          const int e = e0 + rel;
+          vout[e] = av[q];
+          if (e >= eW) wst[e - eW] = aw[q];
+        }
+      }
+    }
+    // ---- W_{j0+jj} tile leaves; the last level also ships V ----------------------------------------------------------
+    const int64_t wrow = (int64_t)(a.j0 + jj - 1) * a.N;
+    if (a.mode == MODE_BULK) {
+      ptx::fence_proxy_async();
+      if (tid == 0) ptx::bulk_wait_read<0>();  // the store issued one level ago has finished reading its staging tile
+      __syncthreads();
+      if (tid == 0) {
+        ptx::bulk_s2g(co_b + wrow + i0, wst, (uint32_t)tlen2 * 8u);
+        if (jj == a.k) ptx::bulk_s2g(vo_b + i0, vout + eW, (uint32_t)tlen2 * 8u);
+        ptx::bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      const int nv = (jj == a.k) ? 2 : 1;
+      for (int v = 0; v < nv; v++) {
+        const double* src = v ? (vout + eW) : wst;
+        double* dst = v ? vo_b : (co_b + wrow);
+        if (a.mode == MODE_VEC2) {
+          const int hp2 = P >> 1, chunks = tlen2 * hp2;
+          for (int q = tid; q < chunks; q += nt) {
+            const int r = q / hp2, pp = (q - r * hp2) * 2;
+            const double2 val = *reinterpret_cast<const double2*>(src + r * P + pp);
+            *reinterpret_cast<double2*>(dst + (i0 + r) * S0 + ph0 + pp) = val;
+          }
+        } else {
+          const int total = tlen2 * P;
+          for (int e = tid; e < total; e += nt) {
+            const int r = e >> a.logP, p = e & (P - 1);
+            dst[(i0 + r) * S0 + ph0 + p] = src[e];
+          }
+        }
+      }
+    }
+  }
+  if (a.mode == MODE_BULK && tid == 0) ptx::bulk_wait_read<0>();
+}
+
+template <int L>
+int launch_fwd_pass(jwc_ctx* ctx, cudaStream_t st, const FwdPassArgs& a, const FilterPair& f, int threads, size_t smem,
+                    int64_t nblocks) {
+  auto kern = modwt_fwd_pass_kernel<L, kModwtR>;
+  JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+int dispatch_fwd_pass(jwc_ctx* ctx, cudaStream_t st, const FwdPassArgs& a, const FilterPair& f, int L, int threads,
+                      size_t smem, int64_t nblocks) {
+  switch (L) {
+#define JWC_CASE(LL) case LL: return launch_fwd_pass<LL>(ctx, st, a, f, threads, smem, nblocks);
+    JWC_CASE(2) JWC_CASE(4) JWC_CASE(6) JWC_CASE(8) JWC_CASE(10) JWC_CASE(12) JWC_CASE(14) JWC_CASE(16) JWC_CASE(18)
+    JWC_CASE(20) JWC_CASE(22) JWC_CASE(24) JWC_CASE(26) JWC_CASE(28) JWC_CASE(30) JWC_CASE(32) JWC_CASE(34) JWC_CASE(36)
+    JWC_CASE(38) JWC_CASE(40)
+#undef JWC_CASE
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
+                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L) {
+  if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
+  if (levels > 30 || n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
+  ModwtPlanInput pin{};
+  pin.n = n; pin.J = levels; pin.L = L;
+  pin.aligned16 = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_coeffs)) & 15) == 0;
+  pin.smem_budget = ctx->tune.modwt_smem > 0 ? ctx->tune.modwt_smem : 75776;
+  if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
+  pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
+  pin.threads_override = ctx->tune.modwt_threads;
+  pin.inverse = false;
+  const ModwtPlan plan = modwt_plan(pin);
+  if (plan.passes.empty()) return JWC_ERR_UNSUPPORTED;
+
+  Scratch ws(st);
+  const int64_t cs = (int64_t)(levels + 1) * n;
+  const int npass = (int)plan.passes.size();
+  const bool need_scratch = !(plan.all_fused && npass == 1);
+  double* vbuf[2] = {nullptr, nullptr};
+  if (need_scratch) {
+    vbuf[0] = ws.get((size_t)batch * n);
+    if (npass >= 2 || !plan.all_fused) vbuf[1] = ws.get((size_t)batch * n);
+    if (!vbuf[0] || !vbuf[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+  }
+  const double* vin = d_x;
+  int64_t vin_sig = n;
+  for (int pi = 0; pi < npass; pi++) {
+    const ModwtPass& p = plan.passes[pi];
+    const bool last = plan.all_fused && pi == npass - 1;
+    FwdPassArgs a{};
+    a.in = vin; a.in_sig = vin_sig;
+    a.coeffs = d_coeffs; a.coeff_sig = cs;
+    if (last) { a.vout = d_coeffs + (int64_t)levels * n; a.vout_sig = cs; }
+    else { a.vout = vbuf[pi & 1]; a.vout_sig = n; }
+    a.N = n; a.Nd = n >> p.j0;
+    a.j0 = p.j0; a.k = p.k; a.logP = p.logP; a.T2 = p.T2; a.Hp = p.Hp;
+    a.tiles_i = (int)((a.Nd + p.T2 - 1) / p.T2);
+    a.groups = (int)(((int64_t)1 << p.j0) >> p.logP);
+    a.vcap = p.vcap; a.mode = p.mode;
+    const int64_t nblocks = (int64_t)a.tiles_i * a.groups * batch;
+    if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+    int rc = dispatch_fwd_pass(ctx, st, a, f, L, p.threads, p.smem, nblocks);
+    if (rc != JWC_OK) return rc;
+    vin = a.vout; vin_sig = a.vout_sig;
+  }
+  if (!plan.all_fused) {
+    // remaining levels on the per-level kernels, continuing from V_{generic_from}
+    return generic_modwt_forward_from(ctx, dev, st, vin, vin_sig, plan.generic_from + 1, d_coeffs, batch, n, levels, f, L);
+  }
+  return JWC_OK;
+}
+
+// ==================================================================================================================
+// inverse: levels j0+k down to j0+1 (reference: transforms/MODWTTransform.java:355-372 + adjoint convolution :703-716)
+//     V_{j-1}[t] = sum_m g~[m] V_j[(t + m 2^(j-1)) mod N]  +  sum_m h~[m] W_j[(t + m 2^(j-1)) mod N]
+// Same column scheme, mirrored: the halo is on the right, (L-1)(2^jj - 1) decimated samples for the level-jj inputs.
+// The k+1 input tiles are read from HBM once (bulk TMA copies, W_{jj-1} prefetched into the second W buffer while level
+// jj is computed), V ping-pongs in shared memory, one bulk store of the V_{j0} tile at the end: 8(k+2) B/sample.
+// ==================================================================================================================
+namespace {
+
+struct InvPassArgs {
+  const double* vin;     // V_{j0+k}
+  const double* coeffs;  // coefficient block base (rows W_1 .. W_J, V_J)
+  double* vout;          // V_{j0}
+  int64_t vin_sig, coeff_sig, vout_sig;
+  int64_t N, Nd;
+  int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
+};
+
+template <int L, int R>
+__device__ __forceinline__ void inv_item(const double* __restrict__ pv, const double* __restrict__ pw, int s,
+                                         const FilterPair& f, double (&out)[R]) {
+  double ag[R], ah[R];
+#pragma unroll
+  for (int q = 0; q < R; q++) { ag[q] = 0.0; ah[q] = 0.0; }
+  // rows 0 .. R+L-2 ascending: accumulator q meets tap m = i - q in ascending m (reference order)
+#pragma unroll
+  for (int i = 0; i < R + L - 1; ++i) {
+    const double xv = *pv, xw = *pw;
+    pv += s;
+    pw += s;
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int m = i - q;
+      if (m >= 0 && m < L) {
+        ag[q] = fma(xv, f.f0[m], ag[q]);
+        ah[q] = fma(xw, f.f1[m], ah[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < R; q++) out[q] = ag[q] + ah[q];   // :366-369: the two sums are added at the end
+}
+
+// rows [i_start, i_start + rows) of the decimated index (circular), P phases each, into dst (virtual layout r*P + p)
+__device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst, const double* src_b, int64_t i_start,
+                                               int rows, int ph0, uint64_t* bar, int tid, int nt) {
+  const int P = 1 << a.logP;
+  const int64_t S0 = (int64_t)1 << a.j0;
+  if (a.mode == MODE_BULK) {
+    if (tid == 0) {
+      // caller has armed `bar` with expect_tx for the total; split at the wrap point (single wrap: rows <= N)
+      const int64_t first = (a.N - i_start < rows) ? (a.N - i_start) : rows;
+      ptx::bulk_g2s(dst, src_b + i_start, (uint32_t)first * 8u, bar);
+      if (first < rows) ptx::bulk_g2s(dst + first, src_b, (uint32_t)(rows - first) * 8u, bar);
+    }
+  } else if (a.mode == MODE_VEC2) {
+    const int hp2 = P >> 1, chunks = rows * hp2;
+    for (int q = tid; q < chunks; q += nt) {
+      const int r = q / hp2, pp = (q - r * hp2) * 2;
+      const int64_t i = (i_start + r) % a.Nd;
+      ptx::cp_async16(dst + r * P + pp, src_b + i * S0 + ph0 + pp);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+    const int total = rows * P;
+    for (int e = tid; e < total; e += nt) {
+      const int r = e >> a.logP, p = e & (P - 1);
+      const int64_t i = (i_start + r) % a.Nd;
+      dst[e] = src_b[i * S0 + ph0 + p];
+    }
+  }
+}
+
+template <int L, int R>
+__global__ void __launch_bounds__(512) modwt_inv_pass_kernel(const __grid_constant__ InvPassArgs a,
+                                                             const __grid_constant__ FilterPair f) {
+  extern __shared__ __align__(128) double smem[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int P = 1 << a.logP;
+  auto Vb = [&](int i) { return smem + (i & 1) * a.vcap; };
+  auto Wb = [&](int i) { return smem + (2 + (i & 1)) * a.vcap; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * (int64_t)a.vcap);
+
+  int64_t bid = blockIdx.x;
+  const int ti = (int)(bid % a.tiles_i);
+  bid /= a.tiles_i;
+  const int pg = (int)(bid % a.groups);
+  const int64_t b = bid / a.groups;
+  const int64_t i0 = (int64_t)ti * a.T2;
+  const int tlen2 = (int)((a.Nd - i0 < a.T2) ? (a.Nd - i0) : a.T2);
+  const int ph0 = pg << a.logP;
+  const int64_t S0 = (int64_t)1 << a.j0;
+  const double* vin_b = a.vin + b * a.vin_sig;
+  const double* co_b = a.coeffs + b * a.coeff_sig;
+  double* vo_b = a.vout + b * a.vout_sig;
+  const bool bulk = (a.mode == MODE_BULK);
+  // halo (decimated) needed by the level-jj inputs; in bulk mode rounded up to an even row count
+  auto halo = [&](int jj) { const int h = (L - 1) * ((1 << jj) - 1); return bulk ? h + (h & 1) : h; };
+
+  if (bulk) {
+    if (tid == 0) {
+      ptx::mbar_init(&bars[0], 1);
+      ptx::mbar_init(&bars[1], 1);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+  }
+  // prologue: V_{j0+k} and W_{j0+k}
+  {
+    const int rows = tlen2 + halo(a.k);
+    if (bulk && tid == 0) ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)rows * 8u);
+    inv_issue_load(a, Vb(0), vin_b, i0, rows, ph0, &bars[0], tid, nt);
+    inv_issue_load(a, Wb(0), co_b + (int64_t)(a.j0 + a.k - 1) * a.N, i0, rows, ph0, &bars[0], tid, nt);
+  }
+  for (int jj = a.k, u = 0; jj >= 1; --jj, ++u) {
+    const int wb = u & 1;
+    if (jj > 1) {  // prefetch W_{j0+jj-1} into the other W buffer (last read two barriers ago)
+      const int rows = tlen2 + halo(jj - 1);
+      if (bulk && tid == 0) ptx::mbar_expect_tx(&bars[wb ^ 1], (uint32_t)rows * 8u);
+      inv_issue_load(a, Wb(wb ^ 1), co_b + (int64_t)(a.j0 + jj - 2) * a.N, i0, rows, ph0, &bars[wb ^ 1], tid, nt);
+    }
+    if (bulk) {
+      ptx::mbar_wait(&bars[wb], (uint32_t)((u >> 1) & 1));
+    } else {
+      if (a.mode == MODE_VEC2) {
+        if (jj > 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+    }
+    const int sh = a.logP + jj - 1;
+    const int s = 1 << sh;
+    const int hout = (L - 1) * ((1 << (jj - 1)) - 1);   // halo the NEXT level still needs
+    const int len = P * (tlen2 + hout);
+    const double* v_in = Vb(u);
+    const double* w_in = Wb(wb);
+    double* v_out = Vb(u + 1);
+    const int rows = (len + s - 1) >> sh;
+    const int nrb = (rows + R - 1) / R;
+    const int items = nrb << sh;
+    for (int w = tid; w < items; w += nt) {
+      const int rb = w >> sh, c = w & (s - 1);
+      const int rel0 = ((rb * R) << sh) + c;
+      double o[R];
+      inv_item<L, R>(v_in + rel0, w_in + rel0, s, f, o);
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const int rel = rel0 + (q << sh);
+        if (rel < len) v_out[rel] = o[q];
+      }
+    }
+    if (bulk && jj == 1) ptx::fence_proxy_async();
+    __syncthreads();
+  }
+  // ---- V_{j0} tile leaves ---------------------------------------------------------------------------------------------
+  const double* res = Vb(a.k);
+  if (bulk) {
+    if (tid == 0) {
+      ptx::bulk_s2g(vo_b + i0, res, (uint32_t)tlen2 * 8u);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read<0>();
+    }
+  } else if (a.mode == MODE_VEC2) {
+    const int hp2 = P >> 1, chunks = tlen2 * hp2;
+    for (int q = tid; q < chunks; q += nt) {
+      const int r = q / hp2, pp = (q - r * hp2) * 2;
+      *reinterpret_cast<double2*>(vo_b + (i0 + r) * S0 + ph0 + pp) = *reinterpret_cast<const double2*>(res + r * P + pp);
+    }
+  } else {
+    const int total = tlen2 * P;
+    for (int e = tid; e < total; e += nt) {
+      const int r = e >> a.logP, p = e & (P - 1);
+      vo_b[(i0 + r) * S0 + ph0 + p] = res[e];
+    }
+  }
+}
+
+template <int L>
+int launch_inv_pass(jwc_ctx* ctx, cudaStream_t st, const InvPassArgs& a, const FilterPair& f, int threads, size_t smem,
+                    int64_t nblocks) {
+  auto kern = modwt_inv_pass_kernel<L, kModwtR>;
+  JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+int dispatch_inv_pass(jwc_ctx* ctx, cudaStream_t st, const InvPassArgs& a, const FilterPair& f, int L, int threads,
+                      size_t smem, int64_t nblocks) {
+  switch (L) {
+#define JWC_CASE(LL) case LL: return launch_inv_pass<LL>(ctx, st, a, f, threads, smem, nblocks);
+    JWC_CASE(2) JWC_CASE(4) JWC_CASE(6) JWC_CASE(8) JWC_CASE(10) JWC_CASE(12) JWC_CASE(14) JWC_CASE(16) JWC_CASE(18)
+    JWC_CASE(20) JWC_CASE(22) JWC_CASE(24) JWC_CASE(26) JWC_CASE(28) JWC_CASE(30) JWC_CASE(32) JWC_CASE(34) JWC_CASE(36)
+    JWC_CASE(38) JWC_CASE(40)
+#undef JWC_CASE
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
+                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L) {
+  if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
+  if (levels > 30 || n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
+  ModwtPlanInput pin{};
+  pin.n = n; pin.J = levels; pin.L = L;
+  pin.aligned16 = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_coeffs)) & 15) == 0;
+  pin.smem_budget = ctx->tune.modwt_smem > 0 ? ctx->tune.modwt_smem : 75776;
+  if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
+  pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
+  pin.threads_override = ctx->tune.modwt_threads;
+  pin.inverse = true;
+  const ModwtPlan plan = modwt_plan(pin);
+  // the inverse starts at the deepest level: it can only be fused if the whole chain is (no generic head)
+  if (plan.passes.empty() || !plan.all_fused) return JWC_ERR_UNSUPPORTED;
+
+  Scratch ws(st);
+  const int64_t cs = (int64_t)(levels + 1) * n;
+  const int npass = (int)plan.passes.size();
+  double* vbuf[2] = {nullptr, nullptr};
+  if (npass >= 2) {
+    vbuf[0] = ws.get((size_t)batch * n);
+    if (npass >= 3) vbuf[1] = ws.get((size_t)batch * n);
+    if (!vbuf[0] || (npass >= 3 && !vbuf[1])) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+  }
+  const double* vin = d_coeffs + (int64_t)levels * n;
+  int64_t vin_sig = cs;
+  for (int pi = npass - 1, step = 0; pi >= 0; --pi, ++step) {   // deepest pass first
+    const ModwtPass& p = plan.passes[pi];
+    InvPassArgs a{};
+    a.vin = vin; a.vin_sig = vin_sig;
+    a.coeffs = d_coeffs; a.coeff_sig = cs;
+    if (pi == 0) { a.vout = d_x; a.vout_sig = n; }
+    else { a.vout = vbuf[step & 1]; a.vout_sig = n; }
+    a.N = n; a.Nd = n >> p.j0;
+    a.j0 = p.j0; a.k = p.k; a.logP = p.logP; a.T2 = p.T2; a.Hp = p.Hp;
+    a.tiles_i = (int)((a.Nd + p.T2 - 1) / p.T2);
+    a.groups = (int)(((int64_t)1 << p.j0) >> p.logP);
+    a.vcap = p.vcap; a.mode = p.mode;
+    const int64_t nblocks = (int64_t)a.tiles_i * a.groups * batch;
+    if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+    int rc = dispatch_inv_pass(ctx, st, a, f, L, p.threads, p.smem, nblocks);
+    if (rc != JWC_OK) return rc;
+    vin = a.vout; vin_sig = a.vout_sig;
+  }
+  return JWC_OK;
+}
+
+}  // namespace jwc

@@ -1,0 +1,132 @@
+// jwc_modwt_plan.cuh -- how a J-level MODWT is cut into fused passes.
+//
+// A pass handles levels j0+1 .. j0+k of every signal on tiles that stay in shared memory.  Level j0+jj convolves with
+// stride 2^(j0+jj-1); seen on the 2^j0 phase subsequences n = i*2^j0 + ph of V_{j0} this is a stride-2^(jj-1)
+// convolution in the decimated index i, so a tile is  P phases x (T2 + halo) decimated samples  with halo
+// (L-1)(2^k - 1) decimated samples -- independent of j0.  That is what keeps the halo (and the redundant work on it)
+// small for long filters / deep levels (Daubechies20, J = 8: 9945 samples in one pass, 585 in each of two passes).
+// Pass boundaries cost one extra write + read of V (16 B/sample); the planner trades that against halo overhead with
+// a two-roof (HBM, fp64) time model.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace jwc {
+
+constexpr int kModwtR = 7;  // outputs per work item; odd => conflict-free LDS.64/STS.64 for every stride (see kernel)
+
+enum { MODE_BULK = 0, MODE_VEC2 = 1, MODE_SCALAR = 2 };
+
+struct ModwtPass {
+  int j0 = 0, k = 0, logP = 0, T2 = 0, Hp = 0, mode = MODE_SCALAR, vcap = 0, threads = 256;
+  size_t smem = 0;
+};
+
+struct ModwtPlan {
+  std::vector<ModwtPass> passes;
+  int generic_from = 0;  // levels > generic_from (1-based: generic_from+1 .. J) run on the per-level generic kernels; 0 = none... see below
+  bool all_fused = true;
+};
+
+struct ModwtPlanInput {
+  int64_t n;
+  int J, L;
+  bool aligned16;      // every base pointer 16-byte aligned
+  int smem_budget;     // bytes per CTA the plan may use
+  int tile_override, group_override, threads_override;
+  bool inverse;        // inverse needs (V ping-pong + W double buffer), forward (V ping-pong + W staging)
+};
+
+inline int64_t modwt_halo(int L, int k) { return (int64_t)(L - 1) * (((int64_t)1 << k) - 1); }
+
+// shared-memory doubles for one CTA of a pass
+inline int64_t modwt_smem_doubles(bool inverse, int P, int T2, int Hp, int k) {
+  const int64_t pad = (int64_t)kModwtR * P * ((int64_t)1 << (k - 1));
+  const int64_t vcap = (int64_t)P * (T2 + Hp) + pad;
+  if (inverse) return 4 * (vcap + (vcap & 1));                       // V0 V1 W0 W1, all tile+halo sized
+  return 2 * (vcap + (vcap & 1)) + 2 * (int64_t)P * T2;              // V0 V1 + two W staging tiles
+}
+
+inline bool modwt_make_pass(const ModwtPlanInput& in, int j0, int k, ModwtPass* out, double* est_time) {
+  const int64_t S0 = (int64_t)1 << j0;
+  if (j0 > 0 && (in.n % S0) != 0) return false;
+  const int64_t Nd = in.n >> j0;
+  int logP = 0;
+  if (j0 > 0) logP = std::min(j0, 2);   // 4 phases = 32-byte rows (one full sector) when available
+  const int P = 1 << logP;
+  int64_t H = modwt_halo(in.L, k);
+  int mode;
+  if (j0 == 0) mode = (in.aligned16 && (in.n % 2) == 0 && H + 1 <= in.n) ? MODE_BULK : MODE_SCALAR;
+  else mode = in.aligned16 ? MODE_VEC2 : MODE_SCALAR;
+  int64_t Hp = H + ((mode == MODE_BULK) ? (H & 1) : 0);
+  const int64_t budget = in.smem_budget / 8 - 8;
+  // largest even T2 that fits
+  int64_t lo = 2, hi = std::max<int64_t>(2, Nd + (Nd & 1)), best = 0;
+  if (in.tile_override > 0) hi = std::min<int64_t>(hi, in.tile_override);
+  if (modwt_smem_doubles(in.inverse, P, (int)hi, (int)Hp, k) <= budget) best = hi;
+  else {
+    while (lo <= hi) {
+      int64_t mid = ((lo + hi) / 2) & ~(int64_t)1;
+      if (mid < 2) mid = 2;
+      if (modwt_smem_doubles(in.inverse, P, (int)mid, (int)Hp, k) <= budget) { best = mid; lo = mid + 2; }
+      else hi = mid - 2;
+    }
+    if (best >= 128) best &= ~(int64_t)63;   // keep tiles 512-byte multiples
+  }
+  if (best < 2) return false;
+  if (best < Nd && best < 2 * H && in.tile_override <= 0) return false;  // halo would dominate the tile
+  out->j0 = j0; out->k = k; out->logP = logP; out->T2 = (int)best; out->Hp = (int)Hp; out->mode = mode;
+  const int64_t pad = (int64_t)kModwtR * P * ((int64_t)1 << (k - 1));
+  int64_t vcap = (int64_t)P * (best + Hp) + pad;
+  vcap += vcap & 1;
+  out->vcap = (int)vcap;
+  out->smem = (size_t)modwt_smem_doubles(in.inverse, P, (int)best, (int)Hp, k) * 8 + 64;
+  out->threads = in.threads_override > 0 ? in.threads_override : 256;
+  // two-roof time model per input sample (arbitrary units: seconds * 1e12)
+  const double T = (double)std::min<int64_t>(best, Nd);
+  double avg_hrem = 0;
+  for (int jj = 1; jj <= k; jj++) avg_hrem += (double)(in.L - 1) * (double)(((int64_t)1 << k) - ((int64_t)1 << jj));
+  avg_hrem /= k;
+  const double bytes = 8.0 * (k + 2) + 8.0 * (double)Hp / T * (in.inverse ? (k + 1) * 0.6 : 1.0);
+  const double flops = 4.0 * in.L * k * (1.0 + avg_hrem / T) / 0.8;   // ~80 % lane efficiency (item quantisation)
+  *est_time = std::max(bytes / 5.5, flops / 30.0);
+  return true;
+}
+
+// dynamic programme over pass boundaries; levels that cannot be fused (e.g. 2^j0 does not divide n) fall to the
+// generic per-level kernels (24 B/sample/level, no fusion).
+inline ModwtPlan modwt_plan(const ModwtPlanInput& in) {
+  const int J = in.J;
+  std::vector<double> best(J + 1, 1e300);
+  std::vector<int> choice(J + 1, 0);   // k > 0: fused pass of k levels; -1: everything from here generic
+  std::vector<ModwtPass> pass_at(J + 1);
+  best[J] = 0;
+  for (int j0 = J - 1; j0 >= 0; j0--) {
+    const double gen = 2.0 * 24.0 / 5.5 * (J - j0);
+    best[j0] = gen;
+    choice[j0] = -1;
+    const int kmax = in.group_override > 0 ? std::min(in.group_override, J - j0) : J - j0;
+    for (int k = 1; k <= kmax; k++) {
+      ModwtPass p;
+      double t;
+      if (!modwt_make_pass(in, j0, k, &p, &t)) continue;
+      if (t + best[j0 + k] < best[j0]) {
+        best[j0] = t + best[j0 + k];
+        choice[j0] = k;
+        pass_at[j0] = p;
+      }
+    }
+  }
+  ModwtPlan plan;
+  int j0 = 0;
+  while (j0 < J && choice[j0] > 0) {
+    plan.passes.push_back(pass_at[j0]);
+    j0 += choice[j0];
+  }
+  plan.generic_from = j0;          // levels j0+1 .. J (if any) are generic
+  plan.all_fused = (j0 == J);
+  return plan;
+}
+
+}  // namespace jwc

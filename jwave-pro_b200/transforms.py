@@ -78,10 +78,12 @@ class WaveletTransform(BasicTransform):
             raise RuntimeError("%s failed (%d): %s" % (fn_name, rc, _native.last_error()))
 
     def _call_dev(self, fn_name, d_src, d_dst, batch, n, levels, f0, f1, flags, stream=0, slot=0):
-        """Device-resident variant: d_src / d_dst are raw device addresses (e.g. torch.Tensor.data_ptr())."""
+        """Device-resident variant: d_src / d_dst are raw device addresses (e.g. torch.Tensor.data_ptr());
+        stream is a cudaStream_t handle.  0 means the legacy default stream (what torch's default stream is), passed
+        as cudaStreamLegacy (0x1) because a NULL stream asks the library for the context's own stream."""
         lib = _native.load()
         f0, f1 = _as_f64(f0), _as_f64(f1)
-        rc = getattr(lib, fn_name + "_dev")(self._context().handle, slot, ctypes.c_void_p(stream or None),
+        rc = getattr(lib, fn_name + "_dev")(self._context().handle, slot, ctypes.c_void_p(stream if stream else 1),
                                             ctypes.c_void_p(d_src), ctypes.c_void_p(d_dst), batch, n, levels,
                                             _ptr(f0), _ptr(f1), len(f0), flags)
         if rc != 0:
