@@ -14,6 +14,8 @@
 // window down the column, R + L - 1 LDS.64 for 2*R*L DFMA (taps are immediate constant-bank operands), so shared
 // memory bandwidth (128 B/clk/SM) stays below the fp64 pipe.  Lanes map to consecutive columns (s >= 16) or to
 // (column, row-block) pairs whose addresses are distinct mod 16 doubles because R is odd -> conflict-free for all s.
+#include <cstdlib>
+
 #include "jwc_internal.cuh"
 #include "jwc_modwt_plan.cuh"
 #include "jwc_tma.cuh"
@@ -21,6 +23,18 @@
 namespace jwc {
 
 namespace {
+
+// JWC_DEBUG=1 prints every plan once per distinct shape to stderr
+void debug_plan(const char* what, const ModwtPlan& plan, int64_t n, int levels, int L) {
+  static const bool on = getenv("JWC_DEBUG") != nullptr;
+  if (!on) return;
+  fprintf(stderr, "[jwc] %s n=%lld J=%d L=%d:", what, (long long)n, levels, L);
+  for (const ModwtPass& p : plan.passes)
+    fprintf(stderr, " [j0=%d k=%d P=%d T2=%d Hp=%d mode=%d smem=%zu thr=%d]", p.j0, p.k, 1 << p.logP, p.T2, p.Hp, p.mode,
+            p.smem, p.threads);
+  if (!plan.all_fused) fprintf(stderr, " generic from level %d", plan.generic_from + 1);
+  fprintf(stderr, "\n");
+}
 
 struct FwdPassArgs {
   const double* in;   // V_{j0}
@@ -31,39 +45,59 @@ struct FwdPassArgs {
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
 };
 
+// Long filters: 2L taps do not fit the uniform-register file (63 x 32 bit), and ptxas then feeds every DFMA through
+// LDC + R2UR moves.  For L > kUniformTapsMax the taps are read from a shared-memory copy (broadcast LDS.64) into a
+// rolling window of R live taps per filter, loaded exactly when the sliding window first needs them.
+constexpr int kUniformTapsMax = 10;
+constexpr int kTapDoubles = 2 * JWC_MAX_TAPS;   // shared-memory copy of FilterPair: f0 at [0..64), f1 at [64..128)
+
 template <int L, int R, bool WITH_W>
-__device__ __forceinline__ void fwd_item(const double* __restrict__ top, int s, const FilterPair& f, double (&av)[R],
-                                         double (&aw)[R]) {
+__device__ __forceinline__ void fwd_item(const double* __restrict__ top, int s, const FilterPair& f,
+                                         const double* __restrict__ taps, double (&av)[R], double (&aw)[R]) {
+  constexpr bool ST = (L > kUniformTapsMax);
 #pragma unroll
   for (int q = 0; q < R; q++) { av[q] = 0.0; aw[q] = 0.0; }
+  double tg[L], th[L];
   // rows R-1 down to -(L-1): every accumulator meets its taps in ascending m, the reference's order
   const double* p = top;
 #pragma unroll
   for (int i = R - 1; i >= -(L - 1); --i) {
+    if (ST) {
+      const int mn = R - 1 - i;   // the one tap index this row uses for the first time
+      if (mn < L) {
+        tg[mn] = taps[mn];
+        if (WITH_W) th[mn] = taps[JWC_MAX_TAPS + mn];
+      }
+    }
     const double x = *p;
     p -= s;
 #pragma unroll
     for (int q = 0; q < R; q++) {
       const int m = q - i;
       if (m >= 0 && m < L) {
-        av[q] = fma(x, f.f0[m], av[q]);
-        if (WITH_W) aw[q] = fma(x, f.f1[m], aw[q]);
+        av[q] = fma(x, ST ? tg[m] : f.f0[m], av[q]);
+        if (WITH_W) aw[q] = fma(x, ST ? th[m] : f.f1[m], aw[q]);
       }
     }
   }
 }
 
 template <int L, int R>
-__global__ void __launch_bounds__(512) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
+__global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
+  // shared memory is addressed as smem[int offset] everywhere: keeps the accesses plain LDS/STS with register offsets
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = 1 << a.logP;
-  double* V0 = smem;
-  double* V1 = V0 + a.vcap;
-  double* W0 = V1 + a.vcap;
-  double* W1 = W0 + P * a.T2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(W1 + P * a.T2);
+  const int oV1 = a.vcap, oW0 = 2 * a.vcap, oW1 = 2 * a.vcap + P * a.T2;
+  const int oT = oW1 + P * a.T2;                   // tap copy (kTapDoubles), then the mbarrier
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oT + kTapDoubles);
+  if (L > kUniformTapsMax) {
+    for (int t = threadIdx.x; t < JWC_MAX_TAPS; t += blockDim.x) {
+      smem[oT + t] = f.f0[t];
+      smem[oT + JWC_MAX_TAPS + t] = f.f1[t];
+    }
+  }
 
   int64_t bid = blockIdx.x;
   const int ti = (int)(bid % a.tiles_i);
@@ -84,20 +118,19 @@ __global__ void __launch_bounds__(512) modwt_fwd_pass_kernel(const __grid_consta
     if (tid == 0) {
       ptx::mbar_init(bar, 1);
       ptx::fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
       const int64_t g0 = i0 - a.Hp;  // even; Hp <= N guaranteed by the planner
       ptx::mbar_expect_tx(bar, (uint32_t)rows_in * 8u);
       if (g0 >= 0) {
-        ptx::bulk_g2s(V0, in_b + g0, (uint32_t)rows_in * 8u, bar);
+        ptx::bulk_g2s(smem, in_b + g0, (uint32_t)rows_in * 8u, bar);
       } else {
         const uint32_t head = (uint32_t)(-g0);
-        ptx::bulk_g2s(V0, in_b + (a.N + g0), head * 8u, bar);
-        ptx::bulk_g2s(V0 + head, in_b, ((uint32_t)rows_in - head) * 8u, bar);
+        ptx::bulk_g2s(smem, in_b + (a.N + g0), head * 8u, bar);
+        ptx::bulk_g2s(smem + head, in_b, ((uint32_t)rows_in - head) * 8u, bar);
       }
+      ptx::mbar_wait(bar, 0);   // one thread sleeps on the mbarrier, the CTA sleeps on the hardware barrier
     }
-    ptx::mbar_wait(bar, 0);
+    __syncthreads();
+    ptx::mbar_wait(bar, 0);     // already complete: every thread takes its own acquire on the TMA-written tile
   } else if (a.mode == MODE_VEC2) {
     const int hp2 = P >> 1;  // 16-byte chunks per row
     const int chunks = rows_in * hp2;
@@ -105,7 +138,7 @@ __global__ void __launch_bounds__(512) modwt_fwd_pass_kernel(const __grid_consta
       const int r = q / hp2, pp = (q - r * hp2) * 2;
       int64_t i = (i0 - a.Hp + r) % a.Nd;
       if (i < 0) i += a.Nd;
-      ptx::cp_async16(V0 + r * P + pp, in_b + i * S0 + ph0 + pp);
+      ptx::cp_async16(smem + r * P + pp, in_b + i * S0 + ph0 + pp);
     }
     ptx::cp_async_commit_wait_all();
     __syncthreads();
@@ -115,7 +148,7 @@ __global__ void __launch_bounds__(512) modwt_fwd_pass_kernel(const __grid_consta
       const int r = e >> a.logP, p = e & (P - 1);
       int64_t i = (i0 - a.Hp + r) % a.Nd;
       if (i < 0) i += a.Nd;
-      V0[e] = in_b[i * S0 + ph0 + p];
+      smem[e] = in_b[i * S0 + ph0 + p];
     }
     __syncthreads();
   }
@@ -128,46 +161,67 @@ __global__ void __launch_bounds__(512) modwt_fwd_pass_kernel(const __grid_consta
     const int hrem = (L - 1) * ((1 << a.k) - (1 << jj));
     const int e0 = P * (a.Hp - hrem);
     const int len = P * (hrem + tlen2);
-    const double* vin = (jj & 1) ? V0 : V1;
-    double* vout = (jj & 1) ? V1 : V0;
-    double* wst = (jj & 1) ? W0 : W1;
+    const int oin = (jj & 1) ? 0 : oV1;
+    const int oout = (jj & 1) ? oV1 : 0;
+    const int owst = ((jj & 1) ? oW0 : oW1) - eW;   // W staging indexed by virtual position
     const int rows = (len + s - 1) >> sh;
     const int nrb = (rows + R - 1) / R;
     const int items = nrb << sh;
+    const int span = (R - 1) << sh;
     for (int w = tid; w < items; w += nt) {
       const int rb = w >> sh, c = w & (s - 1);
       const int rel0 = ((rb * R) << sh) + c;
-      const double* top = vin + e0 + rel0 + ((R - 1) << sh);
+      const int ef = e0 + rel0;
+      const bool full = rel0 + span < len;
       double av[R], aw[R];
-      const bool need_w = (e0 + rel0 + ((R - 1) << sh)) >= eW;   // any row of the item inside the output tile
-      if (need_w) fwd_item<L, R, true>(top, s, f, av, aw);
-      else fwd_item<L, R, false>(top, s, f, av, aw);
+      if (ef + span < eW) {           // item entirely inside the halo: only V is needed by the next level
+        fwd_item<L, R, false>(smem + oin + ef + span, s, f, smem + oT, av, aw);
+        if (full) {
 #pragma unroll
-      for (int q = 0; q < R; q++) {
-        const int rel = rel0 + (q << sh);
-        if (rel < len) {
-          const int e = e0 + rel;
-          vout[e] = av[q];
-          if (e >= eW) wst[e - eW] = aw[q];
+          for (int q = 0; q < R; q++) smem[oout + ef + (q << sh)] = av[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < R; q++)
+            if (rel0 + (q << sh) < len) smem[oout + ef + (q << sh)] = av[q];
+        }
+      } else {
+        fwd_item<L, R, true>(smem + oin + ef + span, s, f, smem + oT, av, aw);
+        if (full && ef >= eW) {
+#pragma unroll
+          for (int q = 0; q < R; q++) {
+            smem[oout + ef + (q << sh)] = av[q];
+            smem[owst + ef + (q << sh)] = aw[q];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < R; q++) {
+            const int e = ef + (q << sh);
+            if (rel0 + (q << sh) < len) {
+              smem[oout + e] = av[q];
+              if (e >= eW) smem[owst + e] = aw[q];
+            }
+          }
         }
       }
     }
     // ---- W_{j0+jj} tile leaves; the last level also ships V ----------------------------------------------------------
     const int64_t wrow = (int64_t)(a.j0 + jj - 1) * a.N;
+    const double* wst = smem + owst + eW;
+    const double* vres = smem + oout + eW;
     if (a.mode == MODE_BULK) {
       ptx::fence_proxy_async();
       if (tid == 0) ptx::bulk_wait_read<0>();  // the store issued one level ago has finished reading its staging tile
       __syncthreads();
       if (tid == 0) {
         ptx::bulk_s2g(co_b + wrow + i0, wst, (uint32_t)tlen2 * 8u);
-        if (jj == a.k) ptx::bulk_s2g(vo_b + i0, vout + eW, (uint32_t)tlen2 * 8u);
+        if (jj == a.k) ptx::bulk_s2g(vo_b + i0, vres, (uint32_t)tlen2 * 8u);
         ptx::bulk_commit();
       }
     } else {
       __syncthreads();
       const int nv = (jj == a.k) ? 2 : 1;
       for (int v = 0; v < nv; v++) {
-        const double* src = v ? (vout + eW) : wst;
+        const double* src = v ? vres : wst;
         double* dst = v ? vo_b : (co_b + wrow);
         if (a.mode == MODE_VEC2) {
           const int hp2 = P >> 1, chunks = tlen2 * hp2;
@@ -228,6 +282,7 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   pin.inverse = false;
   const ModwtPlan plan = modwt_plan(pin);
   if (plan.passes.empty()) return JWC_ERR_UNSUPPORTED;
+  debug_plan("modwt forward", plan, n, levels, L);
 
   Scratch ws(st);
   const int64_t cs = (int64_t)(levels + 1) * n;
@@ -287,13 +342,19 @@ struct InvPassArgs {
 
 template <int L, int R>
 __device__ __forceinline__ void inv_item(const double* __restrict__ pv, const double* __restrict__ pw, int s,
-                                         const FilterPair& f, double (&out)[R]) {
+                                         const FilterPair& f, const double* __restrict__ taps, double (&out)[R]) {
+  constexpr bool ST = (L > kUniformTapsMax);
   double ag[R], ah[R];
 #pragma unroll
   for (int q = 0; q < R; q++) { ag[q] = 0.0; ah[q] = 0.0; }
+  double tg[L], th[L];
   // rows 0 .. R+L-2 ascending: accumulator q meets tap m = i - q in ascending m (reference order)
 #pragma unroll
   for (int i = 0; i < R + L - 1; ++i) {
+    if (ST && i < L) {   // tap i is first needed at row i (by accumulator 0)
+      tg[i] = taps[i];
+      th[i] = taps[JWC_MAX_TAPS + i];
+    }
     const double xv = *pv, xw = *pw;
     pv += s;
     pw += s;
@@ -301,8 +362,8 @@ __device__ __forceinline__ void inv_item(const double* __restrict__ pv, const do
     for (int q = 0; q < R; q++) {
       const int m = i - q;
       if (m >= 0 && m < L) {
-        ag[q] = fma(xv, f.f0[m], ag[q]);
-        ah[q] = fma(xw, f.f1[m], ah[q]);
+        ag[q] = fma(xv, ST ? tg[m] : f.f0[m], ag[q]);
+        ah[q] = fma(xw, ST ? th[m] : f.f1[m], ah[q]);
       }
     }
   }
@@ -341,14 +402,21 @@ __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst
 }
 
 template <int L, int R>
-__global__ void __launch_bounds__(512) modwt_inv_pass_kernel(const __grid_constant__ InvPassArgs a,
+__global__ void __launch_bounds__(256, 3) modwt_inv_pass_kernel(const __grid_constant__ InvPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = 1 << a.logP;
-  auto Vb = [&](int i) { return smem + (i & 1) * a.vcap; };
+  auto Vb = [&](int i) { return smem + (i & 1) * a.vcap; };          // always "smem + int": plain LDS/STS addressing
   auto Wb = [&](int i) { return smem + (2 + (i & 1)) * a.vcap; };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * (int64_t)a.vcap);
+  const int oT = 4 * a.vcap;                       // tap copy (kTapDoubles), then the two mbarriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oT + kTapDoubles);
+  if (L > kUniformTapsMax) {
+    for (int t = threadIdx.x; t < JWC_MAX_TAPS; t += blockDim.x) {
+      smem[oT + t] = f.f0[t];
+      smem[oT + JWC_MAX_TAPS + t] = f.f1[t];
+    }
+  }
 
   int64_t bid = blockIdx.x;
   const int ti = (int)(bid % a.tiles_i);
@@ -389,7 +457,10 @@ __global__ void __launch_bounds__(512) modwt_inv_pass_kernel(const __grid_consta
       inv_issue_load(a, Wb(wb ^ 1), co_b + (int64_t)(a.j0 + jj - 2) * a.N, i0, rows, ph0, &bars[wb ^ 1], tid, nt);
     }
     if (bulk) {
-      ptx::mbar_wait(&bars[wb], (uint32_t)((u >> 1) & 1));
+      const uint32_t par = (uint32_t)((u >> 1) & 1);
+      if (tid == 0) ptx::mbar_wait(&bars[wb], par);   // one sleeper on the mbarrier, the rest on the hardware barrier
+      __syncthreads();
+      ptx::mbar_wait(&bars[wb], par);                 // complete already: per-thread acquire of the TMA-written tiles
     } else {
       if (a.mode == MODE_VEC2) {
         if (jj > 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -401,21 +472,23 @@ __global__ void __launch_bounds__(512) modwt_inv_pass_kernel(const __grid_consta
     const int s = 1 << sh;
     const int hout = (L - 1) * ((1 << (jj - 1)) - 1);   // halo the NEXT level still needs
     const int len = P * (tlen2 + hout);
-    const double* v_in = Vb(u);
-    const double* w_in = Wb(wb);
-    double* v_out = Vb(u + 1);
+    const int ovin = (u & 1) * a.vcap, owin = (2 + wb) * a.vcap, ovout = ((u + 1) & 1) * a.vcap;
     const int rows = (len + s - 1) >> sh;
     const int nrb = (rows + R - 1) / R;
     const int items = nrb << sh;
+    const int span = (R - 1) << sh;
     for (int w = tid; w < items; w += nt) {
       const int rb = w >> sh, c = w & (s - 1);
       const int rel0 = ((rb * R) << sh) + c;
       double o[R];
-      inv_item<L, R>(v_in + rel0, w_in + rel0, s, f, o);
+      inv_item<L, R>(smem + ovin + rel0, smem + owin + rel0, s, f, smem + oT, o);
+      if (rel0 + span < len) {
 #pragma unroll
-      for (int q = 0; q < R; q++) {
-        const int rel = rel0 + (q << sh);
-        if (rel < len) v_out[rel] = o[q];
+        for (int q = 0; q < R; q++) smem[ovout + rel0 + (q << sh)] = o[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < R; q++)
+          if (rel0 + (q << sh) < len) smem[ovout + rel0 + (q << sh)] = o[q];
       }
     }
     if (bulk && jj == 1) ptx::fence_proxy_async();
@@ -484,6 +557,7 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   const ModwtPlan plan = modwt_plan(pin);
   // the inverse starts at the deepest level: it can only be fused if the whole chain is (no generic head)
   if (plan.passes.empty() || !plan.all_fused) return JWC_ERR_UNSUPPORTED;
+  debug_plan("modwt inverse", plan, n, levels, L);
 
   Scratch ws(st);
   const int64_t cs = (int64_t)(levels + 1) * n;

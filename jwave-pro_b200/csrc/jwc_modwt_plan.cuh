@@ -48,19 +48,38 @@ inline int64_t modwt_smem_doubles(bool inverse, int P, int T2, int Hp, int k) {
   return 2 * (vcap + (vcap & 1)) + 2 * (int64_t)P * T2;              // V0 V1 + two W staging tiles
 }
 
-inline bool modwt_make_pass(const ModwtPlanInput& in, int j0, int k, ModwtPass* out, double* est_time) {
+// work items of level jj (1-based inside the pass) for a full tile, see the kernels' item loops
+inline int64_t modwt_items(bool inverse, int L, int k, int jj, int logP, int T2) {
+  const int64_t P = (int64_t)1 << logP, s = P << (jj - 1);
+  const int64_t halo = inverse ? (int64_t)(L - 1) * (((int64_t)1 << (jj - 1)) - 1)
+                               : (int64_t)(L - 1) * (((int64_t)1 << k) - ((int64_t)1 << jj));
+  const int64_t len = P * (T2 + halo);
+  const int64_t rows = (len + s - 1) / s;
+  return ((rows + kModwtR - 1) / kModwtR) * s;
+}
+
+// fraction of thread-rounds doing useful items when `threads` threads share the items of every level
+inline double modwt_lane_efficiency(bool inverse, int L, int k, int logP, int T2, int threads) {
+  double useful = 0, issued = 0;
+  for (int jj = 1; jj <= k; jj++) {
+    const int64_t it = modwt_items(inverse, L, k, jj, logP, T2);
+    useful += (double)it;
+    issued += (double)(((it + threads - 1) / threads) * threads);
+  }
+  return issued > 0 ? useful / issued : 1.0;
+}
+
+inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP, ModwtPass* out, double* est_time) {
   const int64_t S0 = (int64_t)1 << j0;
   if (j0 > 0 && (in.n % S0) != 0) return false;
   const int64_t Nd = in.n >> j0;
-  int logP = 0;
-  if (j0 > 0) logP = std::min(j0, 2);   // 4 phases = 32-byte rows (one full sector) when available
   const int P = 1 << logP;
   int64_t H = modwt_halo(in.L, k);
   int mode;
   if (j0 == 0) mode = (in.aligned16 && (in.n % 2) == 0 && H + 1 <= in.n) ? MODE_BULK : MODE_SCALAR;
-  else mode = in.aligned16 ? MODE_VEC2 : MODE_SCALAR;
+  else mode = (in.aligned16 && logP >= 1) ? MODE_VEC2 : MODE_SCALAR;
   int64_t Hp = H + ((mode == MODE_BULK) ? (H & 1) : 0);
-  const int64_t budget = in.smem_budget / 8 - 8;
+  const int64_t budget = in.smem_budget / 8 - 8 - 128;   // mbarriers + shared-memory tap copy
   // largest even T2 that fits
   int64_t lo = 2, hi = std::max<int64_t>(2, Nd + (Nd & 1)), best = 0;
   if (in.tile_override > 0) hi = std::min<int64_t>(hi, in.tile_override);
@@ -75,23 +94,58 @@ inline bool modwt_make_pass(const ModwtPlanInput& in, int j0, int k, ModwtPass* 
     if (best >= 128) best &= ~(int64_t)63;   // keep tiles 512-byte multiples
   }
   if (best < 2) return false;
-  if (best < Nd && best < 2 * H && in.tile_override <= 0) return false;  // halo would dominate the tile
+  if (best < Nd && best < H && in.tile_override <= 0) return false;  // halo would dominate the tile
   out->j0 = j0; out->k = k; out->logP = logP; out->T2 = (int)best; out->Hp = (int)Hp; out->mode = mode;
   const int64_t pad = (int64_t)kModwtR * P * ((int64_t)1 << (k - 1));
   int64_t vcap = (int64_t)P * (best + Hp) + pad;
   vcap += vcap & 1;
   out->vcap = (int)vcap;
-  out->smem = (size_t)modwt_smem_doubles(in.inverse, P, (int)best, (int)Hp, k) * 8 + 64;
-  out->threads = in.threads_override > 0 ? in.threads_override : 256;
-  // two-roof time model per input sample (arbitrary units: seconds * 1e12)
-  const double T = (double)std::min<int64_t>(best, Nd);
+  out->smem = (size_t)modwt_smem_doubles(in.inverse, P, (int)best, (int)Hp, k) * 8 + 1024 + 64;
+  // threads: the candidate with the best lane efficiency (ties -> more threads)
+  const int Tfull = (int)std::min<int64_t>(best, Nd);
+  int thr = 256;
+  double eff = 0;
+  if (in.threads_override > 0) {
+    thr = in.threads_override;
+    eff = modwt_lane_efficiency(in.inverse, in.L, k, logP, Tfull, thr);
+  } else {
+    for (int cand = 256; cand >= 128; cand -= 32) {
+      const double e = modwt_lane_efficiency(in.inverse, in.L, k, logP, Tfull, cand);
+      if (e > eff + 0.02) { eff = e; thr = cand; }
+    }
+  }
+  out->threads = thr;
+  // time model per input sample (units: ps): memory and fp64 overlap only partly inside a CTA, short passes worst
+  const double T = (double)Tfull;
   double avg_hrem = 0;
-  for (int jj = 1; jj <= k; jj++) avg_hrem += (double)(in.L - 1) * (double)(((int64_t)1 << k) - ((int64_t)1 << jj));
+  for (int jj = 1; jj <= k; jj++)
+    avg_hrem += in.inverse ? (double)(in.L - 1) * (double)(((int64_t)1 << (jj - 1)) - 1)
+                           : (double)(in.L - 1) * (double)(((int64_t)1 << k) - ((int64_t)1 << jj));
   avg_hrem /= k;
-  const double bytes = 8.0 * (k + 2) + 8.0 * (double)Hp / T * (in.inverse ? (k + 1) * 0.6 : 1.0);
-  const double flops = 4.0 * in.L * k * (1.0 + avg_hrem / T) / 0.8;   // ~80 % lane efficiency (item quantisation)
-  *est_time = std::max(bytes / 5.5, flops / 30.0);
+  const double sector = (j0 == 0) ? 1.0 : (P >= 4 ? 1.0 : (P == 2 ? 1.6 : 2.5));   // strided 16 B / 8 B rows waste sectors
+  const double bytes = sector * (8.0 * (k + 2) + 8.0 * (double)Hp / T * (in.inverse ? (k + 1) * 0.6 : 1.0));
+  const double flops = 4.0 * in.L * k * (1.0 + avg_hrem / T) / std::max(eff, 0.3);
+  const double tm = bytes / 5.5, tc = flops / 32.0;
+  *est_time = std::max(tm, tc) + 0.35 * std::min(tm, tc) + 2.0;
   return true;
+}
+
+inline bool modwt_make_pass(const ModwtPlanInput& in, int j0, int k, ModwtPass* out, double* est_time) {
+  if (j0 == 0) return modwt_make_pass_p(in, j0, k, 0, out, est_time);
+  bool ok = false;
+  double bt = 1e300;
+  for (int logP = std::min(j0, 2); logP >= 1; --logP) {   // 4 phases (32-byte rows) or 2 (16-byte rows)
+    ModwtPass p;
+    double t;
+    if (modwt_make_pass_p(in, j0, k, logP, &p, &t) && t < bt) { bt = t; *out = p; ok = true; }
+  }
+  if (!ok) {   // last resort: single phase, scalar gathers
+    ModwtPass p;
+    double t;
+    if (modwt_make_pass_p(in, j0, k, 0, &p, &t)) { bt = t; *out = p; ok = true; }
+  }
+  *est_time = bt;
+  return ok;
 }
 
 // dynamic programme over pass boundaries; levels that cannot be fused (e.g. 2^j0 does not divide n) fall to the
