@@ -337,6 +337,7 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "dwt_tile")) return &t.dwt_tile;
   if (!strcmp(key, "dwt_threads")) return &t.dwt_threads;
   if (!strcmp(key, "dwt_group")) return &t.dwt_group;
+  if (!strcmp(key, "dwt_smem")) return &t.dwt_smem;
   if (!strcmp(key, "h2d_chunk_mb")) return &t.h2d_chunk_mb;
   if (!strcmp(key, "force_generic")) return &t.force_generic;
   return nullptr;

@@ -1,8 +1,569 @@
-// placeholder until the fused kernels land
+// jwc_dwt_fast.cu -- fused multi-level decimated filter bank on shared-memory tiles: FWT pyramid and WPT full tree.
+//
+// Reference (paths relative to /root/reference/src/main/java/jwave/):
+//   one analysis step   transforms/wavelets/Wavelet.java:236-260   lo[i] = sum_j x[(2i+j) mod h] s[j], hi likewise
+//   one synthesis step  transforms/wavelets/Wavelet.java:277-303   out[(2i+j) mod h] += c[i] sR[j] + c[i+h/2] wR[j]
+//   FWT level loops     transforms/FastWaveletTransform.java:85-99, 133-151   (prefix h = N, N/2, ...)
+//   WPT level loops     transforms/WaveletPacketTransform.java:98-120, 167-187 (every block of length h)
+//
+// A pass carries one tile of one node k levels down (forward) or up (inverse) without leaving shared memory; see
+// jwc_dwt_plan.cuh for the geometry.  HBM traffic per pass: the tile is read once (1-D bulk TMA copies, periodic
+// wrap = the copy is split at the node boundary) and every coefficient is written once (bulk stores).
+//
+// Inner loops: one work item = R consecutive outputs of one node.
+//   analysis:  reads R + L/2 - 1 aligned sample pairs (LDS.128), 2*R*L DFMA -> R low-pass + R high-pass outputs
+//   synthesis: reads R + L/2 - 1 (lo, hi) coefficient pairs (2 x LDS.64), 2*R*L DFMA -> R output pairs (STS.128)
+// R is odd, so the lane stride (R x 16 B resp. R x 8 B) maps the lanes of every quarter/half warp to distinct banks.
+#include <cstdlib>
+
+#include "jwc_dwt_plan.cuh"
 #include "jwc_internal.cuh"
+#include "jwc_tma.cuh"
+
 namespace jwc {
-int fast_dwt_forward(jwc_ctx*, const DeviceSlot&, cudaStream_t, const double*, double*, int64_t, int64_t, int,
-                     const FilterPair&, int, bool) { return JWC_ERR_UNSUPPORTED; }
-int fast_dwt_inverse(jwc_ctx*, const DeviceSlot&, cudaStream_t, const double*, double*, int64_t, int64_t, int,
-                     const FilterPair&, int, bool) { return JWC_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int kUniformTapsMaxDwt = 10;   // longer filters read their taps from a shared-memory copy (see MODWT kernel)
+
+void debug_dwt_plan(const char* what, const DwtPlan& plan, int64_t n, int levels, int L, bool tree) {
+  static const bool on = getenv("JWC_DEBUG") != nullptr;
+  if (!on) return;
+  fprintf(stderr, "[jwc] %s %s n=%lld levels=%d L=%d:", tree ? "wpt" : "fwt", what, (long long)n, levels, L);
+  for (const DwtPass& p : plan.passes)
+    fprintf(stderr, " [l0=%d k=%d T=%d cap=%d mode=%d smem=%zu thr=%d]", p.l0, p.k, p.T, p.cap, p.mode, p.smem, p.threads);
+  fprintf(stderr, "\n");
 }
+
+struct DwtPassArgs {
+  const double* in;    // forward: nodes at depth l0; inverse: coefficient source of the children (see below)
+  const double* ain;   // inverse FWT only: A_{l0+k}
+  double* out;         // forward: D / leaf destination (final layout); inverse: depth-l0 node destination
+  double* aout;        // forward FWT only: A_{l0+k} destination
+  int64_t in_sig, ain_sig, out_sig, aout_sig;   // signal strides
+  int64_t N;           // full signal length
+  int64_t h;           // node length at depth l0 (= N >> l0)
+  int l0, k, T, tiles, nodes, cap, mode;
+};
+
+// circular bulk load of `len` doubles starting at node position `start` (may be negative, |start| <= hn) of a node of
+// length hn at `base` into dst.  One thread; the mbarrier must already expect the bytes.
+__device__ __forceinline__ void bulk_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
+                                               uint64_t* bar) {
+  int64_t pos = start;
+  if (pos < 0) pos += hn;
+  int done = 0;
+  while (done < len) {
+    int64_t run = hn - pos;
+    if (run > len - done) run = len - done;
+    ptx::bulk_g2s(dst + done, base + pos, (uint32_t)run * 8u, bar);
+    done += (int)run;
+    pos = 0;
+  }
+}
+
+__device__ __forceinline__ void scalar_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
+                                                 int tid, int nt) {
+  for (int e = tid; e < len; e += nt) {
+    int64_t pos = (start + e) % hn;
+    if (pos < 0) pos += hn;
+    dst[e] = base[pos];
+  }
+}
+
+// =========================================================================================================================
+// forward (analysis)
+// =========================================================================================================================
+template <int L, int R, bool WITH_HI>
+__device__ __forceinline__ void ana_item(const double2* __restrict__ px, const FilterPair& f, const double* __restrict__ taps,
+                                         double (&lo)[R], double (&hi)[R]) {
+  constexpr bool ST = (L > kUniformTapsMaxDwt);
+  constexpr int HL = L / 2;
+#pragma unroll
+  for (int r = 0; r < R; r++) { lo[r] = 0.0; hi[r] = 0.0; }
+  double ts[L], tw[L];
+#pragma unroll
+  for (int pp = 0; pp < R + HL - 1; ++pp) {
+    if (ST && pp < HL) {   // taps 2pp, 2pp+1 are first needed by output 0 at pair pp
+      ts[2 * pp] = taps[2 * pp];
+      ts[2 * pp + 1] = taps[2 * pp + 1];
+      if (WITH_HI) {
+        tw[2 * pp] = taps[JWC_MAX_TAPS + 2 * pp];
+        tw[2 * pp + 1] = taps[JWC_MAX_TAPS + 2 * pp + 1];
+      }
+    }
+    const double2 x = px[pp];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int q = pp - r;   // tap pair index: j = 2q, 2q+1 (ascending j per output, the reference's order)
+      if (q >= 0 && q < HL) {
+        lo[r] = fma(x.x, ST ? ts[2 * q] : f.f0[2 * q], lo[r]);
+        lo[r] = fma(x.y, ST ? ts[2 * q + 1] : f.f0[2 * q + 1], lo[r]);
+        if (WITH_HI) {
+          hi[r] = fma(x.x, ST ? tw[2 * q] : f.f1[2 * q], hi[r]);
+          hi[r] = fma(x.y, ST ? tw[2 * q + 1] : f.f1[2 * q + 1], hi[r]);
+        }
+      }
+    }
+  }
+}
+
+template <int L, int R, bool TREE>
+__global__ void __launch_bounds__(256, 2) dwt_fwd_pass_kernel(const __grid_constant__ DwtPassArgs a,
+                                                              const __grid_constant__ FilterPair f) {
+  extern __shared__ __align__(128) double smem[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int oT = 2 * a.cap;                         // tap copy, then the mbarrier
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
+  if (L > kUniformTapsMaxDwt) {
+    for (int t = tid; t < JWC_MAX_TAPS; t += nt) {
+      smem[oT + t] = f.f0[t];
+      smem[oT + JWC_MAX_TAPS + t] = f.f1[t];
+    }
+  }
+  int64_t bid = blockIdx.x;
+  const int ti = (int)(bid % a.tiles);
+  bid /= a.tiles;
+  const int p = (int)(bid % a.nodes);
+  const int64_t b = bid / a.nodes;
+  const int tlen = (int)((a.h < a.T) ? a.h : a.T);
+  const int64_t a0 = (int64_t)ti * tlen;
+  const double* node = a.in + b * a.in_sig + (int64_t)p * a.h;
+  const bool bulk = (a.mode == DWT_BULK);
+  const int H = (L - 2) * ((1 << a.k) - 1);
+
+  // ---- load: node samples a0 .. a0 + tlen + H - 1 (periodic) ---------------------------------------------------------
+  if (bulk) {
+    if (tid == 0) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_mbar_init();
+      ptx::mbar_expect_tx(bar, (uint32_t)(tlen + H) * 8u);
+      bulk_load_circ(smem, node, a0, tlen + H, a.h, bar);
+      ptx::mbar_wait(bar, 0);
+    }
+    __syncthreads();
+    ptx::mbar_wait(bar, 0);
+  } else {
+    scalar_load_circ(smem, node, a0, tlen + H, a.h, tid, nt);
+    __syncthreads();
+  }
+
+  // ---- k levels ---------------------------------------------------------------------------------------------------------
+  for (int jj = 1; jj <= a.k; jj++) {
+    const int oin = (jj & 1) ? 0 : a.cap, oout = (jj & 1) ? a.cap : 0;
+    const int halo_in = (L - 2) * ((1 << (a.k - jj + 1)) - 1), halo_out = (L - 2) * ((1 << (a.k - jj)) - 1);
+    const int len_in = (tlen >> (jj - 1)) + halo_in, len_out = (tlen >> jj) + halo_out;
+    const int st_in = len_in + (len_in & 1) + 2 * R, st_out = len_out + (len_out & 1) + 2 * R;
+    const int own = tlen >> jj;                       // outputs of each child that belong to this tile
+    const int parents = TREE ? (1 << (jj - 1)) : 1;
+    const int nb = (len_out + R - 1) / R;
+    const int items = parents * nb;
+    for (int w = tid; w < items; w += nt) {
+      const int q = TREE ? (w / nb) : 0;
+      const int i0 = (w - q * nb) * R;
+      const double2* px = reinterpret_cast<const double2*>(smem + oin + q * st_in) + i0;
+      double lo[R], hi[R];
+      const int olo = oout + (2 * q) * st_out + i0, ohi = olo + st_out;
+      const bool full = i0 + R <= len_out;
+      if (!TREE && i0 >= own) {   // FWT: the halo part of D is produced by the neighbouring tile
+        ana_item<L, R, false>(px, f, smem + oT, lo, hi);
+        if (full) {
+#pragma unroll
+          for (int r = 0; r < R; r++) smem[olo + r] = lo[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            if (i0 + r < len_out) smem[olo + r] = lo[r];
+        }
+      } else {
+        ana_item<L, R, true>(px, f, smem + oT, lo, hi);
+        if (full) {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            smem[olo + r] = lo[r];
+            smem[ohi + r] = hi[r];
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            if (i0 + r < len_out) {
+              smem[olo + r] = lo[r];
+              smem[ohi + r] = hi[r];
+            }
+        }
+      }
+    }
+    // ---- ship what is final after this level ------------------------------------------------------------------------------
+    const bool last = (jj == a.k);
+    const bool vec_ok = bulk && (own & 1) == 0;
+    if (vec_ok) ptx::fence_proxy_async();
+    if (bulk && tid < 32) ptx::bulk_wait_read<0>();   // stores issued one level ago have finished reading this buffer pair
+    __syncthreads();
+    if (!TREE) {
+      // D_{l0+jj}: owned prefix of the high-pass child -> out[(N >> (l0+jj)) + (a0 >> jj) ...]
+      const double* src = smem + oout + st_out;
+      double* dst = a.out + b * a.out_sig + (a.N >> (a.l0 + jj)) + (a0 >> jj);
+      if (vec_ok) {
+        if (tid == 0) {
+          ptx::bulk_s2g(dst, src, (uint32_t)own * 8u);
+          if (last) ptx::bulk_s2g(a.aout + b * a.aout_sig + (a0 >> jj), smem + oout, (uint32_t)own * 8u);
+          ptx::bulk_commit();
+        }
+      } else {
+        for (int e = tid; e < own; e += nt) dst[e] = src[e];
+        if (last) {
+          double* ad = a.aout + b * a.aout_sig + (a0 >> jj);
+          for (int e = tid; e < own; e += nt) ad[e] = smem[oout + e];
+        }
+      }
+    } else if (last) {
+      // 2^k leaves in natural (Paley) order: leaf c of this node lives at node_base + c * (h >> k)
+      const int leaves = 1 << a.k;
+      double* dst0 = a.out + b * a.out_sig + (int64_t)p * a.h + (a0 >> a.k);
+      const int64_t leaf_stride = a.h >> a.k;
+      if (vec_ok) {
+        if (tid < 32) {
+          for (int c = tid; c < leaves; c += 32) ptx::bulk_s2g(dst0 + c * leaf_stride, smem + oout + c * st_out, (uint32_t)own * 8u);
+          ptx::bulk_commit();
+        }
+      } else {
+        for (int e = tid; e < leaves * own; e += nt) {
+          const int c = e / own, i = e - c * own;
+          dst0[c * leaf_stride + i] = smem[oout + c * st_out + i];
+        }
+      }
+    }
+  }
+  if (bulk && tid < 32) ptx::bulk_wait_read<0>();
+}
+
+// =========================================================================================================================
+// inverse (synthesis)
+// =========================================================================================================================
+template <int L, int R>
+__device__ __forceinline__ void syn_item(const double* __restrict__ plo, const double* __restrict__ phi,
+                                         const FilterPair& f, const double* __restrict__ taps, double2 (&o)[R]) {
+  constexpr bool ST = (L > kUniformTapsMaxDwt);
+  constexpr int HL = L / 2;
+#pragma unroll
+  for (int r = 0; r < R; r++) { o[r].x = 0.0; o[r].y = 0.0; }
+  double ts[L], tw[L];
+  // children ascending (the reference adds the contributions to one output in ascending child index):
+  // child i feeds output pair r with tap pair q = r + HL - 1 - i
+#pragma unroll
+  for (int i = 0; i < R + HL - 1; ++i) {
+    if (ST) {
+      const int qn = HL - 1 - i;   // the new (smallest so far) tap pair when i < HL
+      if (qn >= 0) {
+        ts[2 * qn] = taps[2 * qn];
+        ts[2 * qn + 1] = taps[2 * qn + 1];
+        tw[2 * qn] = taps[JWC_MAX_TAPS + 2 * qn];
+        tw[2 * qn + 1] = taps[JWC_MAX_TAPS + 2 * qn + 1];
+      }
+    }
+    const double cl = plo[i], ch = phi[i];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int q = r + HL - 1 - i;
+      if (q >= 0 && q < HL) {
+        o[r].x = fma(ch, ST ? tw[2 * q] : f.f1[2 * q], fma(cl, ST ? ts[2 * q] : f.f0[2 * q], o[r].x));
+        o[r].y = fma(ch, ST ? tw[2 * q + 1] : f.f1[2 * q + 1], fma(cl, ST ? ts[2 * q + 1] : f.f0[2 * q + 1], o[r].y));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int inv_halo(int L, int jj) {
+  int h = 0;
+  for (int q = 1; q <= jj; q++) {
+    h = (h + 1) / 2 + (L / 2 - 1);
+    h += h & 1;
+  }
+  return h;
+}
+
+template <int L, int R, bool TREE>
+__global__ void __launch_bounds__(256, 2) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
+                                                              const __grid_constant__ FilterPair f) {
+  extern __shared__ __align__(128) double smem[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int oT = 2 * a.cap;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
+  if (L > kUniformTapsMaxDwt) {
+    for (int t = tid; t < JWC_MAX_TAPS; t += nt) {
+      smem[oT + t] = f.f0[t];
+      smem[oT + JWC_MAX_TAPS + t] = f.f1[t];
+    }
+  }
+  int64_t bid = blockIdx.x;
+  const int ti = (int)(bid % a.tiles);
+  bid /= a.tiles;
+  const int p = (int)(bid % a.nodes);
+  const int64_t b = bid / a.nodes;
+  const int tlen = (int)((a.h < a.T) ? a.h : a.T);
+  const int64_t a0 = (int64_t)ti * tlen;
+  const bool bulk = (a.mode == DWT_BULK);
+  const double* in_b = a.in + b * a.in_sig;
+
+  // geometry of depth jj: children arrays of length len = (tlen >> jj) + HLj, node length hn = h >> jj
+  auto len_of = [&](int jj) { return (tlen >> jj) + inv_halo(L, jj); };
+  auto stride_of = [&](int jj) { const int l = len_of(jj); return l + (l & 1) + 2 * R; };
+
+  if (bulk) {
+    if (tid == 0) {
+      ptx::mbar_init(&bars[0], 1);
+      ptx::mbar_init(&bars[1], 1);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+  }
+  // ---- prologue: the depth-k set into buffer 0 ------------------------------------------------------------------------------
+  {
+    const int jj = a.k, len = len_of(jj), st = stride_of(jj);
+    const int64_t hn = a.h >> jj, start = (a0 >> jj) - inv_halo(L, jj);
+    if (TREE) {
+      const int leaves = 1 << jj;
+      const double* src0 = in_b + (int64_t)p * a.h;       // leaf c of this node at + c * hn
+      if (bulk) {
+        if (tid == 0) ptx::mbar_expect_tx(&bars[0], (uint32_t)(leaves * len) * 8u);
+        __syncthreads();
+        if (tid < 32)
+          for (int c = tid; c < leaves; c += 32) bulk_load_circ(smem + c * st, src0 + c * hn, start, len, hn, &bars[0]);
+      } else {
+        for (int c = 0; c < leaves; c++) scalar_load_circ(smem + c * st, src0 + c * hn, start, len, hn, tid, nt);
+      }
+    } else {
+      const double* asrc = a.ain + b * a.ain_sig;                 // A_{l0+k}
+      const double* dsrc = in_b + (a.N >> (a.l0 + jj));           // D_{l0+k}
+      if (bulk) {
+        if (tid == 0) {
+          ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)len * 8u);
+          bulk_load_circ(smem, asrc, start, len, hn, &bars[0]);
+          bulk_load_circ(smem + st, dsrc, start, len, hn, &bars[0]);
+        }
+      } else {
+        scalar_load_circ(smem, asrc, start, len, hn, tid, nt);
+        scalar_load_circ(smem + st, dsrc, start, len, hn, tid, nt);
+      }
+    }
+  }
+  // ---- k synthesis levels: depth jj (buffer u&1) -> depth jj-1 (buffer (u+1)&1) ---------------------------------------
+  for (int jj = a.k, u = 0; jj >= 1; --jj, ++u) {
+    const int oin = (u & 1) * a.cap, oout = ((u + 1) & 1) * a.cap;
+    const int st_in = stride_of(jj), st_out = stride_of(jj - 1);
+    if (!TREE && jj > 1) {   // prefetch D_{l0+jj-1} into the high-pass slot of the output buffer
+      const int len = len_of(jj - 1);
+      const int64_t hn = a.h >> (jj - 1), start = (a0 >> (jj - 1)) - inv_halo(L, jj - 1);
+      const double* dsrc = in_b + (a.N >> (a.l0 + jj - 1));
+      if (bulk) {
+        if (tid == 0) {
+          ptx::mbar_expect_tx(&bars[(u + 1) & 1], (uint32_t)len * 8u);
+          bulk_load_circ(smem + oout + st_out, dsrc, start, len, hn, &bars[(u + 1) & 1]);
+        }
+      } else {
+        scalar_load_circ(smem + oout + st_out, dsrc, start, len, hn, tid, nt);
+      }
+    }
+    if (bulk && (!TREE || u == 0)) {
+      const uint32_t par = (uint32_t)((u >> 1) & 1);
+      if (tid == 0) ptx::mbar_wait(&bars[u & 1], par);
+      __syncthreads();
+      ptx::mbar_wait(&bars[u & 1], par);
+    } else {
+      __syncthreads();
+    }
+    const int hl_out = inv_halo(L, jj - 1), hl_in = inv_halo(L, jj);
+    const int np = (hl_out >> 1) + (tlen >> jj);          // output pairs per parent
+    const int off = hl_in - (hl_out >> 1) - (L / 2 - 1);   // first child index read by pair 0
+    const int parents = TREE ? (1 << (jj - 1)) : 1;
+    const int nb = (np + R - 1) / R;
+    const int items = parents * nb;
+    for (int w = tid; w < items; w += nt) {
+      const int q = TREE ? (w / nb) : 0;
+      const int u0 = (w - q * nb) * R;
+      const int clo = oin + (2 * q) * st_in + off + u0;
+      double2 o[R];
+      syn_item<L, R>(smem + clo, smem + clo + st_in, f, smem + oT, o);
+      double2* dst = reinterpret_cast<double2*>(smem + oout + q * st_out) + u0;
+      if (u0 + R <= np) {
+#pragma unroll
+        for (int r = 0; r < R; r++) dst[r] = o[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if (u0 + r < np) dst[r] = o[r];
+      }
+    }
+    if (bulk && jj == 1) ptx::fence_proxy_async();
+    __syncthreads();
+  }
+  // ---- the depth-0 tile leaves ---------------------------------------------------------------------------------------------
+  const double* res = smem + (a.k & 1) * a.cap;
+  double* dst = a.out + b * a.out_sig + (int64_t)p * a.h + a0;
+  if (bulk) {
+    if (tid == 0) {
+      ptx::bulk_s2g(dst, res, (uint32_t)tlen * 8u);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read<0>();
+    }
+  } else {
+    for (int e = tid; e < tlen; e += nt) dst[e] = res[e];
+  }
+}
+
+template <int L, bool TREE, bool INV>
+int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int threads, size_t smem,
+                    int64_t nblocks) {
+  if (INV) {
+    auto kern = dwt_inv_pass_kernel<L, kDwtR, TREE>;
+    JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  } else {
+    auto kern = dwt_fwd_pass_kernel<L, kDwtR, TREE>;
+    JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  }
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+template <bool TREE, bool INV>
+int dispatch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int L, int threads,
+                      size_t smem, int64_t nblocks) {
+  switch (L) {
+#define JWC_CASE(LL) case LL: return launch_dwt_pass<LL, TREE, INV>(ctx, st, a, f, threads, smem, nblocks);
+    JWC_CASE(2) JWC_CASE(4) JWC_CASE(6) JWC_CASE(8) JWC_CASE(10) JWC_CASE(12) JWC_CASE(14) JWC_CASE(16) JWC_CASE(18)
+    JWC_CASE(20) JWC_CASE(22) JWC_CASE(24) JWC_CASE(26) JWC_CASE(28) JWC_CASE(30) JWC_CASE(32) JWC_CASE(34) JWC_CASE(36)
+    JWC_CASE(38) JWC_CASE(40)
+#undef JWC_CASE
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
+int steps_forward(int64_t n, int levels) {
+  int steps = 0;
+  for (int64_t h = n; h >= 2 && steps < levels; h >>= 1) steps++;
+  return steps;
+}
+
+DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const void* p1, int64_t n, int steps, int L,
+                  bool tree, bool inverse) {
+  DwtPlanInput pin{};
+  pin.n = n; pin.levels = steps; pin.L = L; pin.tree = tree; pin.inverse = inverse;
+  pin.aligned16 = ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
+  pin.smem_budget = ctx->tune.dwt_smem > 0 ? ctx->tune.dwt_smem : 113000;
+  if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
+  pin.tile_override = ctx->tune.dwt_tile; pin.group_override = ctx->tune.dwt_group;
+  pin.threads_override = ctx->tune.dwt_threads;
+  return dwt_plan(pin, steps);
+}
+
+}  // namespace
+
+int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree) {
+  if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
+  if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
+  const int steps = steps_forward(n, levels);
+  if (steps == 0) return JWC_ERR_UNSUPPORTED;   // plain copy: the generic path handles it
+  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, steps, L, tree, false);
+  if (!plan.ok) return JWC_ERR_UNSUPPORTED;
+  debug_dwt_plan("forward", plan, n, levels, L, tree);
+  Scratch ws(st);
+  const int npass = (int)plan.passes.size();
+  double* tmp[2] = {nullptr, nullptr};
+  if (npass >= 2) {
+    if (tree) {
+      tmp[0] = ws.get((size_t)batch * n);
+      tmp[1] = tmp[0];
+    } else {
+      tmp[0] = ws.get((size_t)batch * (n >> plan.passes[0].k));
+      tmp[1] = (npass >= 3) ? ws.get((size_t)batch * (n >> (plan.passes[0].k + plan.passes[1].k))) : tmp[0];
+    }
+    if (!tmp[0] || !tmp[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+  }
+  const double* src = d_in;
+  int64_t src_sig = n;
+  for (int pi = 0; pi < npass; pi++) {
+    const DwtPass& p = plan.passes[pi];
+    const bool lastp = (pi == npass - 1);
+    DwtPassArgs a{};
+    a.in = src; a.in_sig = src_sig;
+    a.N = n; a.h = n >> p.l0; a.l0 = p.l0; a.k = p.k; a.T = p.T; a.cap = p.cap; a.mode = p.mode;
+    a.tiles = (int)((a.h + p.T - 1) / p.T);
+    if (tree) {
+      a.nodes = 1 << p.l0;
+      // whole-array ping-pong so that the last pass lands in d_out
+      double* dst = (((npass - 1 - pi) & 1) == 0) ? d_out : tmp[0];
+      a.out = dst; a.out_sig = n;
+    } else {
+      a.nodes = 1;
+      a.out = d_out; a.out_sig = n;                                  // D's at their final place
+      if (lastp) { a.aout = d_out; a.aout_sig = n; }
+      else { a.aout = tmp[pi & 1]; a.aout_sig = n >> (p.l0 + p.k); }
+    }
+    const int64_t nblocks = (int64_t)a.tiles * a.nodes * batch;
+    if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+    int rc = tree ? dispatch_dwt_pass<true, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks)
+                  : dispatch_dwt_pass<false, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks);
+    if (rc != JWC_OK) return rc;
+    if (tree) { src = a.out; src_sig = n; }
+    else { src = a.aout; src_sig = a.aout_sig; }
+  }
+  return JWC_OK;
+}
+
+int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree) {
+  if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
+  if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
+  const int steps = steps_forward(n, levels);   // the reverse loops undo exactly the forward's steps
+  if (steps == 0) return JWC_ERR_UNSUPPORTED;
+  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, steps, L, tree, true);
+  if (!plan.ok) return JWC_ERR_UNSUPPORTED;
+  debug_dwt_plan("inverse", plan, n, levels, L, tree);
+  Scratch ws(st);
+  const int npass = (int)plan.passes.size();
+  double* tmp[2] = {nullptr, nullptr};
+  if (npass >= 2) {
+    if (tree) {
+      tmp[0] = ws.get((size_t)batch * n);
+      tmp[1] = tmp[0];
+    } else {
+      // A buffers: the result of pass pi (depth l0_pi) has n >> l0_pi samples; the largest intermediate is pass 1's
+      tmp[0] = ws.get((size_t)batch * (n >> plan.passes[1].l0));
+      tmp[1] = (npass >= 3) ? ws.get((size_t)batch * (n >> plan.passes[2].l0)) : tmp[0];
+    }
+    if (!tmp[0] || !tmp[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+  }
+  const double* asrc = d_in;     // FWT: A_{steps} is the prefix of the coefficient array; WPT: the whole array
+  int64_t asrc_sig = n;
+  for (int pi = npass - 1, step = 0; pi >= 0; --pi, ++step) {   // deepest pass first
+    const DwtPass& p = plan.passes[pi];
+    DwtPassArgs a{};
+    a.N = n; a.h = n >> p.l0; a.l0 = p.l0; a.k = p.k; a.T = p.T; a.cap = p.cap; a.mode = p.mode;
+    a.tiles = (int)((a.h + p.T - 1) / p.T);
+    if (tree) {
+      a.nodes = 1 << p.l0;
+      a.in = asrc; a.in_sig = n;
+      double* dst = (((pi) & 1) == 0) ? d_out : tmp[0];   // pass 0 (executed last) lands in d_out
+      a.out = dst; a.out_sig = n;
+    } else {
+      a.nodes = 1;
+      a.in = d_in; a.in_sig = n;                 // D blocks always come from the coefficient array
+      a.ain = asrc; a.ain_sig = asrc_sig;
+      if (pi == 0) { a.out = d_out; a.out_sig = n; }
+      else { a.out = tmp[(pi - 1) & 1]; a.out_sig = n >> p.l0; }
+    }
+    const int64_t nblocks = (int64_t)a.tiles * a.nodes * batch;
+    if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+    int rc = tree ? dispatch_dwt_pass<true, true>(ctx, st, a, f, L, p.threads, p.smem, nblocks)
+                  : dispatch_dwt_pass<false, true>(ctx, st, a, f, L, p.threads, p.smem, nblocks);
+    if (rc != JWC_OK) return rc;
+    asrc = a.out; asrc_sig = a.out_sig;
+  }
+  return JWC_OK;
+}
+
+}  // namespace jwc

@@ -1,0 +1,156 @@
+// jwc_dwt_plan.cuh -- how a decimated transform (FWT pyramid / WPT full tree) is cut into fused passes.
+//
+// A pass takes every node of length h at tree depth l0 and carries it k levels down inside shared memory:
+// tile = T consecutive samples of one node + the halo the k decimating steps need:
+//   forward (analysis):  right halo (L-2)(2^k - 1) input samples
+//   inverse (synthesis): left halo of HL_jj <= L-2 coefficients in every depth-jj child array (it does not grow)
+// FWT: only the low-pass chain continues, each D_{l0+jj} tile is shipped as soon as it exists.
+// WPT: all 2^jj children stay in shared memory, the 2^k leaves are shipped at the end.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace jwc {
+
+constexpr int kDwtR = 7;  // outputs (forward) / output pairs (inverse) per work item; odd => conflict-free LDS/STS
+
+enum { DWT_BULK = 0, DWT_SCALAR = 2 };
+
+struct DwtPass {
+  int l0 = 0, k = 0, T = 0, cap = 0, threads = 256, mode = DWT_SCALAR;
+  size_t smem = 0;
+};
+
+struct DwtPlanInput {
+  int64_t n;
+  int levels, L;
+  bool tree, inverse, aligned16;
+  int smem_budget, tile_override, group_override, threads_override;
+};
+
+// ---- forward geometry -------------------------------------------------------------------------------------------------
+inline int64_t dwt_fwd_halo(int L, int k, int jj) { return (int64_t)(L - 2) * (((int64_t)1 << (k - jj)) - 1); }
+inline int64_t dwt_fwd_len(int L, int k, int jj, int64_t tlen) { return (tlen >> jj) + dwt_fwd_halo(L, k, jj); }
+inline int64_t dwt_node_stride(int64_t len) { return len + (len & 1) + 2 * kDwtR; }
+inline int64_t dwt_fwd_cap(bool tree, int L, int k, int64_t tlen) {
+  int64_t cap = 0;
+  for (int jj = 0; jj <= k; jj++) {
+    const int64_t nodes = (jj == 0) ? 1 : (tree ? ((int64_t)1 << jj) : 2);
+    cap = std::max(cap, nodes * dwt_node_stride(dwt_fwd_len(L, k, jj, tlen)));
+  }
+  return cap + (cap & 1);
+}
+
+// ---- inverse geometry: left halo of the depth-jj arrays (rounded up to even so bulk copies stay 16-byte aligned)
+inline int64_t dwt_inv_halo(int L, int jj) {
+  int64_t h = 0;
+  for (int q = 1; q <= jj; q++) {
+    h = (h + 1) / 2 + (L / 2 - 1);
+    h += h & 1;
+  }
+  return h;
+}
+inline int64_t dwt_inv_len(int L, int jj, int64_t tlen) { return (tlen >> jj) + dwt_inv_halo(L, jj); }
+inline int64_t dwt_inv_cap(bool tree, int L, int k, int64_t tlen) {
+  int64_t cap = 0;
+  for (int jj = 0; jj <= k; jj++) {
+    const int64_t nodes = (jj == 0) ? 1 : (tree ? ((int64_t)1 << jj) : 2);
+    cap = std::max(cap, nodes * dwt_node_stride(dwt_inv_len(L, jj, tlen)));
+  }
+  return cap + (cap & 1);
+}
+
+inline int64_t dwt_items(const DwtPlanInput& in, int k, int jj, int64_t tlen) {
+  // forward level jj: children of length len_jj from every parent; inverse level jj: parents (depth jj-1) pairs
+  if (!in.inverse) {
+    const int64_t parents = in.tree ? ((int64_t)1 << (jj - 1)) : 1;
+    return parents * ((dwt_fwd_len(in.L, k, jj, tlen) + kDwtR - 1) / kDwtR);
+  }
+  const int64_t parents = in.tree ? ((int64_t)1 << (jj - 1)) : 1;
+  const int64_t pairs = (dwt_inv_len(in.L, jj - 1, tlen) + 1) / 2 + 1;
+  return parents * ((pairs + kDwtR - 1) / kDwtR);
+}
+
+inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, double* est) {
+  const int64_t h = in.n >> l0;                 // node length at the top of the pass
+  if (k < 1 || ((int64_t)1 << k) > h) return false;
+  const int64_t budget = in.smem_budget / 8 - 16 - 2 * 64;   // mbarriers + shared-memory tap copy
+  auto cap_of = [&](int64_t t) { return in.inverse ? dwt_inv_cap(in.tree, in.L, k, t) : dwt_fwd_cap(in.tree, in.L, k, t); };
+  // T: a power of two, 2^k <= T <= h, as large as the budget allows
+  int64_t T = h;
+  if (in.tile_override > 0)
+    while (T > in.tile_override && T > ((int64_t)1 << k)) T >>= 1;
+  while (T > ((int64_t)1 << k) && 2 * cap_of(T) > budget) T >>= 1;
+  if (2 * cap_of(T) > budget) return false;
+  const int64_t H = in.inverse ? dwt_inv_halo(in.L, k) : dwt_fwd_halo(in.L, k, 0);
+  if (T < h && !in.inverse && 2 * H > T && in.tile_override <= 0) return false;   // halo would dominate the tile
+  out->l0 = l0; out->k = k; out->T = (int)T; out->cap = (int)cap_of(T);
+  out->smem = (size_t)(2 * cap_of(T)) * 8 + 2 * 64 * 8 + 128;
+  // bulk (TMA) copies need even piece lengths: forward T >= 2, inverse (T >> k) even
+  const bool even_ok = in.inverse ? ((T >> k) % 2 == 0) : (T >= 2);
+  out->mode = (in.aligned16 && even_ok) ? DWT_BULK : DWT_SCALAR;
+  int thr = in.threads_override > 0 ? in.threads_override : 256;
+  double eff = 0;
+  for (int cand = thr; cand >= (in.threads_override > 0 ? thr : 128); cand -= 32) {
+    double useful = 0, issued = 0;
+    for (int jj = 1; jj <= k; jj++) {
+      const int64_t it = dwt_items(in, k, jj, T);
+      useful += (double)it;
+      issued += (double)(((it + cand - 1) / cand) * cand);
+    }
+    const double e = issued > 0 ? useful / issued : 1.0;
+    if (e > eff + 0.02) { eff = e; thr = cand; }
+  }
+  out->threads = thr;
+  // time model per sample of the pass input (ps)
+  double work = 0;   // output pairs computed per input sample, summed over the levels
+  for (int jj = 1; jj <= k; jj++) {
+    const double parents = in.tree ? (double)((int64_t)1 << (jj - 1)) : 1.0;
+    const double len = in.inverse ? (double)dwt_inv_len(in.L, jj - 1, T) / 2.0 : (double)dwt_fwd_len(in.L, k, jj, T);
+    work += parents * len / (double)T;
+  }
+  const double flops = 4.0 * in.L * work / std::max(eff, 0.3);
+  double halo_rd;
+  if (!in.inverse) halo_rd = (double)H / (double)T;
+  else halo_rd = (in.tree ? (double)((int64_t)1 << k) * (double)H : (double)(k + 1) * (double)(in.L - 2)) / (double)T;
+  const double bytes = 8.0 * (1.0 + halo_rd) + 8.0;
+  const double tm = bytes / 5.5, tc = flops / 32.0;
+  const double frac = in.tree ? 1.0 : 1.0 / (double)((int64_t)1 << l0);   // FWT passes shrink geometrically
+  *est = frac * (std::max(tm, tc) + 0.35 * std::min(tm, tc)) + (in.tree ? 1.0 : 0.2);
+  return true;
+}
+
+struct DwtPlan {
+  std::vector<DwtPass> passes;   // in forward order (l0 ascending); the inverse executes them back to front
+  bool ok = false;
+};
+
+// steps = number of levels actually performed (reference loops stop at h < 2)
+inline DwtPlan dwt_plan(const DwtPlanInput& in, int steps) {
+  DwtPlan plan;
+  if (steps <= 0) return plan;
+  std::vector<double> best(steps + 1, 1e300);
+  std::vector<int> choice(steps + 1, 0);
+  std::vector<DwtPass> pass_at(steps + 1);
+  best[steps] = 0;
+  for (int l0 = steps - 1; l0 >= 0; l0--) {
+    const int kmax = in.group_override > 0 ? std::min(in.group_override, steps - l0) : steps - l0;
+    for (int k = 1; k <= kmax; k++) {
+      DwtPass p;
+      double t;
+      if (!dwt_make_pass(in, l0, k, &p, &t)) continue;
+      if (best[l0 + k] < 1e299 && t + best[l0 + k] < best[l0]) {
+        best[l0] = t + best[l0 + k];
+        choice[l0] = k;
+        pass_at[l0] = p;
+      }
+    }
+  }
+  if (best[0] >= 1e299) return plan;
+  for (int l0 = 0; l0 < steps; l0 += choice[l0]) plan.passes.push_back(pass_at[l0]);
+  plan.ok = true;
+  return plan;
+}
+
+}  // namespace jwc

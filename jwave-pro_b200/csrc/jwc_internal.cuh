@@ -46,6 +46,7 @@ struct Tuning {
   int dwt_tile = 0;
   int dwt_threads = 0;
   int dwt_group = 0;
+  int dwt_smem = 0;
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
   int force_generic = 0;
 };
