@@ -46,11 +46,11 @@ struct DwtPassArgs {
   int l0, k, T, tiles, nodes, cap, mode;
 };
 
-// circular bulk load of `len` doubles starting at node position `start` (may be negative, |start| <= hn) of a node of
-// length hn at `base` into dst.  One thread; the mbarrier must already expect the bytes.
+// circular bulk load of `len` doubles starting at node position `start` (any sign, any number of wraps) of a node of
+// length hn at `base` into dst.  One thread; the mbarrier must already expect the bytes.  start, hn, len are even.
 __device__ __forceinline__ void bulk_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
                                                uint64_t* bar) {
-  int64_t pos = start;
+  int64_t pos = start % hn;
   if (pos < 0) pos += hn;
   int done = 0;
   while (done < len) {
@@ -109,7 +109,49 @@ __device__ __forceinline__ void ana_item(const double2* __restrict__ px, const F
 }
 
 template <int L, int R, bool TREE>
-__global__ void __launch_bounds__(256, 2) dwt_fwd_pass_kernel(const __grid_constant__ DwtPassArgs a,
+__device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int oT, int oin, int oout, int st_in,
+                                          int st_out, int len_out, int own, int parents, int tid, int nt) {
+  const int nb = (len_out + R - 1) / R;
+  const int items = parents * nb;
+  for (int w = tid; w < items; w += nt) {
+    const int q = TREE ? (w / nb) : 0;
+    const int i0 = (w - q * nb) * R;
+    const double2* px = reinterpret_cast<const double2*>(smem + oin + q * st_in) + i0;
+    double lo[R], hi[R];
+    const int olo = oout + (2 * q) * st_out + i0, ohi = olo + st_out;
+    const bool full = i0 + R <= len_out;
+    if (!TREE && i0 >= own) {   // FWT: the halo part of D is produced by the neighbouring tile
+      ana_item<L, R, false>(px, f, smem + oT, lo, hi);
+      if (full) {
+#pragma unroll
+        for (int r = 0; r < R; r++) smem[olo + r] = lo[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if (i0 + r < len_out) smem[olo + r] = lo[r];
+      }
+    } else {
+      ana_item<L, R, true>(px, f, smem + oT, lo, hi);
+      if (full) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          smem[olo + r] = lo[r];
+          smem[ohi + r] = hi[r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if (i0 + r < len_out) {
+            smem[olo + r] = lo[r];
+            smem[ohi + r] = hi[r];
+          }
+      }
+    }
+  }
+}
+
+template <int L, int RMAX, bool TREE>
+__global__ void __launch_bounds__(256, 3) dwt_fwd_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -153,46 +195,16 @@ __global__ void __launch_bounds__(256, 2) dwt_fwd_pass_kernel(const __grid_const
     const int oin = (jj & 1) ? 0 : a.cap, oout = (jj & 1) ? a.cap : 0;
     const int halo_in = (L - 2) * ((1 << (a.k - jj + 1)) - 1), halo_out = (L - 2) * ((1 << (a.k - jj)) - 1);
     const int len_in = (tlen >> (jj - 1)) + halo_in, len_out = (tlen >> jj) + halo_out;
-    const int st_in = len_in + (len_in & 1) + 2 * R, st_out = len_out + (len_out & 1) + 2 * R;
+    const int st_in = len_in + (len_in & 1) + 2 * kDwtR, st_out = len_out + (len_out & 1) + 2 * kDwtR;
     const int own = tlen >> jj;                       // outputs of each child that belong to this tile
     const int parents = TREE ? (1 << (jj - 1)) : 1;
-    const int nb = (len_out + R - 1) / R;
-    const int items = parents * nb;
-    for (int w = tid; w < items; w += nt) {
-      const int q = TREE ? (w / nb) : 0;
-      const int i0 = (w - q * nb) * R;
-      const double2* px = reinterpret_cast<const double2*>(smem + oin + q * st_in) + i0;
-      double lo[R], hi[R];
-      const int olo = oout + (2 * q) * st_out + i0, ohi = olo + st_out;
-      const bool full = i0 + R <= len_out;
-      if (!TREE && i0 >= own) {   // FWT: the halo part of D is produced by the neighbouring tile
-        ana_item<L, R, false>(px, f, smem + oT, lo, hi);
-        if (full) {
-#pragma unroll
-          for (int r = 0; r < R; r++) smem[olo + r] = lo[r];
-        } else {
-#pragma unroll
-          for (int r = 0; r < R; r++)
-            if (i0 + r < len_out) smem[olo + r] = lo[r];
-        }
-      } else {
-        ana_item<L, R, true>(px, f, smem + oT, lo, hi);
-        if (full) {
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            smem[olo + r] = lo[r];
-            smem[ohi + r] = hi[r];
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < R; r++)
-            if (i0 + r < len_out) {
-              smem[olo + r] = lo[r];
-              smem[ohi + r] = hi[r];
-            }
-        }
-      }
-    }
+    // rows per item: as many as RMAX while every thread still gets an item, fewer on the small (deep) levels
+    if (parents * ((len_out + RMAX - 1) / RMAX) >= nt || RMAX == 1)
+      ana_level<L, RMAX, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+    else if (parents * ((len_out + 2) / 3) >= nt)
+      ana_level<L, 3, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+    else
+      ana_level<L, 1, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
     // ---- ship what is final after this level ------------------------------------------------------------------------------
     const bool last = (jj == a.k);
     const bool vec_ok = bulk && (own & 1) == 0;
@@ -283,7 +295,30 @@ __device__ __forceinline__ int inv_halo(int L, int jj) {
 }
 
 template <int L, int R, bool TREE>
-__global__ void __launch_bounds__(256, 2) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
+__device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int oT, int oin, int oout, int st_in,
+                                          int st_out, int np, int off, int parents, int tid, int nt) {
+  const int nb = (np + R - 1) / R;
+  const int items = parents * nb;
+  for (int w = tid; w < items; w += nt) {
+    const int q = TREE ? (w / nb) : 0;
+    const int u0 = (w - q * nb) * R;
+    const int clo = oin + (2 * q) * st_in + off + u0;
+    double2 o[R];
+    syn_item<L, R>(smem + clo, smem + clo + st_in, f, smem + oT, o);
+    double2* dst = reinterpret_cast<double2*>(smem + oout + q * st_out) + u0;
+    if (u0 + R <= np) {
+#pragma unroll
+      for (int r = 0; r < R; r++) dst[r] = o[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (u0 + r < np) dst[r] = o[r];
+    }
+  }
+}
+
+template <int L, int RMAX, bool TREE>
+__global__ void __launch_bounds__(256, 3) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -307,7 +342,7 @@ __global__ void __launch_bounds__(256, 2) dwt_inv_pass_kernel(const __grid_const
 
   // geometry of depth jj: children arrays of length len = (tlen >> jj) + HLj, node length hn = h >> jj
   auto len_of = [&](int jj) { return (tlen >> jj) + inv_halo(L, jj); };
-  auto stride_of = [&](int jj) { const int l = len_of(jj); return l + (l & 1) + 2 * R; };
+  auto stride_of = [&](int jj) { const int l = len_of(jj); return l + (l & 1) + 2 * kDwtR; };
 
   if (bulk) {
     if (tid == 0) {
@@ -376,24 +411,12 @@ __global__ void __launch_bounds__(256, 2) dwt_inv_pass_kernel(const __grid_const
     const int np = (hl_out >> 1) + (tlen >> jj);          // output pairs per parent
     const int off = hl_in - (hl_out >> 1) - (L / 2 - 1);   // first child index read by pair 0
     const int parents = TREE ? (1 << (jj - 1)) : 1;
-    const int nb = (np + R - 1) / R;
-    const int items = parents * nb;
-    for (int w = tid; w < items; w += nt) {
-      const int q = TREE ? (w / nb) : 0;
-      const int u0 = (w - q * nb) * R;
-      const int clo = oin + (2 * q) * st_in + off + u0;
-      double2 o[R];
-      syn_item<L, R>(smem + clo, smem + clo + st_in, f, smem + oT, o);
-      double2* dst = reinterpret_cast<double2*>(smem + oout + q * st_out) + u0;
-      if (u0 + R <= np) {
-#pragma unroll
-        for (int r = 0; r < R; r++) dst[r] = o[r];
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; r++)
-          if (u0 + r < np) dst[r] = o[r];
-      }
-    }
+    if (parents * ((np + RMAX - 1) / RMAX) >= nt || RMAX == 1)
+      syn_level<L, RMAX, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+    else if (parents * ((np + 2) / 3) >= nt)
+      syn_level<L, 3, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+    else
+      syn_level<L, 1, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
     if (bulk && jj == 1) ptx::fence_proxy_async();
     __syncthreads();
   }
@@ -415,11 +438,11 @@ template <int L, bool TREE, bool INV>
 int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int threads, size_t smem,
                     int64_t nblocks) {
   if (INV) {
-    auto kern = dwt_inv_pass_kernel<L, kDwtR, TREE>;
+    auto kern = dwt_inv_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE>;
     JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   } else {
-    auto kern = dwt_fwd_pass_kernel<L, kDwtR, TREE>;
+    auto kern = dwt_fwd_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE>;
     JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   }
@@ -452,7 +475,7 @@ DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const voi
   DwtPlanInput pin{};
   pin.n = n; pin.levels = steps; pin.L = L; pin.tree = tree; pin.inverse = inverse;
   pin.aligned16 = ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
-  pin.smem_budget = ctx->tune.dwt_smem > 0 ? ctx->tune.dwt_smem : 113000;
+  pin.smem_budget = ctx->tune.dwt_smem > 0 ? ctx->tune.dwt_smem : 45000;
   if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
   pin.tile_override = ctx->tune.dwt_tile; pin.group_override = ctx->tune.dwt_group;
   pin.threads_override = ctx->tune.dwt_threads;

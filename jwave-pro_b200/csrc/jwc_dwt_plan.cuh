@@ -61,15 +61,15 @@ inline int64_t dwt_inv_cap(bool tree, int L, int k, int64_t tlen) {
   return cap + (cap & 1);
 }
 
+inline int dwt_rmax(int L) { return L > 10 ? 5 : kDwtR; }   // rows per item of the kernels (register budget)
+
 inline int64_t dwt_items(const DwtPlanInput& in, int k, int jj, int64_t tlen) {
   // forward level jj: children of length len_jj from every parent; inverse level jj: parents (depth jj-1) pairs
-  if (!in.inverse) {
-    const int64_t parents = in.tree ? ((int64_t)1 << (jj - 1)) : 1;
-    return parents * ((dwt_fwd_len(in.L, k, jj, tlen) + kDwtR - 1) / kDwtR);
-  }
+  const int R = dwt_rmax(in.L);
   const int64_t parents = in.tree ? ((int64_t)1 << (jj - 1)) : 1;
+  if (!in.inverse) return parents * ((dwt_fwd_len(in.L, k, jj, tlen) + R - 1) / R);
   const int64_t pairs = (dwt_inv_len(in.L, jj - 1, tlen) + 1) / 2 + 1;
-  return parents * ((pairs + kDwtR - 1) / kDwtR);
+  return parents * ((pairs + R - 1) / R);
 }
 
 inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, double* est) {
@@ -117,7 +117,8 @@ inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, d
   const double bytes = 8.0 * (1.0 + halo_rd) + 8.0;
   const double tm = bytes / 5.5, tc = flops / 32.0;
   const double frac = in.tree ? 1.0 : 1.0 / (double)((int64_t)1 << l0);   // FWT passes shrink geometrically
-  *est = frac * (std::max(tm, tc) + 0.35 * std::min(tm, tc)) + (in.tree ? 1.0 : 0.2);
+  // every level is a block-wide barrier whose latency is only partly hidden by the other resident CTAs
+  *est = frac * (std::max(tm, tc) + 0.35 * std::min(tm, tc) + 0.25 * k) + (in.tree ? 1.0 : 0.2);
   return true;
 }
 
