@@ -1,0 +1,131 @@
+/*
+ * JwcNative -- Panama FFM (java.lang.foreign) binding of libjwavecuda.so (include/jwavecuda.h).
+ *
+ * NOT COMPILED IN THIS REPOSITORY: the build image has no JDK (SURVEY.md section 0.2).  Java 21 needs
+ * --enable-preview for java.lang.foreign (final in 22).  The same C ABI is exercised by the Python ctypes
+ * mirror (jwave-pro_b200/_native.py), which is what the test-suite runs.
+ *
+ * Library lookup: -Djwave.cuda.lib=/path/to/libjwavecuda.so, else System.loadLibrary-style "jwavecuda".
+ */
+package jwave.transforms.cuda;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.SymbolLookup;
+import java.lang.invoke.MethodHandle;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+public final class JwcNative {
+
+  public static final int FLAG_EXACT = 1;          // JWC_FLAG_EXACT: unfused mul/add, bit-identical to the JVM loops
+  public static final int FLAG_FORCE_GENERIC = 2;  // JWC_FLAG_FORCE_GENERIC
+
+  private static final Linker LINKER = Linker.nativeLinker();
+  private static final SymbolLookup LIB;
+  private static final MethodHandle CREATE, DESTROY, LAST_ERROR, ALLOC_PINNED, FREE_PINNED;
+  private static final MethodHandle[] TRANSFORMS = new MethodHandle[6];
+  private static final String[] NAMES = {
+      "jwc_modwt_forward", "jwc_modwt_inverse", "jwc_fwt_forward", "jwc_fwt_inverse", "jwc_wpt_forward",
+      "jwc_wpt_inverse" };
+
+  public static final int MODWT_FORWARD = 0, MODWT_INVERSE = 1, FWT_FORWARD = 2, FWT_INVERSE = 3, WPT_FORWARD = 4,
+      WPT_INVERSE = 5;
+
+  static {
+    String path = System.getProperty("jwave.cuda.lib");
+    LIB = path != null ? SymbolLookup.libraryLookup(path, Arena.global())
+                       : SymbolLookup.libraryLookup(System.mapLibraryName("jwavecuda"), Arena.global());
+    CREATE = handle("jwc_create", FunctionDescriptor.of(ADDRESS, ADDRESS, JAVA_INT));
+    DESTROY = handle("jwc_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    LAST_ERROR = handle("jwc_last_error", FunctionDescriptor.of(ADDRESS));
+    ALLOC_PINNED = handle("jwc_alloc_pinned", FunctionDescriptor.of(ADDRESS, JAVA_LONG));
+    FREE_PINNED = handle("jwc_free_pinned", FunctionDescriptor.ofVoid(ADDRESS));
+    // int f(jwc_ctx*, const double* in, double* out, int64 batch, int64 n, int levels,
+    //       const double* f0, const double* f1, int L, unsigned flags)
+    FunctionDescriptor t = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT,
+        ADDRESS, ADDRESS, JAVA_INT, JAVA_INT);
+    for (int i = 0; i < NAMES.length; i++) TRANSFORMS[i] = handle(NAMES[i], t);
+  }
+
+  private static MethodHandle handle(String name, FunctionDescriptor fd) {
+    return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
+  }
+
+  private JwcNative() { }
+
+  /** One context per process is enough; devices == null means "current CUDA device". No CPU fallback exists. */
+  public static MemorySegment create(int[] devices) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment dev = devices == null ? MemorySegment.NULL : a.allocateArray(JAVA_INT, devices);
+      MemorySegment ctx = (MemorySegment) CREATE.invokeExact(dev, devices == null ? 0 : devices.length);
+      if (ctx.equals(MemorySegment.NULL)) throw new IllegalStateException("jwc_create: " + lastError());
+      return ctx;
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  public static void destroy(MemorySegment ctx) {
+    try { DESTROY.invokeExact(ctx); } catch (Throwable t) { throw new IllegalStateException(t); }
+  }
+
+  public static String lastError() {
+    try {
+      MemorySegment p = (MemorySegment) LAST_ERROR.invokeExact();
+      return p.reinterpret(512).getUtf8String(0);
+    } catch (Throwable t) {
+      return t.toString();
+    }
+  }
+
+  /** Pinned, off-heap staging buffer of `doubles` fp64 values (cudaHostAlloc); free with freePinned. */
+  public static MemorySegment allocPinned(long doubles) {
+    try {
+      MemorySegment p = (MemorySegment) ALLOC_PINNED.invokeExact(doubles * 8L);
+      if (p.equals(MemorySegment.NULL)) throw new OutOfMemoryError("jwc_alloc_pinned: " + lastError());
+      return p.reinterpret(doubles * 8L);
+    } catch (Error e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  public static void freePinned(MemorySegment p) {
+    try { FREE_PINNED.invokeExact(p); } catch (Throwable t) { throw new IllegalStateException(t); }
+  }
+
+  /** Run one transform on (pinned or plain off-heap) host segments; throws on a non-zero status. */
+  public static void run(int which, MemorySegment ctx, MemorySegment in, MemorySegment out, long batch, long n,
+      int levels, double[] f0, double[] f1, int flags) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment s0 = a.allocateArray(JAVA_DOUBLE, f0);
+      MemorySegment s1 = a.allocateArray(JAVA_DOUBLE, f1);
+      int rc = (int) TRANSFORMS[which].invokeExact(ctx, in, out, batch, n, levels, s0, s1, f0.length, flags);
+      if (rc != 0) throw new IllegalStateException(NAMES[which] + " failed (" + rc + "): " + lastError());
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  /** Convenience for the double[] API: copy in, transform, copy out (the reference never mutates its input). */
+  public static double[] run(int which, MemorySegment ctx, double[] in, long batch, long n, int levels, int outLen,
+      double[] f0, double[] f1, int flags) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment si = a.allocateArray(JAVA_DOUBLE, in);
+      MemorySegment so = a.allocateArray(JAVA_DOUBLE, outLen);
+      run(which, ctx, si, so, batch, n, levels, f0, f1, flags);
+      return so.toArray(JAVA_DOUBLE);
+    }
+  }
+}

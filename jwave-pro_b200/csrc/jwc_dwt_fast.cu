@@ -198,10 +198,11 @@ __global__ void __launch_bounds__(256, 3) dwt_fwd_pass_kernel(const __grid_const
     const int st_in = len_in + (len_in & 1) + 2 * kDwtR, st_out = len_out + (len_out & 1) + 2 * kDwtR;
     const int own = tlen >> jj;                       // outputs of each child that belong to this tile
     const int parents = TREE ? (1 << (jj - 1)) : 1;
-    // rows per item: as many as RMAX while every thread still gets an item, fewer on the small (deep) levels
-    if (parents * ((len_out + RMAX - 1) / RMAX) >= nt || RMAX == 1)
+    // rows per item: RMAX unless that would leave more than 3/4 of the threads without an item (deep, small levels).
+    // Small R costs shared-memory bandwidth (the window overlap L/2-1 and the tap loads are paid per item).
+    if (4 * parents * ((len_out + RMAX - 1) / RMAX) >= nt || RMAX == 1)
       ana_level<L, RMAX, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
-    else if (parents * ((len_out + 2) / 3) >= nt)
+    else if (4 * parents * ((len_out + 2) / 3) >= nt)
       ana_level<L, 3, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
     else
       ana_level<L, 1, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
@@ -411,9 +412,9 @@ __global__ void __launch_bounds__(256, 3) dwt_inv_pass_kernel(const __grid_const
     const int np = (hl_out >> 1) + (tlen >> jj);          // output pairs per parent
     const int off = hl_in - (hl_out >> 1) - (L / 2 - 1);   // first child index read by pair 0
     const int parents = TREE ? (1 << (jj - 1)) : 1;
-    if (parents * ((np + RMAX - 1) / RMAX) >= nt || RMAX == 1)
+    if (4 * parents * ((np + RMAX - 1) / RMAX) >= nt || RMAX == 1)
       syn_level<L, RMAX, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
-    else if (parents * ((np + 2) / 3) >= nt)
+    else if (4 * parents * ((np + 2) / 3) >= nt)
       syn_level<L, 3, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
     else
       syn_level<L, 1, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);

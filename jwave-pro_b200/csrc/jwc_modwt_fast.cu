@@ -89,8 +89,12 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = 1 << a.logP;
-  const int oV1 = a.vcap, oW0 = 2 * a.vcap, oW1 = 2 * a.vcap + P * a.T2;
-  const int oT = oW1 + P * a.T2;                   // tap copy (kTapDoubles), then the mbarrier
+  // passes on >= 4 phases (all strides >= 4 doubles = one 32-byte sector per row) store W straight from registers;
+  // only the single-phase pass needs the shared-memory staging tiles to make its stride-1/2 levels coalesced
+  const bool direct_w = (a.logP >= 2);
+  const int wtile = direct_w ? 0 : P * a.T2;
+  const int oV1 = a.vcap, oW0 = 2 * a.vcap, oW1 = 2 * a.vcap + wtile;
+  const int oT = oW1 + wtile;                      // tap copy (kTapDoubles), then the mbarrier
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oT + kTapDoubles);
   if (L > kUniformTapsMax) {
     for (int t = threadIdx.x; t < JWC_MAX_TAPS; t += blockDim.x) {
@@ -168,6 +172,8 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
     const int nrb = (rows + R - 1) / R;
     const int items = nrb << sh;
     const int span = (R - 1) << sh;
+    double* gw = co_b + (int64_t)(a.j0 + jj - 1) * a.N + i0 * S0 + ph0;   // direct_w: W row of this level, tile origin
+    const int64_t gstep = ((int64_t)s >> a.logP) * S0;                      // global distance of two rows of an item
     for (int w = tid; w < items; w += nt) {
       const int rb = w >> sh, c = w & (s - 1);
       const int rel0 = ((rb * R) << sh) + c;
@@ -186,7 +192,19 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
         }
       } else {
         fwd_item<L, R, true>(smem + oin + ef + span, s, f, smem + oT, av, aw);
-        if (full && ef >= eW) {
+        if (direct_w) {
+          // virtual position e -> row r = (e - eW) >> logP, phase p = (e - eW) & (P - 1); rows of one item are s/P apart
+          const int v0 = ef - eW;   // may be negative for an item that starts in the halo
+          double* g0 = gw + ((int64_t)(v0 >> a.logP)) * S0 + (v0 & (P - 1));
+#pragma unroll
+          for (int q = 0; q < R; q++) {
+            const int e = ef + (q << sh);
+            if (full || rel0 + (q << sh) < len) {
+              smem[oout + e] = av[q];
+              if (e >= eW) g0[q * gstep] = aw[q];
+            }
+          }
+        } else if (full && ef >= eW) {
 #pragma unroll
           for (int q = 0; q < R; q++) {
             smem[oout + ef + (q << sh)] = av[q];
@@ -220,7 +238,7 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
     } else {
       __syncthreads();
       const int nv = (jj == a.k) ? 2 : 1;
-      for (int v = 0; v < nv; v++) {
+      for (int v = direct_w ? 1 : 0; v < nv; v++) {
         const double* src = v ? vres : wst;
         double* dst = v ? vo_b : (co_b + wrow);
         if (a.mode == MODE_VEC2) {

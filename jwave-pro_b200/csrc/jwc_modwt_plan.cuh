@@ -45,6 +45,7 @@ inline int64_t modwt_smem_doubles(bool inverse, int P, int T2, int Hp, int k) {
   const int64_t pad = (int64_t)kModwtR * P * ((int64_t)1 << (k - 1));
   const int64_t vcap = (int64_t)P * (T2 + Hp) + pad;
   if (inverse) return 4 * (vcap + (vcap & 1));                       // V0 V1 W0 W1, all tile+halo sized
+  if (P >= 4) return 2 * (vcap + (vcap & 1));                        // V0 V1; W goes straight from registers to HBM
   return 2 * (vcap + (vcap & 1)) + 2 * (int64_t)P * T2;              // V0 V1 + two W staging tiles
 }
 
