@@ -289,10 +289,9 @@ def main():
     total_ms = max(e[0].elapsed_time(e[-1]) for e in ev)
     fwd_ms = max(sum(e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(args.steps)) for e in ev) / args.steps
     inv_ms = max(sum(e[2 * k + 1].elapsed_time(e[2 * k + 2]) for k in range(args.steps)) for e in ev) / args.steps
-    if distributed:
-        t = torch.tensor([total_ms, fwd_ms, inv_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, fwd_ms, inv_ms = [float(v) for v in t.tolist()]
+    if distributed:   # device time = max over ranks
+        from jwave_pro_b200.sharding import reduce_max
+        total_ms, fwd_ms, inv_ms = reduce_max([total_ms, fwd_ms, inv_ms], device="cuda")
     ms_per_step = total_ms / args.steps
     samples_per_step = 2.0 * batch * n * n_gpus
     value = samples_per_step / (ms_per_step * 1e-3) / 1e9
@@ -333,9 +332,8 @@ def main():
             step()
         e_ms = (time.perf_counter() - t0) * 1e3 / esteps
         if distributed:
-            t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
+            from jwave_pro_b200.sharding import reduce_max
+            e_ms = reduce_max([e_ms], device="cuda")[0]
         assert float(np.max(np.abs(R - X))) <= 1e-10
         io = (1 + out_rows) * eb * n * 8 * (world if distributed else 1)
         e2e = {"value": 2.0 * eb * n * (world if distributed else 1) / (e_ms * 1e-3) / 1e9, "unit": "Gsamples/s",

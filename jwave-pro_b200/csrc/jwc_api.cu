@@ -112,7 +112,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
   int64_t in_per, out_per;
   io_sizes(op, n, levels, &in_per, &out_per);
   const int64_t per_sig_bytes = (in_per + out_per) * (int64_t)sizeof(double);
-  int64_t chunk_mb = ctx->tune.h2d_chunk_mb > 0 ? ctx->tune.h2d_chunk_mb : 512;
+  int64_t chunk_mb = ctx->tune.h2d_chunk_mb > 0 ? ctx->tune.h2d_chunk_mb : 128;   // in + out bytes per chunk
   int64_t chunk = (chunk_mb << 20) / per_sig_bytes;
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;

@@ -1,0 +1,83 @@
+// C++ host-mirror test (reads like the reference's JUnit tests): KATs from MODWTTransformTest.java:39-71,
+// SteppingTest.java:37-179, error behaviour from MODWT1DInterfaceTest.java:108-137.  Needs a GPU; run by
+// tests/test_cpp_mirror.py (gpu-marked).  Exit code 0 = all checks passed.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/jwave_cuda.hpp"
+#include "../../include/jwc_filters_generated.h"
+
+using namespace jwave;
+
+static int fails = 0;
+#define CHECK(c) do { if (!(c)) { printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); fails++; } } while (0)
+
+static Wavelet make(const char* cls) {
+  for (int i = 0; i < jwc_num_wavelet_tables; i++)
+    if (!strcmp(jwc_wavelet_tables[i].cls, cls))
+      return Wavelet(jwc_wavelet_tables[i].name, std::vector<double>(jwc_wavelet_tables[i].scaling_decom, jwc_wavelet_tables[i].scaling_decom + jwc_wavelet_tables[i].L));
+  throw std::runtime_error("no such wavelet");
+}
+
+int main() {
+  auto ctx = std::make_shared<Context>();
+  {  // MODWT Haar level 1 of [1..8]
+    CudaMODWTTransform t(make("Haar1"), ctx);
+    std::vector<double> x = {1, 2, 3, 4, 5, 6, 7, 8};
+    auto c = t.forwardMODWT(x, 1);
+    const double d1[8] = {-3.5, .5, .5, .5, .5, .5, .5, .5}, a1[8] = {4.5, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5};
+    for (int i = 0; i < 8; i++) { CHECK(std::fabs(c[0][i] - d1[i]) < 1e-9); CHECK(std::fabs(c[1][i] - a1[i]) < 1e-9); }
+    auto xr = t.inverseMODWT(c);
+    for (int i = 0; i < 8; i++) CHECK(std::fabs(xr[i] - x[i]) < 1e-9);
+    auto flat = t.forward(x, 2);
+    CHECK(flat.size() == 24);
+    auto back = t.reverse(flat, 2);
+    for (int i = 0; i < 8; i++) CHECK(std::fabs(back[i] - x[i]) < 1e-9);
+    auto back2 = t.reverse(flat);   // level search: 24 = 8 * 3
+    for (int i = 0; i < 8; i++) CHECK(std::fabs(back2[i] - x[i]) < 1e-9);
+    bool thrown = false;
+    try { t.forwardMODWT(x, 0); } catch (const std::invalid_argument& e) { thrown = strstr(e.what(), "at least 1") != nullptr; }
+    CHECK(thrown);
+    thrown = false;
+    try { t.forwardMODWT(x, 4); } catch (const std::invalid_argument& e) { thrown = strstr(e.what(), "exceeds theoretical limit 3") != nullptr; }
+    CHECK(thrown);
+    thrown = false;
+    try { t.forward(std::vector<double>(7, 1.0), 2); } catch (const JWaveFailure& e) { thrown = strstr(e.what(), "2^p") != nullptr; }
+    CHECK(thrown);
+    CHECK(t.forwardMODWT({}, 3).size() == 4);
+  }
+  // all-ones ladders for every in-scope wavelet, FWT and WPT, N = 64
+  for (int wi = 0; wi < jwc_num_wavelet_tables; wi++) {
+    Wavelet w(jwc_wavelet_tables[wi].name, std::vector<double>(jwc_wavelet_tables[wi].scaling_decom, jwc_wavelet_tables[wi].scaling_decom + jwc_wavelet_tables[wi].L));
+    CudaFastWaveletTransform fwt(w, ctx);
+    CudaWaveletPacketTransform wpt(w, ctx);
+    std::vector<double> ones(64, 1.0);
+    for (int p = 0; p <= 6; p++) {
+      auto a = fwt.forward(ones, p), b = wpt.forward(ones, p);
+      for (int i = 0; i < 64; i++) {
+        const double e = (i < (64 >> p)) ? std::pow(2.0, p / 2.0) : 0.0;
+        CHECK(std::fabs(a[i] - e) < 1e-8);
+        CHECK(std::fabs(b[i] - e) < 1e-8);
+      }
+      auto ra = fwt.reverse(a, p), rb = wpt.reverse(b, p);
+      for (int i = 0; i < 64; i++) { CHECK(std::fabs(ra[i] - 1.0) < 1e-8); CHECK(std::fabs(rb[i] - 1.0) < 1e-8); }
+    }
+  }
+  {
+    CudaFastWaveletTransform fwt(make("Daubechies4"), ctx);
+    CHECK(fwt.getName() == "Fast Wavelet Transform");
+    bool thrown = false;
+    try { fwt.forward(std::vector<double>(17, 1.0), 2); } catch (const JWaveFailure& e) { thrown = strstr(e.what(), "2^p") != nullptr; }
+    CHECK(thrown);
+    thrown = false;
+    try { fwt.forward(std::vector<double>(8, 1.0), 10); } catch (const JWaveFailure& e) { thrown = strstr(e.what(), "out of range") != nullptr; }
+    CHECK(thrown);
+    auto m = fwt.decompose(std::vector<double>(16, 1.0));
+    CHECK(m.size() == 5);
+    auto r = fwt.recompose(m, 3);
+    for (double v : r) CHECK(std::fabs(v - 1.0) < 1e-8);
+  }
+  printf(fails ? "%d checks FAILED\n" : "host mirror ok\n", fails);
+  return fails ? 1 : 0;
+}
