@@ -90,19 +90,17 @@ inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, d
   // bulk (TMA) copies need even piece lengths: forward T >= 2, inverse (T >> k) even
   const bool even_ok = in.inverse ? ((T >> k) % 2 == 0) : (T >= 2);
   out->mode = (in.aligned16 && even_ok) ? DWT_BULK : DWT_SCALAR;
-  // threads: small CTAs (more of them resident per SM hide the per-level barriers better); go up only if the lane
-  // efficiency (useful items / issued thread-rounds) improves by more than 5 %
-  int thr = in.threads_override > 0 ? in.threads_override : 128;
-  double eff = 0;
-  for (int cand = thr; cand <= (in.threads_override > 0 ? thr : 256); cand += 32) {
+  // threads: 128 (measured best on B200 for FWT db8 and WPT sym8: more resident CTAs hide the per-level barriers)
+  const int thr = in.threads_override > 0 ? in.threads_override : 128;
+  double eff;
+  {
     double useful = 0, issued = 0;
     for (int jj = 1; jj <= k; jj++) {
       const int64_t it = dwt_items(in, k, jj, T);
       useful += (double)it;
-      issued += (double)(((it + cand - 1) / cand) * cand);
+      issued += (double)(((it + thr - 1) / thr) * thr);
     }
-    const double e = issued > 0 ? useful / issued : 1.0;
-    if (e > eff + 0.05) { eff = e; thr = cand; }
+    eff = issued > 0 ? useful / issued : 1.0;
   }
   out->threads = thr;
   // time model per sample of the pass input (ps)

@@ -36,6 +36,14 @@ void debug_plan(const char* what, const ModwtPlan& plan, int64_t n, int levels, 
   fprintf(stderr, "\n");
 }
 
+// CTAs resident on the whole device for this launch shape ~ one wave; that is how far ahead tiles are pulled into L2
+int prefetch_distance(jwc_ctx* ctx, const DeviceSlot& dev, size_t smem, int threads) {
+  (void)smem; (void)threads;
+  if (ctx->tune.l2_prefetch < 0) return 0;
+  if (ctx->tune.l2_prefetch > 0) return ctx->tune.l2_prefetch;
+  return 2 * dev.sm_count;   // measured on B200: ~2 CTAs per SM ahead is best, a whole wave ahead already evicts
+}
+
 struct FwdPassArgs {
   const double* in;   // V_{j0}
   double* coeffs;     // coefficient block base
@@ -43,6 +51,8 @@ struct FwdPassArgs {
   int64_t in_sig, coeff_sig, vout_sig;
   int64_t N, Nd;
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
+  int pf_dist;   // L2 prefetch distance in CTAs (0 = off): the tile of CTA blockIdx + pf_dist is pulled into L2
+  unsigned nblocks;
 };
 
 // Long filters: 2L taps do not fit the uniform-register file (63 x 32 bit), and ptxas then feeds every DFMA through
@@ -130,6 +140,15 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
         const uint32_t head = (uint32_t)(-g0);
         ptx::bulk_g2s(smem, in_b + (a.N + g0), head * 8u, bar);
         ptx::bulk_g2s(smem + head, in_b, ((uint32_t)rows_in - head) * 8u, bar);
+      }
+      if (a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {
+        // roughly one wave ahead: the CTA that will own tile blockIdx + pf_dist finds its input in L2
+        int64_t nb = (int64_t)blockIdx.x + a.pf_dist;
+        const int ti2 = (int)(nb % a.tiles_i);
+        const int64_t b2 = nb / a.tiles_i;   // groups == 1 in bulk mode
+        const int64_t i2 = (int64_t)ti2 * a.T2;
+        const int64_t l2 = (a.Nd - i2 < a.T2) ? (a.Nd - i2) : a.T2;
+        ptx::bulk_prefetch_l2(a.in + b2 * a.in_sig + i2, (uint32_t)l2 * 8u);
       }
       ptx::mbar_wait(bar, 0);   // one thread sleeps on the mbarrier, the CTA sleeps on the hardware barrier
     }
@@ -329,6 +348,8 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     a.vcap = p.vcap; a.mode = p.mode;
     const int64_t nblocks = (int64_t)a.tiles_i * a.groups * batch;
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+    a.nblocks = (unsigned)nblocks;
+    a.pf_dist = (p.mode == MODE_BULK) ? prefetch_distance(ctx, dev, p.smem, p.threads) : 0;
     int rc = dispatch_fwd_pass(ctx, st, a, f, L, p.threads, p.smem, nblocks);
     if (rc != JWC_OK) return rc;
     vin = a.vout; vin_sig = a.vout_sig;
@@ -356,6 +377,8 @@ struct InvPassArgs {
   int64_t vin_sig, coeff_sig, vout_sig;
   int64_t N, Nd;
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
+  int pf_dist;
+  unsigned nblocks;
 };
 
 template <int L, int R>
@@ -459,6 +482,16 @@ __global__ void __launch_bounds__(256, 3) modwt_inv_pass_kernel(const __grid_con
       ptx::fence_mbar_init();
     }
     __syncthreads();
+  }
+  if (bulk && a.pf_dist > 0 && tid <= a.k && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {
+    // one wave ahead: thread t pulls the W_{j0+t} tile (t = 1..k) resp. the V tile (t = 0) of CTA blockIdx + pf_dist into L2
+    int64_t nb = (int64_t)blockIdx.x + a.pf_dist;
+    const int ti2 = (int)(nb % a.tiles_i);
+    const int64_t b2 = nb / a.tiles_i;
+    const int64_t i2 = (int64_t)ti2 * a.T2;
+    const int64_t l2 = (a.Nd - i2 < a.T2) ? (a.Nd - i2) : a.T2;
+    const double* src = (tid == 0) ? (a.vin + b2 * a.vin_sig) : (a.coeffs + b2 * a.coeff_sig + (int64_t)(a.j0 + tid - 1) * a.N);
+    ptx::bulk_prefetch_l2(src + i2, (uint32_t)l2 * 8u);
   }
   // prologue: V_{j0+k} and W_{j0+k}
   {
@@ -602,6 +635,8 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     a.vcap = p.vcap; a.mode = p.mode;
     const int64_t nblocks = (int64_t)a.tiles_i * a.groups * batch;
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+    a.nblocks = (unsigned)nblocks;
+    a.pf_dist = (p.mode == MODE_BULK && ctx->tune.l2_prefetch > 0) ? ctx->tune.l2_prefetch : 0;   // off by default: measured slower
     int rc = dispatch_inv_pass(ctx, st, a, f, L, p.threads, p.smem, nblocks);
     if (rc != JWC_OK) return rc;
     vin = a.vout; vin_sig = a.vout_sig;
