@@ -70,7 +70,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
@@ -168,8 +168,8 @@ def run_reference(args, kind, cls, levels, batch, n, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override signals per GPU (debug; invalidates the headline)")
@@ -301,8 +301,16 @@ def main():
     bps = algorithmic_bytes_per_sample(kind, levels)
     fwd_gbs = bps * batch * n / (fwd_ms * 1e-3) / 1e9
     inv_gbs = bps * batch * n / (inv_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:   # measured DRAM bytes of this kernel from the committed ncu capture, scaled to this launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if args.workload in tj:
+            traffic = tj[args.workload]["forward_bytes_per_sample"] * batch * n
+            traffic_src = "profiles/r1_traffic.json (ncu --set full capture at a smaller batch, scaled per sample)"
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak,
-                "traffic": None, "kernel": "%s forward" % kind, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "%s forward" % kind, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bps * batch * n, "avg_ms": fwd_ms,
                 "inverse": {"achieved": inv_gbs, "frac": inv_gbs / peak, "avg_ms": inv_ms}}
 
