@@ -342,3 +342,24 @@ def test_fwt_wpt_full_size_properties(jw, gpu_ctx, oracle, kind, cls, n, lvl, ba
     t.forwardDevice(z.data_ptr(), cz.data_ptr(), 8, n, lvl, stream=st)
     torch.cuda.synchronize()
     assert float((cz - (2.0 * c[:8] + 0.5 * cy)).abs().max()) <= 1e-11
+
+
+def test_multi_device_context_shards_by_signal(jw, oracle):
+    """jwc_create(devices...) fans a host batch out over the devices (contiguous blocks of signals, no collective)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    ctx = jw.Context(list(range(min(ndev, 4))))
+    assert ctx.num_devices() == min(ndev, 4)
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaMODWTTransform(w, context=ctx)
+    X = _inputs(5, 37, 4096)
+    ref, (g, h) = _modwt_oracle(oracle, w, X, 5)
+    got = t.forwardMODWTBatch(X, 5)
+    assert _maxerr(got, ref, X) <= TOL
+    assert _maxerr(t.inverseMODWTBatch(got), X, X) <= PR_TOL
+    f = jw.CudaFastWaveletTransform(w, context=ctx)
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    assert _maxerr(f.forwardBatch(X, 12), oracle.batch("fwt_fwd", X, 12, s, wv, nthreads=8), X) <= TOL
+    ctx.close()
