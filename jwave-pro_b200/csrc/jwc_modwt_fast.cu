@@ -92,6 +92,19 @@ __device__ __forceinline__ void fwd_item(const double* __restrict__ top, int s, 
   }
 }
 
+// row index modulo the decimated signal length: one conditional add/subtract covers every tile whose halo is shorter
+// than the signal; only the pathological multi-wrap shapes pay for the 64-bit modulo
+__device__ __forceinline__ int64_t wrap_row(int64_t i, int64_t nd) {
+  if (i < 0) {
+    i += nd;
+    if (i < 0) { i %= nd; if (i < 0) i += nd; }
+  } else if (i >= nd) {
+    i -= nd;
+    if (i >= nd) i %= nd;
+  }
+  return i;
+}
+
 template <int L, int R>
 __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
@@ -158,9 +171,8 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
     const int hp2 = P >> 1;  // 16-byte chunks per row
     const int chunks = rows_in * hp2;
     for (int q = tid; q < chunks; q += nt) {
-      const int r = q / hp2, pp = (q - r * hp2) * 2;
-      int64_t i = (i0 - a.Hp + r) % a.Nd;
-      if (i < 0) i += a.Nd;
+      const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
+      const int64_t i = wrap_row(i0 - a.Hp + r, a.Nd);
       ptx::cp_async16(smem + r * P + pp, in_b + i * S0 + ph0 + pp);
     }
     ptx::cp_async_commit_wait_all();
@@ -169,8 +181,7 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
     const int total = rows_in * P;
     for (int e = tid; e < total; e += nt) {
       const int r = e >> a.logP, p = e & (P - 1);
-      int64_t i = (i0 - a.Hp + r) % a.Nd;
-      if (i < 0) i += a.Nd;
+      const int64_t i = wrap_row(i0 - a.Hp + r, a.Nd);
       smem[e] = in_b[i * S0 + ph0 + p];
     }
     __syncthreads();
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
         if (a.mode == MODE_VEC2) {
           const int hp2 = P >> 1, chunks = tlen2 * hp2;
           for (int q = tid; q < chunks; q += nt) {
-            const int r = q / hp2, pp = (q - r * hp2) * 2;
+            const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
             const double2 val = *reinterpret_cast<const double2*>(src + r * P + pp);
             *reinterpret_cast<double2*>(dst + (i0 + r) * S0 + ph0 + pp) = val;
           }
@@ -427,8 +438,8 @@ __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst
   } else if (a.mode == MODE_VEC2) {
     const int hp2 = P >> 1, chunks = rows * hp2;
     for (int q = tid; q < chunks; q += nt) {
-      const int r = q / hp2, pp = (q - r * hp2) * 2;
-      const int64_t i = (i_start + r) % a.Nd;
+      const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
+      const int64_t i = wrap_row(i_start + r, a.Nd);
       ptx::cp_async16(dst + r * P + pp, src_b + i * S0 + ph0 + pp);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -436,7 +447,7 @@ __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst
     const int total = rows * P;
     for (int e = tid; e < total; e += nt) {
       const int r = e >> a.logP, p = e & (P - 1);
-      const int64_t i = (i_start + r) % a.Nd;
+      const int64_t i = wrap_row(i_start + r, a.Nd);
       dst[e] = src_b[i * S0 + ph0 + p];
     }
   }
@@ -556,7 +567,7 @@ __global__ void __launch_bounds__(256, 3) modwt_inv_pass_kernel(const __grid_con
   } else if (a.mode == MODE_VEC2) {
     const int hp2 = P >> 1, chunks = tlen2 * hp2;
     for (int q = tid; q < chunks; q += nt) {
-      const int r = q / hp2, pp = (q - r * hp2) * 2;
+      const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
       *reinterpret_cast<double2*>(vo_b + (i0 + r) * S0 + ph0 + pp) = *reinterpret_cast<const double2*>(res + r * P + pp);
     }
   } else {
