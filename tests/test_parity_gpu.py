@@ -363,3 +363,24 @@ def test_multi_device_context_shards_by_signal(jw, oracle):
     s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
     assert _maxerr(f.forwardBatch(X, 12), oracle.batch("fwt_fwd", X, 12, s, wv, nthreads=8), X) <= TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("family", ["Haar1", "Daubechies", "Symlet", "Coiflet"])
+def test_every_wavelet_through_the_fused_kernels(jw, gpu_ctx, oracle, family):
+    """Every filter length (every template instantiation of the fused kernels, L = 2..40) against the oracle:
+    MODWT J=5, FWT and WPT 6 levels on 3 signals of 8192 samples; tolerance 1e-12 * max|x|."""
+    n, batch = 8192, 3
+    X = _inputs(len(family), batch, n)
+    for cls in [c for c in jw.wavelets.ALL_CLASSES if c.startswith(family)]:
+        w = jw.wavelets.create(cls)
+        s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+        t = jw.CudaMODWTTransform(w)
+        ref, (g, h) = _modwt_oracle(oracle, w, X, 5)
+        got = t.forwardMODWTBatch(X, 5)
+        assert _maxerr(got, ref, X) <= TOL, cls
+        assert _maxerr(t.inverseMODWTBatch(ref), oracle.batch("modwt_inv", ref, 5, g, h, nthreads=8), X) <= TOL, cls
+        for T, kind in ((jw.CudaFastWaveletTransform, "fwt"), (jw.CudaWaveletPacketTransform, "wpt")):
+            tr = T(w)
+            r = oracle.batch(kind + "_fwd", X, 6, s, wv, nthreads=8)
+            assert _maxerr(tr.forwardBatch(X, 6), r, X) <= TOL, (cls, kind)
+            assert _maxerr(tr.reverseBatch(r, 6), oracle.batch(kind + "_rev", r, 6, s, wv, nthreads=8), X) <= TOL, (cls, kind)
