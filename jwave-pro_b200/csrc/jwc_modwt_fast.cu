@@ -324,7 +324,8 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   pin.n = n; pin.J = levels; pin.L = L;
   pin.aligned16 = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_coeffs)) & 15) == 0;
   // measured on B200 (C2): forward best with 2 large CTAs per SM (113 KB), inverse best with 3 (75 KB)
-  pin.smem_budget = ctx->tune.modwt_smem > 0 ? ctx->tune.modwt_smem : 113000;
+  // (fp64-bound long filters prefer 3 CTAs per SM: db20 J8 34.9 ms at 75 KB vs 37.3 ms at 113 KB)
+  pin.smem_budget = ctx->tune.modwt_smem > 0 ? ctx->tune.modwt_smem : (L <= 10 ? 113000 : 75776);
   if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
   pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
   pin.threads_override = ctx->tune.modwt_threads;
