@@ -75,6 +75,16 @@ __device__ __forceinline__ void scalar_load_circ(double* dst, const double* base
   }
 }
 
+// Taps for long filters come from the kernel-parameter constant bank through an index the compiler cannot prove
+// uniform: that makes every tap one LDC.64 into an ordinary register.  (Uniform-register operands run out at 2L > 31
+// taps and ptxas then shuttles every tap through LDC + R2UR; a shared-memory copy read with broadcast LDS.128 costs a
+// full 4-wavefront LSU slot per load -- measured: 48 % of all shared-memory wavefronts of the db8 FWT kernel.)
+__device__ __forceinline__ const double* const_taps(const FilterPair& f) {
+  int z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return reinterpret_cast<const double*>(&f) + z;   // f0 at [0, 64), f1 at [64, 128)
+}
+
 // =========================================================================================================================
 // forward (analysis)
 // =========================================================================================================================
@@ -117,6 +127,9 @@ __device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int
                                           int st_out, int len_out, int own, int parents, int tid, int nt) {
   const int nb = (len_out + R - 1) / R;
   const int items = parents * nb;
+  // tap source: constant bank for 10 < L <= 20, shared-memory copy above (ptxas spills the hoisted LDC results there)
+  const double* ctaps = (L <= 20) ? const_taps(f) : (smem + oT);
+#pragma unroll 1
   for (int w = tid; w < items; w += nt) {
     const int q = TREE ? (w / nb) : 0;
     const int i0 = (w - q * nb) * R;
@@ -125,7 +138,7 @@ __device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int
     const int olo = oout + (2 * q) * st_out + i0, ohi = olo + st_out;
     const bool full = i0 + R <= len_out;
     if (!TREE && i0 >= own) {   // FWT: the halo part of D is produced by the neighbouring tile
-      ana_item<L, R, false>(px, f, smem + oT, lo, hi);
+      ana_item<L, R, false>(px, f, ctaps, lo, hi);
       if (full) {
 #pragma unroll
         for (int r = 0; r < R; r++) smem[olo + r] = lo[r];
@@ -135,7 +148,7 @@ __device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int
           if (i0 + r < len_out) smem[olo + r] = lo[r];
       }
     } else {
-      ana_item<L, R, true>(px, f, smem + oT, lo, hi);
+      ana_item<L, R, true>(px, f, ctaps, lo, hi);
       if (full) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -155,7 +168,7 @@ __device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int
 }
 
 template <int L, int RMAX, bool TREE>
-__global__ void __launch_bounds__(256, 3) dwt_fwd_pass_kernel(const __grid_constant__ DwtPassArgs a,
+__global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(256, 3) dwt_fwd_pass_kernel(const __grid_const
 // latency except on its first tile.  Buffers: IN[2] (depth-0 set, then the even depths) and W (odd depths).
 // -------------------------------------------------------------------------------------------------------------------------
 template <int L, int RMAX, bool TREE>
-__global__ void __launch_bounds__(256, 3) dwt_fwd_pers_kernel(const __grid_constant__ DwtPassArgs a,
+__global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pers_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -426,12 +439,16 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int
                                           int st_out, int np, int off, int parents, int tid, int nt) {
   const int nb = (np + R - 1) / R;
   const int items = parents * nb;
+  // tap source: constant bank in the packet-tree kernel; the pyramid (FWT) instantiation spills with it, so it keeps
+  // the shared-memory copy
+  const double* ctaps = (TREE && L <= 20) ? const_taps(f) : (smem + oT);
+#pragma unroll 1
   for (int w = tid; w < items; w += nt) {
     const int q = TREE ? (w / nb) : 0;
     const int u0 = (w - q * nb) * R;
     const int clo = oin + (2 * q) * st_in + off + u0;
     double2 o[R];
-    syn_item<L, R>(smem + clo, smem + clo + st_in, f, smem + oT, o);
+    syn_item<L, R>(smem + clo, smem + clo + st_in, f, ctaps, o);
     double2* dst = reinterpret_cast<double2*>(smem + oout + q * st_out) + u0;
     if (u0 + R <= np) {
 #pragma unroll
@@ -445,10 +462,12 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int
 }
 
 template <int L, int RMAX, bool TREE>
-__global__ void __launch_bounds__(256, 3) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
+__global__ void __launch_bounds__(256, (L > 6 ? 2 : 3)) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
+  __shared__ int s_hl[16];   // halo table (dynamic indexing of a kernel-parameter array would go through local memory)
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < 16) s_hl[tid] = a.hl[tid];
   const int oT = 2 * a.cap;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
   if (L > kUniformTapsMaxDwt) {
@@ -468,17 +487,15 @@ __global__ void __launch_bounds__(256, 3) dwt_inv_pass_kernel(const __grid_const
   const double* in_b = a.in + b * a.in_sig;
 
   // geometry of depth jj: children arrays of length len = (tlen >> jj) + HLj, node length hn = h >> jj
-  auto len_of = [&](int jj) { return (tlen >> jj) + a.hl[jj]; };
+  auto len_of = [&](int jj) { return (tlen >> jj) + s_hl[jj]; };
   auto stride_of = [&](int jj) { const int l = len_of(jj); return l + (l & 1) + 2 * kDwtR; };
 
-  if (bulk) {
-    if (tid == 0) {
-      ptx::mbar_init(&bars[0], 1);
-      ptx::mbar_init(&bars[1], 1);
-      ptx::fence_mbar_init();
-    }
-    __syncthreads();
+  if (bulk && tid == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_mbar_init();
   }
+  __syncthreads();   // mbarriers, s_hl and the tap copy are visible
   if (bulk && a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {   // one wave ahead into L2
     int64_t nb = (int64_t)blockIdx.x + a.pf_dist;
     const int ti2 = (int)(nb % a.tiles);
@@ -500,7 +517,7 @@ __global__ void __launch_bounds__(256, 3) dwt_inv_pass_kernel(const __grid_const
   // ---- prologue: the depth-k set into buffer 0 ------------------------------------------------------------------------------
   {
     const int jj = a.k, len = len_of(jj), st = stride_of(jj);
-    const int64_t hn = a.h >> jj, start = (a0 >> jj) - a.hl[jj];
+    const int64_t hn = a.h >> jj, start = (a0 >> jj) - s_hl[jj];
     if (TREE) {
       const int leaves = 1 << jj;
       const double* src0 = in_b + (int64_t)p * a.h;       // leaf c of this node at + c * hn
@@ -533,7 +550,7 @@ __global__ void __launch_bounds__(256, 3) dwt_inv_pass_kernel(const __grid_const
     const int st_in = stride_of(jj), st_out = stride_of(jj - 1);
     if (!TREE && jj > 1) {   // prefetch D_{l0+jj-1} into the high-pass slot of the output buffer
       const int len = len_of(jj - 1);
-      const int64_t hn = a.h >> (jj - 1), start = (a0 >> (jj - 1)) - a.hl[jj - 1];
+      const int64_t hn = a.h >> (jj - 1), start = (a0 >> (jj - 1)) - s_hl[jj - 1];
       const double* dsrc = in_b + (a.N >> (a.l0 + jj - 1));
       if (bulk) {
         if (tid == 0) {
@@ -552,7 +569,7 @@ __global__ void __launch_bounds__(256, 3) dwt_inv_pass_kernel(const __grid_const
     } else {
       __syncthreads();
     }
-    const int hl_out = a.hl[jj - 1], hl_in = a.hl[jj];
+    const int hl_out = s_hl[jj - 1], hl_in = s_hl[jj];
     const int np = (hl_out >> 1) + (tlen >> jj);          // output pairs per parent
     const int off = hl_in - (hl_out >> 1) - (L / 2 - 1);   // first child index read by pair 0
     const int parents = TREE ? (1 << (jj - 1)) : 1;

@@ -58,6 +58,12 @@ struct FwdPassArgs {
 // Long filters: 2L taps do not fit the uniform-register file (63 x 32 bit), and ptxas then feeds every DFMA through
 // LDC + R2UR moves.  For L > kUniformTapsMax the taps are read from a shared-memory copy (broadcast LDS.64) into a
 // rolling window of R live taps per filter, loaded exactly when the sliding window first needs them.
+__device__ __forceinline__ const double* const_taps(const FilterPair& f) {
+  // index the compiler cannot prove uniform => every tap is one LDC.64 into an ordinary register (see jwc_dwt_fast.cu)
+  int z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return reinterpret_cast<const double*>(&f) + z;   // f0 at [0, 64), f1 at [64, 128)
+}
 constexpr int kUniformTapsMax = 10;
 constexpr int kTapDoubles = 2 * JWC_MAX_TAPS;   // shared-memory copy of FilterPair: f0 at [0..64), f1 at [64..128)
 
@@ -106,7 +112,7 @@ __device__ __forceinline__ int64_t wrap_row(int64_t i, int64_t nd) {
 }
 
 template <int L, int R>
-__global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
+__global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
   // shared memory is addressed as smem[int offset] everywhere: keeps the accesses plain LDS/STS with register offsets
   extern __shared__ __align__(128) double smem[];
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
   }
 
   // ---- k fused levels ---------------------------------------------------------------------------------------------
+  const double* ctaps = const_taps(f);
   const int eW = P * a.Hp;  // first virtual position whose W / final V is an output of this tile
   for (int jj = 1; jj <= a.k; jj++) {
     const int sh = a.logP + jj - 1;
@@ -204,14 +211,15 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
     const int span = (R - 1) << sh;
     double* gw = co_b + (int64_t)(a.j0 + jj - 1) * a.N + i0 * S0 + ph0;   // direct_w: W row of this level, tile origin
     const int64_t gstep = ((int64_t)s >> a.logP) * S0;                      // global distance of two rows of an item
-    for (int w = tid; w < items; w += nt) {
+  #pragma unroll 1
+  for (int w = tid; w < items; w += nt) {
       const int rb = w >> sh, c = w & (s - 1);
       const int rel0 = ((rb * R) << sh) + c;
       const int ef = e0 + rel0;
       const bool full = rel0 + span < len;
       double av[R], aw[R];
       if (ef + span < eW) {           // item entirely inside the halo: only V is needed by the next level
-        fwd_item<L, R, false>(smem + oin + ef + span, s, f, smem + oT, av, aw);
+        fwd_item<L, R, false>(smem + oin + ef + span, s, f, ctaps, av, aw);
         if (full) {
 #pragma unroll
           for (int q = 0; q < R; q++) smem[oout + ef + (q << sh)] = av[q];
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(256, 3) modwt_fwd_pass_kernel(const __grid_con
             if (rel0 + (q << sh) < len) smem[oout + ef + (q << sh)] = av[q];
         }
       } else {
-        fwd_item<L, R, true>(smem + oin + ef + span, s, f, smem + oT, av, aw);
+        fwd_item<L, R, true>(smem + oin + ef + span, s, f, ctaps, av, aw);
         if (direct_w) {
           // virtual position e -> row r = (e - eW) >> logP, phase p = (e - eW) & (P - 1); rows of one item are s/P apart
           const int v0 = ef - eW;   // may be negative for an item that starts in the halo
@@ -456,7 +464,7 @@ __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst
 }
 
 template <int L, int R>
-__global__ void __launch_bounds__(256, 3) modwt_inv_pass_kernel(const __grid_constant__ InvPassArgs a,
+__global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(const __grid_constant__ InvPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -513,6 +521,7 @@ __global__ void __launch_bounds__(256, 3) modwt_inv_pass_kernel(const __grid_con
     inv_issue_load(a, Vb(0), vin_b, i0, rows, ph0, &bars[0], tid, nt);
     inv_issue_load(a, Wb(0), co_b + (int64_t)(a.j0 + a.k - 1) * a.N, i0, rows, ph0, &bars[0], tid, nt);
   }
+  const double* ctaps = const_taps(f);
   for (int jj = a.k, u = 0; jj >= 1; --jj, ++u) {
     const int wb = u & 1;
     if (jj > 1) {  // prefetch W_{j0+jj-1} into the other W buffer (last read two barriers ago)
@@ -541,11 +550,12 @@ __global__ void __launch_bounds__(256, 3) modwt_inv_pass_kernel(const __grid_con
     const int nrb = (rows + R - 1) / R;
     const int items = nrb << sh;
     const int span = (R - 1) << sh;
-    for (int w = tid; w < items; w += nt) {
+  #pragma unroll 1
+  for (int w = tid; w < items; w += nt) {
       const int rb = w >> sh, c = w & (s - 1);
       const int rel0 = ((rb * R) << sh) + c;
       double o[R];
-      inv_item<L, R>(smem + ovin + rel0, smem + owin + rel0, s, f, smem + oT, o);
+      inv_item<L, R>(smem + ovin + rel0, smem + owin + rel0, s, f, ctaps, o);
       if (rel0 + span < len) {
 #pragma unroll
         for (int q = 0; q < R; q++) smem[ovout + rel0 + (q << sh)] = o[q];
