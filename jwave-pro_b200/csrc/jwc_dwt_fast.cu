@@ -441,10 +441,14 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int
   const int items = parents * nb;
   // tap source: constant bank in the packet-tree kernel; the pyramid (FWT) instantiation spills with it, so it keeps
   // the shared-memory copy
+  // tap source: constant bank for the packet tree (L <= 20); the pyramid (FWT) instantiation needs 128 registers
+  // with it and measured slower (db8 inverse 5.9 ms vs 4.9 ms), so it keeps the shared-memory copy
   const double* ctaps = (TREE && L <= 20) ? const_taps(f) : (smem + oT);
+  int zq;
+  asm volatile("mov.u32 %0, 0;" : "=r"(zq));   // opaque 0: keeps the pyramid instantiation on the same code shape as the tree one
 #pragma unroll 1
   for (int w = tid; w < items; w += nt) {
-    const int q = TREE ? (w / nb) : 0;
+    const int q = TREE ? (w / nb) : zq;
     const int u0 = (w - q * nb) * R;
     const int clo = oin + (2 * q) * st_in + off + u0;
     double2 o[R];
@@ -462,7 +466,7 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int
 }
 
 template <int L, int RMAX, bool TREE>
-__global__ void __launch_bounds__(256, (L > 6 ? 2 : 3)) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
+__global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L == 10) ? 2 : 3))) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   __shared__ int s_hl[16];   // halo table (dynamic indexing of a kernel-parameter array would go through local memory)
