@@ -88,10 +88,17 @@ __device__ __forceinline__ const double* const_taps(const FilterPair& f) {
 // =========================================================================================================================
 // forward (analysis)
 // =========================================================================================================================
-template <int L, int R, bool WITH_HI>
+// QMF variant: when the high-pass filter is the exact quadrature mirror of the low-pass one (every orthogonal wavelet
+// of the reference, wavelets/Wavelet.java:104-122: w[j] = (-1)^j s[L-1-j]) and 12 <= L <= 20, the L low-pass taps stay
+// RESIDENT in registers for the whole kernel (2L registers, fewer than the rolling window) and the high-pass taps are
+// the same registers read mirrored with a free sign flip: no tap loads in the inner loop at all.
+template <int L>
+constexpr bool qmf_supported() { return L >= 12 && L <= 20; }
+
+template <int L, int R, bool WITH_HI, bool QMF, int NS>
 __device__ __forceinline__ void ana_item(const double2* __restrict__ px, const FilterPair& f, const double* __restrict__ taps,
-                                         double (&lo)[R], double (&hi)[R]) {
-  constexpr bool ST = (L > kUniformTapsMaxDwt);
+                                         const double (&sreg)[NS], double (&lo)[R], double (&hi)[R]) {
+  constexpr bool ST = (L > kUniformTapsMaxDwt) && !QMF;
   constexpr int HL = L / 2;
 #pragma unroll
   for (int r = 0; r < R; r++) { lo[r] = 0.0; hi[r] = 0.0; }
@@ -111,20 +118,30 @@ __device__ __forceinline__ void ana_item(const double2* __restrict__ px, const F
     for (int r = 0; r < R; r++) {
       const int q = pp - r;   // tap pair index: j = 2q, 2q+1 (ascending j per output, the reference's order)
       if (q >= 0 && q < HL) {
-        lo[r] = fma(x.x, ST ? ts[2 * q] : f.f0[2 * q], lo[r]);
-        lo[r] = fma(x.y, ST ? ts[2 * q + 1] : f.f0[2 * q + 1], lo[r]);
-        if (WITH_HI) {
-          hi[r] = fma(x.x, ST ? tw[2 * q] : f.f1[2 * q], hi[r]);
-          hi[r] = fma(x.y, ST ? tw[2 * q + 1] : f.f1[2 * q + 1], hi[r]);
+        if (QMF) {
+          lo[r] = fma(x.x, sreg[(2 * q) % NS], lo[r]);
+          lo[r] = fma(x.y, sreg[(2 * q + 1) % NS], lo[r]);
+          if (WITH_HI) {   // w[2q] = +s[L-1-2q], w[2q+1] = -s[L-2-2q]
+            hi[r] = fma(x.x, sreg[(L - 1 - 2 * q) % NS], hi[r]);
+            hi[r] = fma(x.y, -sreg[(L - 2 - 2 * q) % NS], hi[r]);
+          }
+        } else {
+          lo[r] = fma(x.x, ST ? ts[2 * q] : f.f0[2 * q], lo[r]);
+          lo[r] = fma(x.y, ST ? ts[2 * q + 1] : f.f0[2 * q + 1], lo[r]);
+          if (WITH_HI) {
+            hi[r] = fma(x.x, ST ? tw[2 * q] : f.f1[2 * q], hi[r]);
+            hi[r] = fma(x.y, ST ? tw[2 * q + 1] : f.f1[2 * q + 1], hi[r]);
+          }
         }
       }
     }
   }
 }
 
-template <int L, int R, bool TREE>
-__device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int oT, int oin, int oout, int st_in,
-                                          int st_out, int len_out, int own, int parents, int tid, int nt) {
+template <int L, int R, bool TREE, bool QMF, int NS>
+__device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, const double (&sreg)[NS], int oT, int oin,
+                                          int oout, int st_in, int st_out, int len_out, int own, int parents, int tid,
+                                          int nt) {
   const int nb = (len_out + R - 1) / R;
   const int items = parents * nb;
   // tap source: constant bank for 10 < L <= 20, shared-memory copy above (ptxas spills the hoisted LDC results there)
@@ -138,7 +155,7 @@ __device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int
     const int olo = oout + (2 * q) * st_out + i0, ohi = olo + st_out;
     const bool full = i0 + R <= len_out;
     if (!TREE && i0 >= own) {   // FWT: the halo part of D is produced by the neighbouring tile
-      ana_item<L, R, false>(px, f, ctaps, lo, hi);
+      ana_item<L, R, false, QMF, NS>(px, f, ctaps, sreg, lo, hi);
       if (full) {
 #pragma unroll
         for (int r = 0; r < R; r++) smem[olo + r] = lo[r];
@@ -148,7 +165,7 @@ __device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int
           if (i0 + r < len_out) smem[olo + r] = lo[r];
       }
     } else {
-      ana_item<L, R, true>(px, f, ctaps, lo, hi);
+      ana_item<L, R, true, QMF, NS>(px, f, ctaps, sreg, lo, hi);
       if (full) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -167,11 +184,20 @@ __device__ __forceinline__ void ana_level(double* smem, const FilterPair& f, int
   }
 }
 
-template <int L, int RMAX, bool TREE>
+template <int L, int RMAX, bool TREE, bool QMF>
 __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
+  constexpr int NS = QMF ? L : 1;
+  double sreg[NS];
+  if (QMF) {
+    const double* ct = const_taps(f);
+#pragma unroll
+    for (int m = 0; m < NS; m++) sreg[m] = ct[m];
+  } else {
+    sreg[0] = 0.0;
+  }
   const int oT = 2 * a.cap;                         // tap copy, then the mbarrier
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
   if (L > kUniformTapsMaxDwt) {
@@ -226,11 +252,11 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
     // rows per item: RMAX unless that would leave more than 3/4 of the threads without an item (deep, small levels).
     // Small R costs shared-memory bandwidth (the window overlap L/2-1 and the tap loads are paid per item).
     if (4 * parents * ((len_out + RMAX - 1) / RMAX) >= nt || RMAX == 1)
-      ana_level<L, RMAX, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+      ana_level<L, RMAX, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
     else if (4 * parents * ((len_out + 2) / 3) >= nt)
-      ana_level<L, 3, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+      ana_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
     else
-      ana_level<L, 1, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+      ana_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
     // ---- ship what is final after this level ------------------------------------------------------------------------------
     const bool last = (jj == a.k);
     const bool vec_ok = bulk && (own & 1) == 0;
@@ -281,11 +307,20 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
 // already in flight (TMA into the other input buffer) while the current tile is computed, so no CTA ever waits for HBM
 // latency except on its first tile.  Buffers: IN[2] (depth-0 set, then the even depths) and W (odd depths).
 // -------------------------------------------------------------------------------------------------------------------------
-template <int L, int RMAX, bool TREE>
+template <int L, int RMAX, bool TREE, bool QMF>
 __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pers_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
+  constexpr int NS = QMF ? L : 1;
+  double sreg[NS];
+  if (QMF) {
+    const double* ct = const_taps(f);
+#pragma unroll
+    for (int m = 0; m < NS; m++) sreg[m] = ct[m];
+  } else {
+    sreg[0] = 0.0;
+  }
   const int oW = 2 * a.cap_in;
   const int oT = oW + a.cap_work;                    // tap copy, then two mbarriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
@@ -341,11 +376,11 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pers_kernel(con
       const int own = tlen >> jj;
       const int parents = TREE ? (1 << (jj - 1)) : 1;
       if (4 * parents * ((len_out + RMAX - 1) / RMAX) >= nt || RMAX == 1)
-        ana_level<L, RMAX, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+        ana_level<L, RMAX, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
       else if (4 * parents * ((len_out + 2) / 3) >= nt)
-        ana_level<L, 3, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+        ana_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
       else
-        ana_level<L, 1, TREE>(smem, f, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+        ana_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
       const bool last = (jj == a.k);
       const bool vec_ok = (own & 1) == 0;
       if (vec_ok) ptx::fence_proxy_async();
@@ -392,10 +427,11 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pers_kernel(con
 // =========================================================================================================================
 // inverse (synthesis)
 // =========================================================================================================================
-template <int L, int R>
+template <int L, int R, bool QMF, int NS>
 __device__ __forceinline__ void syn_item(const double* __restrict__ plo, const double* __restrict__ phi,
-                                         const FilterPair& f, const double* __restrict__ taps, double2 (&o)[R]) {
-  constexpr bool ST = (L > kUniformTapsMaxDwt);
+                                         const FilterPair& f, const double* __restrict__ taps, const double (&sreg)[NS],
+                                         double2 (&o)[R]) {
+  constexpr bool ST = (L > kUniformTapsMaxDwt) && !QMF;
   constexpr int HL = L / 2;
 #pragma unroll
   for (int r = 0; r < R; r++) { o[r].x = 0.0; o[r].y = 0.0; }
@@ -418,8 +454,13 @@ __device__ __forceinline__ void syn_item(const double* __restrict__ plo, const d
     for (int r = 0; r < R; r++) {
       const int q = r + HL - 1 - i;
       if (q >= 0 && q < HL) {
-        o[r].x = fma(ch, ST ? tw[2 * q] : f.f1[2 * q], fma(cl, ST ? ts[2 * q] : f.f0[2 * q], o[r].x));
-        o[r].y = fma(ch, ST ? tw[2 * q + 1] : f.f1[2 * q + 1], fma(cl, ST ? ts[2 * q + 1] : f.f0[2 * q + 1], o[r].y));
+        if (QMF) {
+          o[r].x = fma(ch, sreg[(L - 1 - 2 * q) % NS], fma(cl, sreg[(2 * q) % NS], o[r].x));
+          o[r].y = fma(ch, -sreg[(L - 2 - 2 * q) % NS], fma(cl, sreg[(2 * q + 1) % NS], o[r].y));
+        } else {
+          o[r].x = fma(ch, ST ? tw[2 * q] : f.f1[2 * q], fma(cl, ST ? ts[2 * q] : f.f0[2 * q], o[r].x));
+          o[r].y = fma(ch, ST ? tw[2 * q + 1] : f.f1[2 * q + 1], fma(cl, ST ? ts[2 * q + 1] : f.f0[2 * q + 1], o[r].y));
+        }
       }
     }
   }
@@ -434,9 +475,9 @@ __device__ __forceinline__ int inv_halo(int L, int jj) {
   return h;
 }
 
-template <int L, int R, bool TREE>
-__device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int oT, int oin, int oout, int st_in,
-                                          int st_out, int np, int off, int parents, int tid, int nt) {
+template <int L, int R, bool TREE, bool QMF, int NS>
+__device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, const double (&sreg)[NS], int oT, int oin,
+                                          int oout, int st_in, int st_out, int np, int off, int parents, int tid, int nt) {
   const int nb = (np + R - 1) / R;
   const int items = parents * nb;
   // tap source: constant bank in the packet-tree kernel; the pyramid (FWT) instantiation spills with it, so it keeps
@@ -452,7 +493,7 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int
     const int u0 = (w - q * nb) * R;
     const int clo = oin + (2 * q) * st_in + off + u0;
     double2 o[R];
-    syn_item<L, R>(smem + clo, smem + clo + st_in, f, ctaps, o);
+    syn_item<L, R, QMF, NS>(smem + clo, smem + clo + st_in, f, ctaps, sreg, o);
     double2* dst = reinterpret_cast<double2*>(smem + oout + q * st_out) + u0;
     if (u0 + R <= np) {
 #pragma unroll
@@ -465,9 +506,18 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, int
   }
 }
 
-template <int L, int RMAX, bool TREE>
+template <int L, int RMAX, bool TREE, bool QMF>
 __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L == 10) ? 2 : 3))) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
+  constexpr int NS = QMF ? L : 1;
+  double sreg[NS];
+  if (QMF) {
+    const double* ct = const_taps(f);
+#pragma unroll
+    for (int m = 0; m < NS; m++) sreg[m] = ct[m];
+  } else {
+    sreg[0] = 0.0;
+  }
   extern __shared__ __align__(128) double smem[];
   __shared__ int s_hl[16];   // halo table (dynamic indexing of a kernel-parameter array would go through local memory)
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -578,11 +628,11 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L =
     const int off = hl_in - (hl_out >> 1) - (L / 2 - 1);   // first child index read by pair 0
     const int parents = TREE ? (1 << (jj - 1)) : 1;
     if (4 * parents * ((np + RMAX - 1) / RMAX) >= nt || RMAX == 1)
-      syn_level<L, RMAX, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+      syn_level<L, RMAX, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
     else if (4 * parents * ((np + 2) / 3) >= nt)
-      syn_level<L, 3, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+      syn_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
     else
-      syn_level<L, 1, TREE>(smem, f, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+      syn_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
     if (bulk && jj == 1) ptx::fence_proxy_async();
     __syncthreads();
   }
@@ -600,15 +650,15 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L =
   }
 }
 
-template <int L, bool TREE, bool INV>
+template <int L, bool TREE, bool INV, bool QMF>
 int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int threads, size_t smem,
                     int64_t nblocks) {
   if (INV) {
-    auto kern = dwt_inv_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE>;
+    auto kern = dwt_inv_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
     JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   } else if (a.cap_in > 0) {
-    auto kern = dwt_fwd_pers_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE>;
+    auto kern = dwt_fwd_pers_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
     JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, dev = 0, sms = 0;
     JWC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -618,7 +668,7 @@ int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const F
     if (grid > nblocks) grid = nblocks;
     kern<<<(unsigned)grid, threads, smem, st>>>(a, f);
   } else {
-    auto kern = dwt_fwd_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE>;
+    auto kern = dwt_fwd_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
     JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   }
@@ -627,11 +677,29 @@ int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const F
   return JWC_OK;
 }
 
+// exact quadrature-mirror relation of the reference's orthogonal wavelets (Wavelet.java:109-113)
+bool is_qmf(const FilterPair& f, int L) {
+  for (int i = 0; i < L; i++) {
+    const double e = (i % 2 == 0) ? f.f0[L - 1 - i] : -f.f0[L - 1 - i];
+    if (!(f.f1[i] == e)) return false;
+  }
+  return true;
+}
+
 template <bool TREE, bool INV>
 int dispatch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int L, int threads,
                       size_t smem, int64_t nblocks) {
+  // forward only: the synthesis kernels gain nothing from it (measured) and the pyramid instantiation spills
+  if constexpr (!INV) if (L >= 12 && L <= 20 && ctx->tune.dwt_qmf >= 0 && is_qmf(f, L)) {
+    switch (L) {
+#define JWC_QCASE(LL) case LL: return launch_dwt_pass<LL, TREE, INV, true>(ctx, st, a, f, threads, smem, nblocks);
+      JWC_QCASE(12) JWC_QCASE(14) JWC_QCASE(16) JWC_QCASE(18) JWC_QCASE(20)
+#undef JWC_QCASE
+      default: break;
+    }
+  }
   switch (L) {
-#define JWC_CASE(LL) case LL: return launch_dwt_pass<LL, TREE, INV>(ctx, st, a, f, threads, smem, nblocks);
+#define JWC_CASE(LL) case LL: return launch_dwt_pass<LL, TREE, INV, false>(ctx, st, a, f, threads, smem, nblocks);
     JWC_CASE(2) JWC_CASE(4) JWC_CASE(6) JWC_CASE(8) JWC_CASE(10) JWC_CASE(12) JWC_CASE(14) JWC_CASE(16) JWC_CASE(18)
     JWC_CASE(20) JWC_CASE(22) JWC_CASE(24) JWC_CASE(26) JWC_CASE(28) JWC_CASE(30) JWC_CASE(32) JWC_CASE(34) JWC_CASE(36)
     JWC_CASE(38) JWC_CASE(40)

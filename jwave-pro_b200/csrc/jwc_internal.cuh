@@ -47,6 +47,7 @@ struct Tuning {
   int dwt_threads = 0;
   int dwt_group = 0;
   int dwt_smem = 0;
+  int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
   int dwt_persistent = 0;   // 1 = persistent CTAs with double-buffered TMA input (experimental, measured slower)
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
   int force_generic = 0;
