@@ -62,7 +62,9 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling of SM clock / throttle reasons.  Started before the warm-up (nvidia-smi takes a few hundred
+    ms to produce its first line); stop(t0, t1) keeps the samples whose timestamp lies inside the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -75,10 +77,12 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -86,23 +90,27 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 8:
+            if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             [nm for nm, v in zip(names, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if t0 is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        use = inside if inside else rows[-3:]
+        if use:
+            reasons = set()
+            for r in use:
+                reasons.update(r[3])
+            out.update(sm_mhz=float(np.median([r[1] for r in use])), sm_max_mhz=float(max(r[2] for r in use)),
+                       reasons=sorted(reasons), samples=len(use), samples_inside_timed_region=len(inside))
         return out
 
 
@@ -168,7 +176,7 @@ def run_reference(args, kind, cls, levels, batch, n, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -257,6 +265,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    clock = ClockSampler(devices[0]) if rank == 0 else None
     for _ in range(args.warmup):
         for s in range(len(devices)):
             fwd(s)
@@ -266,10 +275,10 @@ def main():
     pr = max(float((b[2] - b[0]).abs().max()) for b in bufs) if args.warmup > 0 else 0.0
 
     # ---- timed region ---------------------------------------------------------------------------------------------
-    clock = ClockSampler(devices[0]) if rank == 0 else None
     ev = []
     launches0 = ctx.launch_count()
     sync_all()
+    t_region0 = time.time()
     for s, d in enumerate(devices):
         with torch.cuda.device(d):
             st = bufs[s][3]
@@ -284,8 +293,9 @@ def main():
                 inv(s)
                 ev[s][2 * k + 2].record(bufs[s][3])
     sync_all()
+    t_region1 = time.time()
     launches = ctx.launch_count() - launches0
-    clocks = clock.stop() if clock else None
+    clocks = clock.stop(t_region0, t_region1) if clock else None
     total_ms = max(e[0].elapsed_time(e[-1]) for e in ev)
     fwd_ms = max(sum(e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(args.steps)) for e in ev) / args.steps
     inv_ms = max(sum(e[2 * k + 1].elapsed_time(e[2 * k + 2]) for k in range(args.steps)) for e in ev) / args.steps
