@@ -19,6 +19,7 @@
  *  - There is NO CPU fallback: every transform runs as CUDA kernels; without a usable device
  *    jwc_create() returns NULL.
  *  - Batches: `batch` independent signals of length n each; signal b starts at in + b*n.
+ *  - Input and output buffers of one call must not overlap (the reference never mutates its input either).
  *  - A context may be used from several host threads at once (calls are re-entrant; scratch memory is
  *    stream-ordered per call).  Filters are passed per call; the library keeps no filter state.
  */
