@@ -339,7 +339,6 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "dwt_group")) return &t.dwt_group;
   if (!strcmp(key, "dwt_smem")) return &t.dwt_smem;
   if (!strcmp(key, "dwt_qmf")) return &t.dwt_qmf;
-  if (!strcmp(key, "dwt_persistent")) return &t.dwt_persistent;
   if (!strcmp(key, "h2d_chunk_mb")) return &t.h2d_chunk_mb;
   if (!strcmp(key, "force_generic")) return &t.force_generic;
   if (!strcmp(key, "l2_prefetch")) return &t.l2_prefetch;

@@ -46,7 +46,6 @@ struct DwtPassArgs {
   int l0, k, T, tiles, nodes, cap, mode;
   int pf_dist;        // L2 prefetch distance in CTAs (0 = off)
   unsigned nblocks;
-  int cap_in, cap_work;   // persistent forward kernel: input buffers / work buffer capacities
   int hl[16];             // inverse: left halo of the depth-jj arrays (dwt_inv_halo), precomputed on the host
 };
 
@@ -302,128 +301,6 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
 }
 
 
-// -------------------------------------------------------------------------------------------------------------------------
-// persistent forward kernel: grid = resident CTAs, each walks tiles blockIdx.x, +gridDim.x, ...; the NEXT tile's input is
-// already in flight (TMA into the other input buffer) while the current tile is computed, so no CTA ever waits for HBM
-// latency except on its first tile.  Buffers: IN[2] (depth-0 set, then the even depths) and W (odd depths).
-// -------------------------------------------------------------------------------------------------------------------------
-template <int L, int RMAX, bool TREE, bool QMF>
-__global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pers_kernel(const __grid_constant__ DwtPassArgs a,
-                                                              const __grid_constant__ FilterPair f) {
-  extern __shared__ __align__(128) double smem[];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  constexpr int NS = QMF ? L : 1;
-  double sreg[NS];
-  if (QMF) {
-    const double* ct = const_taps(f);
-#pragma unroll
-    for (int m = 0; m < NS; m++) sreg[m] = ct[m];
-  } else {
-    sreg[0] = 0.0;
-  }
-  const int oW = 2 * a.cap_in;
-  const int oT = oW + a.cap_work;                    // tap copy, then two mbarriers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
-  if (L > kUniformTapsMaxDwt) {
-    for (int t = tid; t < JWC_MAX_TAPS; t += nt) {
-      smem[oT + t] = f.f0[t];
-      smem[oT + JWC_MAX_TAPS + t] = f.f1[t];
-    }
-  }
-  const int tlen = (int)((a.h < a.T) ? a.h : a.T);
-  const int H = (L - 2) * ((1 << a.k) - 1);
-  auto issue_load = [&](unsigned tile, int buf) {   // one thread
-    int64_t bid = tile;
-    const int ti = (int)(bid % a.tiles);
-    bid /= a.tiles;
-    const int p = (int)(bid % a.nodes);
-    const int64_t b = bid / a.nodes;
-    ptx::mbar_expect_tx(&bars[buf], (uint32_t)(tlen + H) * 8u);
-    bulk_load_circ(smem + buf * a.cap_in, a.in + b * a.in_sig + (int64_t)p * a.h, (int64_t)ti * tlen, tlen + H, a.h,
-                   &bars[buf]);
-  };
-  if (tid == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
-    ptx::fence_mbar_init();
-    if (blockIdx.x < a.nblocks) issue_load(blockIdx.x, 0);
-  }
-  __syncthreads();
-  int it = 0;
-  for (unsigned tile = blockIdx.x; tile < a.nblocks; tile += gridDim.x, ++it) {
-    const int cur = it & 1;
-    // the other input buffer and W are free once the previous tile's bulk stores have finished reading them
-    if (tid < 32) ptx::bulk_wait_read<0>();
-    __syncthreads();
-    if (tid == 0) {
-      if (tile + gridDim.x < a.nblocks) issue_load(tile + gridDim.x, cur ^ 1);
-      ptx::mbar_wait(&bars[cur], (uint32_t)((it >> 1) & 1));
-    }
-    __syncthreads();
-    ptx::mbar_wait(&bars[cur], (uint32_t)((it >> 1) & 1));
-    int64_t bid = tile;
-    const int ti = (int)(bid % a.tiles);
-    bid /= a.tiles;
-    const int p = (int)(bid % a.nodes);
-    const int64_t b = bid / a.nodes;
-    const int64_t a0 = (int64_t)ti * tlen;
-    const int oI = cur * a.cap_in;
-    for (int jj = 1; jj <= a.k; jj++) {
-      const int oin = ((jj - 1) & 1) ? oW : oI, oout = (jj & 1) ? oW : oI;
-      const int halo_in = (L - 2) * ((1 << (a.k - jj + 1)) - 1), halo_out = (L - 2) * ((1 << (a.k - jj)) - 1);
-      const int len_in = (tlen >> (jj - 1)) + halo_in, len_out = (tlen >> jj) + halo_out;
-      const int st_in = len_in + (len_in & 1) + 2 * kDwtR, st_out = len_out + (len_out & 1) + 2 * kDwtR;
-      const int own = tlen >> jj;
-      const int parents = TREE ? (1 << (jj - 1)) : 1;
-      if (4 * parents * ((len_out + RMAX - 1) / RMAX) >= nt || RMAX == 1)
-        ana_level<L, RMAX, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
-      else if (4 * parents * ((len_out + 2) / 3) >= nt)
-        ana_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
-      else
-        ana_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
-      const bool last = (jj == a.k);
-      const bool vec_ok = (own & 1) == 0;
-      if (vec_ok) ptx::fence_proxy_async();
-      if (tid < 32) ptx::bulk_wait_read<0>();   // stores issued one level ago have finished reading their buffer
-      __syncthreads();
-      if (!TREE) {
-        const double* src = smem + oout + st_out;
-        double* dst = a.out + b * a.out_sig + (a.N >> (a.l0 + jj)) + (a0 >> jj);
-        if (vec_ok) {
-          if (tid == 0) {
-            ptx::bulk_s2g(dst, src, (uint32_t)own * 8u);
-            if (last) ptx::bulk_s2g(a.aout + b * a.aout_sig + (a0 >> jj), smem + oout, (uint32_t)own * 8u);
-            ptx::bulk_commit();
-          }
-        } else {
-          for (int e = tid; e < own; e += nt) dst[e] = src[e];
-          if (last) {
-            double* ad = a.aout + b * a.aout_sig + (a0 >> jj);
-            for (int e = tid; e < own; e += nt) ad[e] = smem[oout + e];
-          }
-        }
-      } else if (last) {
-        const int leaves = 1 << a.k;
-        double* dst0 = a.out + b * a.out_sig + (int64_t)p * a.h + (a0 >> a.k);
-        const int64_t leaf_stride = a.h >> a.k;
-        if (vec_ok) {
-          if (tid < 32) {
-            for (int c = tid; c < leaves; c += 32)
-              ptx::bulk_s2g(dst0 + c * leaf_stride, smem + oout + c * st_out, (uint32_t)own * 8u);
-            ptx::bulk_commit();
-          }
-        } else {
-          for (int e = tid; e < leaves * own; e += nt) {
-            const int c = e / own, i = e - c * own;
-            dst0[c * leaf_stride + i] = smem[oout + c * st_out + i];
-          }
-        }
-      }
-    }
-  }
-  if (tid < 32) ptx::bulk_wait_read<0>();
-}
-
 // =========================================================================================================================
 // inverse (synthesis)
 // =========================================================================================================================
@@ -657,16 +534,6 @@ int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const F
     auto kern = dwt_inv_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
     JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
-  } else if (a.cap_in > 0) {
-    auto kern = dwt_fwd_pers_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
-    JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0, dev = 0, sms = 0;
-    JWC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    JWC_CUDA_CHECK(cudaGetDevice(&dev));
-    JWC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int64_t grid = (int64_t)std::max(per_sm, 1) * sms;
-    if (grid > nblocks) grid = nblocks;
-    kern<<<(unsigned)grid, threads, smem, st>>>(a, f);
   } else {
     auto kern = dwt_fwd_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
     JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -733,7 +600,6 @@ DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const voi
   // (measured, Haar 2^20: k <= 3 gives 3.10 ms, the model's k = 5 gives 3.38 ms)
   if (inverse && !tree && pin.group_override <= 0) pin.group_override = 3;
   pin.threads_override = ctx->tune.dwt_threads;
-  pin.persistent = ctx->tune.dwt_persistent > 0;   // measured slower than one CTA per tile + L2 prefetch (B200, round 1)
   return dwt_plan(pin, steps);
 }
 
@@ -785,7 +651,6 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
     a.nblocks = (unsigned)nblocks;
     a.pf_dist = (p.mode == DWT_BULK) ? dwt_prefetch_distance(ctx, dev, p.smem, p.threads) : 0;
-    if (p.persistent && p.mode == DWT_BULK) { a.cap_in = p.cap_in; a.cap_work = p.cap_work; }
     int rc = tree ? dispatch_dwt_pass<true, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks)
                   : dispatch_dwt_pass<false, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks);
     if (rc != JWC_OK) return rc;

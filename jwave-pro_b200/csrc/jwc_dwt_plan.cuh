@@ -19,8 +19,6 @@ enum { DWT_BULK = 0, DWT_SCALAR = 2 };
 
 struct DwtPass {
   int l0 = 0, k = 0, T = 0, cap = 0, threads = 256, mode = DWT_SCALAR;
-  int cap_in = 0, cap_work = 0;   // persistent forward kernel
-  bool persistent = false;
   size_t smem = 0;
 };
 
@@ -29,7 +27,6 @@ struct DwtPlanInput {
   int levels, L;
   bool tree, inverse, aligned16;
   int smem_budget, tile_override, group_override, threads_override;
-  bool persistent;   // forward: persistent CTAs with double-buffered TMA input
 };
 
 // ---- forward geometry -------------------------------------------------------------------------------------------------
@@ -43,18 +40,6 @@ inline int64_t dwt_fwd_cap(bool tree, int L, int k, int64_t tlen) {
     cap = std::max(cap, nodes * dwt_node_stride(dwt_fwd_len(L, k, jj, tlen)));
   }
   return cap + (cap & 1);
-}
-
-// persistent forward kernel: two input buffers (even-depth sets live in the current one) + one work buffer (odd depths)
-inline void dwt_fwd_caps(bool tree, int L, int k, int64_t tlen, int64_t* cap_in, int64_t* cap_work) {
-  int64_t ci = 0, cw = 0;
-  for (int jj = 0; jj <= k; jj++) {
-    const int64_t nodes = (jj == 0) ? 1 : (tree ? ((int64_t)1 << jj) : 2);
-    const int64_t sz = nodes * dwt_node_stride(dwt_fwd_len(L, k, jj, tlen));
-    if (jj & 1) cw = std::max(cw, sz); else ci = std::max(ci, sz);
-  }
-  *cap_in = ci + (ci & 1);
-  *cap_work = cw + (cw & 1);
 }
 
 // ---- inverse geometry: left halo of the depth-jj arrays (rounded up to even so bulk copies stay 16-byte aligned)
@@ -92,13 +77,7 @@ inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, d
   if (k < 1 || ((int64_t)1 << k) > h) return false;
   const int64_t budget = in.smem_budget / 8 - 16 - 2 * 64;   // mbarriers + shared-memory tap copy
   auto cap_of = [&](int64_t t) { return in.inverse ? dwt_inv_cap(in.tree, in.L, k, t) : dwt_fwd_cap(in.tree, in.L, k, t); };
-  const bool pers = !in.inverse && in.aligned16 && in.persistent;
-  auto smem_doubles = [&](int64_t t) {
-    if (!pers) return 2 * cap_of(t);
-    int64_t ci, cw;
-    dwt_fwd_caps(in.tree, in.L, k, t, &ci, &cw);
-    return 2 * ci + cw;
-  };
+  auto smem_doubles = [&](int64_t t) { return 2 * cap_of(t); };
   // T: a power of two, 2^k <= T <= h, as large as the budget allows
   int64_t T = h;
   if (in.tile_override > 0)
@@ -109,13 +88,6 @@ inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, d
   if (T < h && !in.inverse && 2 * H > T && in.tile_override <= 0) return false;   // halo would dominate the tile
   out->l0 = l0; out->k = k; out->T = (int)T; out->cap = (int)cap_of(T);
   out->smem = (size_t)smem_doubles(T) * 8 + 2 * 64 * 8 + 128;
-  out->persistent = pers && T >= 2;
-  if (out->persistent) {
-    int64_t ci, cw;
-    dwt_fwd_caps(in.tree, in.L, k, T, &ci, &cw);
-    out->cap_in = (int)ci;
-    out->cap_work = (int)cw;
-  }
   // bulk (TMA) copies need even piece lengths: forward T >= 2, inverse (T >> k) even
   const bool even_ok = in.inverse ? ((T >> k) % 2 == 0) : (T >= 2);
   out->mode = (in.aligned16 && even_ok) ? DWT_BULK : DWT_SCALAR;

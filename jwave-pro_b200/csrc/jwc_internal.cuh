@@ -48,7 +48,6 @@ struct Tuning {
   int dwt_group = 0;
   int dwt_smem = 0;
   int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
-  int dwt_persistent = 0;   // 1 = persistent CTAs with double-buffered TMA input (experimental, measured slower)
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
   int force_generic = 0;
   int l2_prefetch = 0;      // 0 = auto (one wave of CTAs ahead), -1 = off, > 0 = distance in CTAs

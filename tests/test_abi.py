@@ -65,4 +65,4 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
-                assert "oracle" not in txt.lower() or f == "__init__.py" and False, "%s mentions the oracle" % f
+                assert "oracle" not in txt.lower(), "%s mentions the oracle" % f
