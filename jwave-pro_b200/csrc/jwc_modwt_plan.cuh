@@ -158,7 +158,9 @@ inline ModwtPlan modwt_plan(const ModwtPlanInput& in) {
   std::vector<ModwtPass> pass_at(J + 1);
   best[J] = 0;
   for (int j0 = J - 1; j0 >= 0; j0--) {
-    const double gen = 2.0 * 24.0 / 5.5 * (J - j0);
+    // per-level generic kernels: 24 B/sample/level of traffic at about half the copy rate, and their uncoalesced,
+    // unfused inner loop reaches roughly a quarter of the fp64 peak for long filters
+    const double gen = (2.0 * 24.0 / 5.5 + 4.0 * in.L / 32.0 * 4.0) * (J - j0);
     best[j0] = gen;
     choice[j0] = -1;
     const int kmax = in.group_override > 0 ? std::min(in.group_override, J - j0) : J - j0;
