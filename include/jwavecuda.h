@@ -105,6 +105,16 @@ JWC_API int jwc_modwt_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const do
                                   int64_t batch, int64_t n, int levels, const double* g, const double* h, int L,
                                   unsigned flags);
 
+/* One long series split over the context's devices (a series too long, or too slow, for one GPU): device slot p holds
+ * the contiguous chunk [n*p/P, n*(p+1)/P) of x in d_x_chunks[p] and of every coefficient row in d_coeff_chunks[p]
+ * ([levels+1][chunk_len], row-major).  One halo exchange of (L-1)(2^levels - 1) samples per transform between ring
+ * neighbours (cudaMemcpyPeerAsync over NVLink), no collective.  Every chunk must be at least one halo long.  The chunk
+ * buffers must be ready (producers synchronised) on entry; the call returns after all devices have finished. */
+JWC_API int jwc_modwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_x_chunks, double* const* d_coeff_chunks,
+                                        int64_t n, int levels, const double* g, const double* h, int L, unsigned flags);
+JWC_API int jwc_modwt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_coeff_chunks, double* const* d_x_chunks,
+                                        int64_t n, int levels, const double* g, const double* h, int L, unsigned flags);
+
 /* ---- FWT --------------------------------------------------------------------------------------------
  * lo, hi: scalingDeCom / waveletDeCom for forward, scalingReCon / waveletReCon for inverse (Wavelet.java:178-219).
  * n must be 2^p, 0 <= levels <= p (FastWaveletTransform.java:74-83); levels = 0 copies.

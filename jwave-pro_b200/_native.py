@@ -26,7 +26,8 @@ _TRANSFORMS = ["modwt_forward", "modwt_inverse", "fwt_forward", "fwt_inverse", "
 SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal", "jwc_last_error", "jwc_version",
             "jwc_launch_count", "jwc_set_tuning", "jwc_get_tuning", "jwc_alloc_pinned", "jwc_free_pinned",
             "jwc_alloc_device", "jwc_free_device", "jwc_copy_to_device", "jwc_copy_to_host", "jwc_synchronize"]
-           + ["jwc_" + t for t in _TRANSFORMS] + ["jwc_" + t + "_dev" for t in _TRANSFORMS])
+           + ["jwc_" + t for t in _TRANSFORMS] + ["jwc_" + t + "_dev" for t in _TRANSFORMS]
+           + ["jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"])
 
 _lib = None
 _lock = threading.Lock()
@@ -84,6 +85,10 @@ def load():
             fn.restype = _int
             fn = getattr(lib, "jwc_" + t + "_dev")
             fn.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _dp, _dp, _int, _u32]
+            fn.restype = _int
+        for nm in ("jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"):
+            fn = getattr(lib, nm)
+            fn.argtypes = [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _int, _dp, _dp, _int, _u32]
             fn.restype = _int
         _lib = lib
         return _lib

@@ -234,6 +234,96 @@ int run_dev(jwc_ctx* ctx, int slot, void* stream, Op op, const double* d_in, dou
   return run_device(ctx, dev, st, op, d_in, d_out, batch, n, levels, fp, L, flags);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One long series split over the context's devices (second row).
+// Device slot p owns the contiguous chunk [n*p/P, n*(p+1)/P).  MODWT output t depends on inputs t-H .. t (forward,
+// H = (L-1)(2^J - 1)) resp. t .. t+H (inverse), so one halo exchange per transform is enough: every device extends
+// its chunk with the neighbour's H boundary samples (cudaMemcpyPeerAsync over NVLink, ring order, circular), runs the
+// ordinary kernels on the extended chunk (their circular wrap only contaminates the H positions that are thrown away)
+// and keeps the chunk part.  No collective.
+// ---------------------------------------------------------------------------------------------------------------------
+int modwt_split(jwc_ctx* ctx, bool inverse, const double* const* d_in, double* const* d_out, int64_t n, int levels,
+                const double* g, const double* h, int L, unsigned flags) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  JWC_REQUIRE(d_in != nullptr && d_out != nullptr && g != nullptr && h != nullptr, "NULL pointer");
+  JWC_REQUIRE(levels >= 1 && levels <= 30, "MODWT level %d out of range", levels);
+  JWC_REQUIRE(L >= 1 && L <= JWC_MAX_TAPS, "filter length %d outside 1..%d", L, JWC_MAX_TAPS);
+  const int P = (int)ctx->slots.size();
+  const int64_t H0 = (int64_t)(L - 1) * (((int64_t)1 << levels) - 1);
+  const int64_t H = H0 + (H0 & 1);   // even, so the extended chunk keeps the 16-byte alignment of the bulk copies
+  for (int p = 0; p < P; p++) {
+    const int64_t len = n * (p + 1) / P - n * p / P;
+    JWC_REQUIRE(d_in[p] != nullptr && d_out[p] != nullptr, "chunk pointer %d is NULL", p);
+    JWC_REQUIRE(len >= H && len >= 1, "series of %lld samples is too short to split over %d devices (halo %lld)",
+                (long long)n, P, (long long)H);
+  }
+  FilterPair fp;
+  load_filters(fp, g, h, L);
+  const int rows = levels + 1;
+  int rc = JWC_OK;
+  std::vector<double*> ext_in(P, nullptr), ext_out(P, nullptr);
+  // phase 1: build the extended inputs (own chunk + neighbour halo), all devices
+  for (int p = 0; p < P && rc == JWC_OK; p++) {
+    const DeviceSlot& dev = ctx->slots[p];
+    DeviceGuard guard(dev.ordinal);
+    const int64_t len = n * (p + 1) / P - n * p / P, next = len + H;
+    const int in_rows = inverse ? rows : 1, out_rows = inverse ? 1 : rows;
+    cudaError_t e;
+    if ((e = cudaMallocAsync((void**)&ext_in[p], (size_t)(in_rows * next) * sizeof(double), dev.stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void**)&ext_out[p], (size_t)(out_rows * next) * sizeof(double), dev.stream)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("split staging allocation failed on slot %d: %s", p, cudaGetErrorString(e));
+      rc = JWC_ERR_NOMEM;
+      break;
+    }
+    if (!inverse) {
+      // [halo from the left neighbour's tail | own chunk]
+      const int q = (p + P - 1) % P;
+      const int64_t qlen = n * (q + 1) / P - n * q / P;
+      e = cudaMemcpyPeerAsync(ext_in[p], dev.ordinal, d_in[q] + (qlen - H), ctx->slots[q].ordinal, (size_t)H * sizeof(double),
+                              dev.stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ext_in[p] + H, d_in[p], (size_t)len * sizeof(double), cudaMemcpyDeviceToDevice, dev.stream);
+    } else {
+      // every coefficient row: [own chunk | halo from the right neighbour's head]
+      const int q = (p + 1) % P;
+      const int64_t qlen = n * (q + 1) / P - n * q / P;
+      e = cudaMemcpy2DAsync(ext_in[p], (size_t)next * sizeof(double), d_in[p], (size_t)len * sizeof(double),
+                            (size_t)len * sizeof(double), (size_t)rows, cudaMemcpyDeviceToDevice, dev.stream);
+      for (int r = 0; r < rows && e == cudaSuccess; r++)
+        e = cudaMemcpyPeerAsync(ext_in[p] + (int64_t)r * next + len, dev.ordinal, d_in[q] + (int64_t)r * qlen,
+                                ctx->slots[q].ordinal, (size_t)H * sizeof(double), dev.stream);
+    }
+    if (e != cudaSuccess) { set_error("halo exchange failed on slot %d: %s", p, cudaGetErrorString(e)); rc = JWC_ERR_CUDA; }
+  }
+  // phase 2: the ordinary transform on the extended chunk, then keep the chunk part
+  for (int p = 0; p < P && rc == JWC_OK; p++) {
+    const DeviceSlot& dev = ctx->slots[p];
+    DeviceGuard guard(dev.ordinal);
+    const int64_t len = n * (p + 1) / P - n * p / P, next = len + H;
+    rc = run_device(ctx, dev, dev.stream, inverse ? Op::ModwtInv : Op::ModwtFwd, ext_in[p], ext_out[p], 1, next, levels, fp,
+                    L, flags);
+    if (rc != JWC_OK) break;
+    cudaError_t e;
+    if (!inverse)   // rows of the extended result, positions H .. H+len
+      e = cudaMemcpy2DAsync(d_out[p], (size_t)len * sizeof(double), ext_out[p] + H, (size_t)next * sizeof(double),
+                            (size_t)len * sizeof(double), (size_t)rows, cudaMemcpyDeviceToDevice, dev.stream);
+    else            // positions 0 .. len
+      e = cudaMemcpyAsync(d_out[p], ext_out[p], (size_t)len * sizeof(double), cudaMemcpyDeviceToDevice, dev.stream);
+    if (e != cudaSuccess) { set_error("split result copy failed on slot %d: %s", p, cudaGetErrorString(e)); rc = JWC_ERR_CUDA; }
+  }
+  for (int p = 0; p < P; p++) {
+    const DeviceSlot& dev = ctx->slots[p];
+    DeviceGuard guard(dev.ordinal);
+    if (ext_in[p]) cudaFreeAsync(ext_in[p], dev.stream);
+    if (ext_out[p]) cudaFreeAsync(ext_out[p], dev.stream);
+    cudaError_t e = cudaStreamSynchronize(dev.stream);
+    if (e != cudaSuccess && rc == JWC_OK) { set_error("split: stream sync failed on slot %d: %s", p, cudaGetErrorString(e)); rc = JWC_ERR_CUDA; }
+  }
+  return rc;
+}
+
 }  // namespace
 }  // namespace jwc
 
@@ -427,5 +517,14 @@ JWC_DEFINE(fwt_forward, Op::FwtFwd)
 JWC_DEFINE(fwt_inverse, Op::FwtInv)
 JWC_DEFINE(wpt_forward, Op::WptFwd)
 JWC_DEFINE(wpt_inverse, Op::WptInv)
+
+JWC_API int jwc_modwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_x_chunks, double* const* d_coeff_chunks,
+                                        int64_t n, int levels, const double* g, const double* h, int L, unsigned flags) {
+  return modwt_split(ctx, false, d_x_chunks, d_coeff_chunks, n, levels, g, h, L, flags);
+}
+JWC_API int jwc_modwt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_coeff_chunks, double* const* d_x_chunks,
+                                        int64_t n, int levels, const double* g, const double* h, int L, unsigned flags) {
+  return modwt_split(ctx, true, d_coeff_chunks, d_x_chunks, n, levels, g, h, L, flags);
+}
 
 }  // extern "C"

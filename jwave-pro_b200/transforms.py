@@ -368,6 +368,27 @@ class CudaMODWTTransform(WaveletTransform):
         self._call("jwc_modwt_inverse", C, out, B, N, J1 - 1, g, h, flags)
         return out
 
+    # ---- one long series split over the context's devices (halo exchange between ring neighbours) -----------------
+    def _split(self, fn_name, src_ptrs, dst_ptrs, n, maxLevel, flags):
+        lib = _native.load()
+        g, h = self._filters()
+        P = self._context().num_devices()
+        if len(src_ptrs) != P or len(dst_ptrs) != P:
+            raise ValueError("need one chunk pointer per device of the context (%d)" % P)
+        a = (ctypes.c_void_p * P)(*src_ptrs)
+        b = (ctypes.c_void_p * P)(*dst_ptrs)
+        rc = getattr(lib, fn_name)(self._context().handle, a, b, n, maxLevel, _ptr(g), _ptr(h), len(g), flags)
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (fn_name, rc, _native.last_error()))
+
+    def forwardMODWTSplitDevice(self, d_x_chunks, d_coeff_chunks, n, maxLevel, flags=0):
+        """d_x_chunks[p]: device address of x[n*p/P .. n*(p+1)/P) on device p; d_coeff_chunks[p]: [J+1][chunk_len]."""
+        self._check_levels(maxLevel, n)
+        self._split("jwc_modwt_forward_split_dev", d_x_chunks, d_coeff_chunks, n, maxLevel, flags)
+
+    def inverseMODWTSplitDevice(self, d_coeff_chunks, d_x_chunks, n, maxLevel, flags=0):
+        self._split("jwc_modwt_inverse_split_dev", d_coeff_chunks, d_x_chunks, n, maxLevel, flags)
+
     # ---- device-resident ----------------------------------------------------------------------------------------
     def forwardMODWTDevice(self, d_x, d_coeffs, batch, n, maxLevel, stream=0, flags=0, slot=0):
         self._check_levels(maxLevel, n)

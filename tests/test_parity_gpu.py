@@ -384,3 +384,37 @@ def test_every_wavelet_through_the_fused_kernels(jw, gpu_ctx, oracle, family):
             r = oracle.batch(kind + "_fwd", X, 6, s, wv, nthreads=8)
             assert _maxerr(tr.forwardBatch(X, 6), r, X) <= TOL, (cls, kind)
             assert _maxerr(tr.reverseBatch(r, 6), oracle.batch(kind + "_rev", r, 6, s, wv, nthreads=8), X) <= TOL, (cls, kind)
+
+
+@pytest.mark.parametrize("cls,n,J", [("Daubechies4", 1 << 18, 6), ("Daubechies20", 300000, 5), ("Haar1", 65536, 13)])
+def test_modwt_single_series_split_over_devices(jw, oracle, cls, n, J):
+    """one long series in contiguous chunks on the context's devices, one halo exchange
+    (cudaMemcpyPeerAsync, ring) per transform; equals the unsplit transform bit for bit and the oracle to 1e-12."""
+    import torch
+    P = min(torch.cuda.device_count(), 4)
+    ctx = jw.Context(list(range(P)))
+    w = jw.wavelets.create(cls)
+    t = jw.CudaMODWTTransform(w, context=ctx)
+    x = _inputs(n + J, 2, n)[1]          # a chirp
+    x = x + 0.25 * splitmix_uniform(17, (n,))
+    bounds = [n * p // P for p in range(P + 1)]
+    xs, cs, xr = [], [], []
+    for p in range(P):
+        ln = bounds[p + 1] - bounds[p]
+        xs.append(torch.from_numpy(x[bounds[p]:bounds[p + 1]].copy()).to("cuda:%d" % p))
+        cs.append(torch.empty((J + 1, ln), dtype=torch.float64, device="cuda:%d" % p))
+        xr.append(torch.empty(ln, dtype=torch.float64, device="cuda:%d" % p))
+    for p in range(P):
+        torch.cuda.synchronize(p)
+    t.forwardMODWTSplitDevice([a.data_ptr() for a in xs], [c.data_ptr() for c in cs], n, J)
+    got = np.concatenate([c.cpu().numpy() for c in cs], axis=1)
+    whole = jw.CudaMODWTTransform(w).forwardMODWT(x, J)
+    assert np.array_equal(got, whole)
+    g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+    ref = oracle.modwt_forward(x, J, g, h)
+    assert _maxerr(got, ref, x) <= TOL
+    t.inverseMODWTSplitDevice([c.data_ptr() for c in cs], [a.data_ptr() for a in xr], n, J)
+    back = np.concatenate([a.cpu().numpy() for a in xr])
+    assert np.array_equal(back, jw.CudaMODWTTransform(w).inverseMODWT(whole))
+    assert _maxerr(back, x, x) <= PR_TOL
+    ctx.close()
