@@ -146,7 +146,8 @@ def run_reference(args, kind, cls, levels, batch, n, rank, world):
     cores = os.cpu_count() or 1
     # bounded sample per step: a few signals per core, so K+W steps finish in minutes
     probe = cpu_reference_time(kind, cls, levels, n, cores, cores)
-    target = 6.0  # seconds per step
+    # seconds of host work per step, sized so that the whole --steps K --warmup W run ends within ~2.5 minutes
+    target = min(6.0, max(0.5, 150.0 / max(1, args.steps + args.warmup)))
     nsig = int(max(cores, min(batch, cores * max(1, round(target / max(probe, 1e-3))))))
     times = []
     for i in range(args.warmup + args.steps):
