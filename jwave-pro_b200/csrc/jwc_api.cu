@@ -103,12 +103,47 @@ void io_sizes(Op op, int64_t n, int levels, int64_t* in_per, int64_t* out_per) {
 
 // Host-buffer pipeline on ONE slot: chunks of signals, double-buffered device staging, H2D / kernels / D2H on three
 // streams chained by events.  Called on its own host thread per slot when the context spans several devices.
+// Borrow a stream triple of `slot` for one host-buffer call (device must be current); give it back when the call is
+// drained.  Returns false when stream creation fails.
+void lane_destroy(Lane& l) {
+  for (cudaStream_t* st : {&l.compute, &l.copy_in, &l.copy_out})
+    if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
+}
+
+bool lane_acquire(jwc_ctx* ctx, int slot, Lane* lane) {
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto& idle = ctx->slots[slot].idle_lanes;
+    if (!idle.empty()) {
+      *lane = idle.back();
+      idle.pop_back();
+      return true;
+    }
+  }
+  Lane l;
+  if (cudaStreamCreateWithFlags(&l.compute, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&l.copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&l.copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+    (void)cudaGetLastError();
+    lane_destroy(l);
+    return false;
+  }
+  *lane = l;
+  return true;
+}
+void lane_release(jwc_ctx* ctx, int slot, const Lane& lane) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->slots[slot].idle_lanes.push_back(lane);
+}
+
 int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, int64_t batch, int64_t n, int levels,
                   const FilterPair& fp, int L, unsigned flags) {
   if (batch == 0) return JWC_OK;
   const DeviceSlot& dev = ctx->slots[slot];
   DeviceGuard guard(dev.ordinal);
   if (!guard.ok) { set_error("cudaSetDevice(%d) failed", dev.ordinal); return JWC_ERR_CUDA; }
+  Lane lane;
+  if (!lane_acquire(ctx, slot, &lane)) { set_error("cannot create streams on device %d", dev.ordinal); return JWC_ERR_CUDA; }
   int64_t in_per, out_per;
   io_sizes(op, n, levels, &in_per, &out_per);
   const int64_t per_sig_bytes = (in_per + out_per) * (int64_t)sizeof(double);
@@ -116,12 +151,27 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
   int64_t chunk = (chunk_mb << 20) / per_sig_bytes;
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
-  const int nbuf = (chunk < batch) ? 2 : 1;
+  constexpr int kMaxBuf = 4;
+  const int64_t nchunks = (batch + chunk - 1) / chunk;
+  int nbuf = ctx->tune.h2d_buffers > 0 ? ctx->tune.h2d_buffers : 3;   // staging depth of the copy/compute pipeline
+  if (nbuf > kMaxBuf) nbuf = kMaxBuf;
+  if (nbuf > nchunks) nbuf = (int)nchunks;
 
-  cudaStream_t sc = dev.stream, si = dev.copy_in, so = dev.copy_out;
-  double* d_in[2] = {nullptr, nullptr};
-  double* d_out[2] = {nullptr, nullptr};
-  cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {}, ev_alloc = nullptr;
+  cudaStream_t sc = lane.compute, si = lane.copy_in, so = lane.copy_out;
+  // Copy pacing.  A copy engine drains one stream's queued copies before it looks at another stream (measured: with a
+  // forward and an inverse call in flight, the forward's 33 MB H2D sat behind ALL of the inverse's 235 MB H2D chunks,
+  // serialising the two calls; piece-wise copies and stream priorities did not change that).  So while other host
+  // calls are in flight, a call keeps at most ONE copy queued in the direction it is heavy in: the next one is issued
+  // only when the previous one has finished, which lets the other call's small copy slip in between.
+  const bool pace_in = in_per >= out_per, pace_out = out_per > in_per;
+  struct InFlight {
+    std::atomic<int>& n;
+    explicit InFlight(std::atomic<int>& a) : n(a) { n.fetch_add(1); }
+    ~InFlight() { n.fetch_sub(1); }
+  } in_flight(ctx->host_calls);
+  double* d_in[kMaxBuf] = {};
+  double* d_out[kMaxBuf] = {};
+  cudaEvent_t ev_in[kMaxBuf] = {}, ev_k[kMaxBuf] = {}, ev_out[kMaxBuf] = {}, ev_alloc = nullptr;
   int rc = JWC_OK;
   auto fail = [&](cudaError_t e, const char* what) {
     set_error("%s failed: %s", what, cudaGetErrorString(e));
@@ -158,6 +208,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
       if ((e = cudaStreamWaitEvent(si, ev_k[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
       if ((e = cudaStreamWaitEvent(sc, ev_out[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
     }
+    if (c > 0 && pace_in && ctx->host_calls.load() > 1) cudaEventSynchronize(ev_in[(c - 1) % nbuf]);
     if ((e = cudaMemcpyAsync(d_in[k], in + b0 * in_per, (size_t)(nb * in_per) * sizeof(double), cudaMemcpyHostToDevice,
                              si)) != cudaSuccess) { fail(e, "cudaMemcpyAsync(H2D)"); break; }
     if ((e = cudaEventRecord(ev_in[k], si)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
@@ -166,6 +217,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
     if (rc != JWC_OK) break;
     if ((e = cudaEventRecord(ev_k[k], sc)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
     if ((e = cudaStreamWaitEvent(so, ev_k[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
+    if (c > 0 && pace_out && ctx->host_calls.load() > 1) cudaEventSynchronize(ev_out[(c - 1) % nbuf]);
     if ((e = cudaMemcpyAsync(out + b0 * out_per, d_out[k], (size_t)(nb * out_per) * sizeof(double),
                              cudaMemcpyDeviceToHost, so)) != cudaSuccess) { fail(e, "cudaMemcpyAsync(D2H)"); break; }
     if ((e = cudaEventRecord(ev_out[k], so)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
@@ -177,7 +229,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
     else if (e2 != cudaSuccess) fail(e2, "cudaStreamSynchronize(compute)");
     else if (e3 != cudaSuccess) fail(e3, "cudaStreamSynchronize(copy_out)");
   }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < kMaxBuf; i++) {
     if (d_in[i]) cudaFreeAsync(d_in[i], sc);
     if (d_out[i]) cudaFreeAsync(d_out[i], sc);
     if (ev_in[i]) cudaEventDestroy(ev_in[i]);
@@ -185,6 +237,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
     if (ev_out[i]) cudaEventDestroy(ev_out[i]);
   }
   if (ev_alloc) cudaEventDestroy(ev_alloc);
+  lane_release(ctx, slot, lane);
   return rc;
 }
 
@@ -376,9 +429,7 @@ JWC_API jwc_ctx* jwc_create(const int* devices, int ndev) {
     }
     s.sm_count = prop.multiProcessorCount;
     s.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) {
       set_error("cannot create streams on device %d: %s", o, cudaGetErrorString(cudaGetLastError()));
       cudaSetDevice(prev);
       jwc_destroy(ctx);
@@ -403,8 +454,7 @@ JWC_API void jwc_destroy(jwc_ctx* ctx) {
   for (auto& s : ctx->slots) {
     cudaSetDevice(s.ordinal);
     if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
-    if (s.copy_in) { cudaStreamSynchronize(s.copy_in); cudaStreamDestroy(s.copy_in); }
-    if (s.copy_out) { cudaStreamSynchronize(s.copy_out); cudaStreamDestroy(s.copy_out); }
+    for (auto& l : s.idle_lanes) jwc::lane_destroy(l);
   }
   cudaSetDevice(prev);
   delete ctx;
@@ -430,6 +480,7 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "dwt_smem")) return &t.dwt_smem;
   if (!strcmp(key, "dwt_qmf")) return &t.dwt_qmf;
   if (!strcmp(key, "h2d_chunk_mb")) return &t.h2d_chunk_mb;
+  if (!strcmp(key, "h2d_buffers")) return &t.h2d_buffers;
   if (!strcmp(key, "force_generic")) return &t.force_generic;
   if (!strcmp(key, "l2_prefetch")) return &t.l2_prefetch;
   return nullptr;
@@ -493,9 +544,7 @@ JWC_API int jwc_synchronize(jwc_ctx* ctx) {
   if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
   for (auto& s : ctx->slots) {
     DeviceGuard guard(s.ordinal);
-    JWC_CUDA_CHECK(cudaStreamSynchronize(s.copy_in));
-    JWC_CUDA_CHECK(cudaStreamSynchronize(s.stream));
-    JWC_CUDA_CHECK(cudaStreamSynchronize(s.copy_out));
+    JWC_CUDA_CHECK(cudaStreamSynchronize(s.stream));   // host-buffer calls drain their own lanes before returning
   }
   return JWC_OK;
 }

@@ -49,17 +49,24 @@ struct Tuning {
   int dwt_smem = 0;
   int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
+  int h2d_buffers = 0;      // host pipeline staging depth (1..4), 0 = auto
   int force_generic = 0;
   int l2_prefetch = 0;      // 0 = auto (one wave of CTAs ahead), -1 = off, > 0 = distance in CTAs
 };
 
+// One host-buffer call in flight owns one lane (three streams: kernels, H2D, D2H), so concurrent calls on a context --
+// e.g. a forward and an inverse from two host threads, which together keep both PCIe directions busy -- never queue
+// behind each other's copies.  Lanes are created on demand and recycled.
+struct Lane {
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+};
+
 struct DeviceSlot {
   int ordinal = 0;
-  cudaStream_t stream = nullptr;      // compute stream of the slot (used when the caller passes NULL)
-  cudaStream_t copy_in = nullptr;     // host-pipeline H2D stream
-  cudaStream_t copy_out = nullptr;    // host-pipeline D2H stream
+  cudaStream_t stream = nullptr;      // compute stream of the slot (device-pointer calls that pass NULL)
   int sm_count = 0;
   int max_smem_optin = 0;
+  std::vector<Lane> idle_lanes;       // guarded by jwc_ctx::mu
 };
 
 }  // namespace jwc
@@ -67,6 +74,7 @@ struct DeviceSlot {
 struct jwc_ctx {
   std::vector<jwc::DeviceSlot> slots;
   std::atomic<uint64_t> launches{0};
+  std::atomic<int> host_calls{0};   // host-buffer calls in flight (copy pacing, see run_host_slot)
   jwc::Tuning tune;
   std::mutex mu;
 };

@@ -236,6 +236,34 @@ def test_empty_batch_and_bad_arguments(jw, gpu_ctx):
     assert rc == -1 and b"filter length" in lib.jwc_last_error()
 
 
+def test_concurrent_host_calls_use_separate_lanes(jw, oracle):
+    """A forward and an inverse host-buffer call in flight at once on ONE context (the streaming pattern bench.py's
+    e2e leg uses): each gets its own stream lane, results stay exact, many pipeline chunks each."""
+    ctx = jw.Context([0])
+    ctx.set_tuning("h2d_chunk_mb", 1)
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaMODWTTransform(w, context=ctx)
+    X = splitmix_uniform(77, (96, 8192))
+    ref, (g, h) = _modwt_oracle(oracle, w, X, 5)
+    res = {}
+
+    def fwd(i):
+        res["f%d" % i] = t.forwardMODWTBatch(X, 5)
+
+    def inv(i):
+        res["i%d" % i] = t.inverseMODWTBatch(ref)
+
+    th = [threading.Thread(target=f, args=(i,)) for i in range(3) for f in (fwd, inv)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    back = oracle.batch("modwt_inv", ref, 5, g, h, nthreads=8)
+    for i in range(3):
+        assert _maxerr(res["f%d" % i], ref, X) <= TOL
+        assert _maxerr(res["i%d" % i], back, X) <= TOL
+        assert np.array_equal(res["f%d" % i], res["f0"]) and np.array_equal(res["i%d" % i], res["i0"])
+    ctx.close()
+
+
 def test_thread_safety_shared_instance(jw, gpu_ctx, oracle):
     """MODWTThreadSafetyTest.java:24-104: 10 threads x iterations on ONE instance, clearFilterCache every 10th."""
     w = jw.wavelets.Daubechies4()
