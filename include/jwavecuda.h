@@ -146,6 +146,35 @@ JWC_API int jwc_wpt_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const doub
                                 int64_t batch, int64_t n, int levels, const double* lo, const double* hi, int L,
                                 unsigned flags);
 
+/* ---- 2-D FWT / WPT ----------------------------------------------------------------------------------
+ * The reference's matrix overloads: transforms/BasicTransform.java:361-399 forward(double[][], lvlM, lvlN) sends every
+ * row through forward(row, lvlN) and then every column of the result through forward(col, lvlM); :436-474
+ * reverse(double[][], lvlM, lvlN) undoes the columns (lvlM) first, then the rows (lvlN).
+ * transforms/ParallelTransform.java:70-91,222-271 is the same arithmetic with rows spread over host threads.
+ * in, out: [batch][rows][cols] row-major, rows and cols both 2^p, 0 <= lvl_m <= log2(rows), 0 <= lvl_n <= log2(cols);
+ * lo/hi as for the 1-D calls (DeCom for forward, ReCon for inverse).  The column pass runs in place on the row-major
+ * matrix (no transposes); the host variants shard the batch of matrices over the context's devices. */
+JWC_API int jwc_fwt2d_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t rows, int64_t cols,
+                              int lvl_m, int lvl_n, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt2d_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t rows, int64_t cols,
+                              int lvl_m, int lvl_n, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt2d_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t rows, int64_t cols,
+                              int lvl_m, int lvl_n, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt2d_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t rows, int64_t cols,
+                              int lvl_m, int lvl_n, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt2d_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                  int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt2d_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                  int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt2d_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                  int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt2d_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                  int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,13 @@ struct DeviceGuard {
 
 enum class Op { ModwtFwd, ModwtInv, FwtFwd, FwtInv, WptFwd, WptInv };
 
+// 2-D calls reuse the 1-D plumbing: `n` is the row length (cols), `levels` the level along a row (lvlN); rows > 0
+// switches the unit of work from one signal to one rows x n matrix with lvl_m levels down the columns.
+struct Dim2 {
+  int64_t rows = 0;
+  int lvl_m = 0;
+};
+
 bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 int ilog2(int64_t n) {
   int p = 0;
@@ -42,7 +49,15 @@ int ilog2(int64_t n) {
 }
 
 int validate(Op op, const void* in, const void* out, int64_t batch, int64_t n, int levels, const double* f0,
-             const double* f1, int L) {
+             const double* f1, int L, const Dim2& d2 = Dim2()) {
+  if (d2.rows != 0) {
+    JWC_REQUIRE(op != Op::ModwtFwd && op != Op::ModwtInv, "no 2-D MODWT");
+    JWC_REQUIRE(is_pow2(d2.rows), "given matrix height is not 2^p (got %lld)", (long long)d2.rows);
+    JWC_REQUIRE(d2.lvl_m >= 0 && d2.lvl_m <= ilog2(d2.rows),
+                "given level %d is out of range for given array of length %lld", d2.lvl_m, (long long)d2.rows);
+    JWC_REQUIRE(d2.rows < ((int64_t)1 << 40) / (n > 0 ? n : 1), "matrix %lld x %lld too large", (long long)d2.rows,
+                (long long)n);
+  }
   JWC_REQUIRE(in != nullptr && out != nullptr, "input/output pointer is NULL");
   JWC_REQUIRE(f0 != nullptr && f1 != nullptr, "filter pointer is NULL");
   JWC_REQUIRE(batch >= 0, "batch must be >= 0 (got %lld)", (long long)batch);
@@ -67,9 +82,33 @@ void load_filters(FilterPair& fp, const double* f0, const double* f1, int L) {
 
 // One transform on device-resident buffers of slot `dev`, enqueued on `st`.
 int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, const double* d_in, double* d_out,
-               int64_t batch, int64_t n, int levels, const FilterPair& fp, int L, unsigned flags) {
+               int64_t batch, int64_t n, int levels, const FilterPair& fp, int L, unsigned flags,
+               const Dim2& d2 = Dim2()) {
   if (batch == 0) return JWC_OK;
   const bool exact = (flags & JWC_FLAG_EXACT) != 0;
+  if (d2.rows != 0) {
+    // BasicTransform.java:361-399 forward: rows (lvlN) then columns (lvlM); :436-474 reverse: columns, then rows.
+    const bool tree = (op == Op::WptFwd || op == Op::WptInv);
+    const bool fwd = (op == Op::FwtFwd || op == Op::WptFwd);
+    const int64_t rows = d2.rows, cols = n;
+    const int col_steps = dwt2d_column_steps(rows, d2.lvl_m);
+    const int row_steps = dwt2d_column_steps(cols, levels);
+    if (col_steps == 0) return run_device(ctx, dev, st, op, d_in, d_out, batch * rows, cols, levels, fp, L, flags);
+    if (row_steps == 0)
+      return fwd ? dwt2d_columns_forward(ctx, dev, st, d_in, d_out, batch, rows, cols, d2.lvl_m, fp, L, tree, exact)
+                 : dwt2d_columns_inverse(ctx, dev, st, d_in, d_out, batch, rows, cols, d2.lvl_m, fp, L, tree, exact);
+    Scratch ws(st);
+    double* mid = ws.get((size_t)(batch * rows * cols));
+    if (!mid) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+    if (fwd) {
+      const int rc = run_device(ctx, dev, st, op, d_in, mid, batch * rows, cols, levels, fp, L, flags);
+      if (rc != JWC_OK) return rc;
+      return dwt2d_columns_forward(ctx, dev, st, mid, d_out, batch, rows, cols, d2.lvl_m, fp, L, tree, exact);
+    }
+    const int rc = dwt2d_columns_inverse(ctx, dev, st, d_in, mid, batch, rows, cols, d2.lvl_m, fp, L, tree, exact);
+    if (rc != JWC_OK) return rc;
+    return run_device(ctx, dev, st, op, mid, d_out, batch * rows, cols, levels, fp, L, flags);
+  }
   const bool generic = exact || (flags & JWC_FLAG_FORCE_GENERIC) != 0 || ctx->tune.force_generic != 0;
   int rc = JWC_ERR_UNSUPPORTED;
   if (!generic) {
@@ -94,9 +133,10 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
   return JWC_ERR_INVALID;
 }
 
-void io_sizes(Op op, int64_t n, int levels, int64_t* in_per, int64_t* out_per) {
+void io_sizes(Op op, int64_t n, int levels, int64_t* in_per, int64_t* out_per, const Dim2& d2 = Dim2()) {
   *in_per = n;
   *out_per = n;
+  if (d2.rows != 0) *in_per = *out_per = n * d2.rows;
   if (op == Op::ModwtFwd) *out_per = (int64_t)(levels + 1) * n;
   if (op == Op::ModwtInv) *in_per = (int64_t)(levels + 1) * n;
 }
@@ -137,7 +177,7 @@ void lane_release(jwc_ctx* ctx, int slot, const Lane& lane) {
 }
 
 int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, int64_t batch, int64_t n, int levels,
-                  const FilterPair& fp, int L, unsigned flags) {
+                  const FilterPair& fp, int L, unsigned flags, const Dim2& d2 = Dim2()) {
   if (batch == 0) return JWC_OK;
   const DeviceSlot& dev = ctx->slots[slot];
   DeviceGuard guard(dev.ordinal);
@@ -145,7 +185,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
   Lane lane;
   if (!lane_acquire(ctx, slot, &lane)) { set_error("cannot create streams on device %d", dev.ordinal); return JWC_ERR_CUDA; }
   int64_t in_per, out_per;
-  io_sizes(op, n, levels, &in_per, &out_per);
+  io_sizes(op, n, levels, &in_per, &out_per, d2);
   const int64_t per_sig_bytes = (in_per + out_per) * (int64_t)sizeof(double);
   int64_t chunk_mb = ctx->tune.h2d_chunk_mb > 0 ? ctx->tune.h2d_chunk_mb : 128;   // in + out bytes per chunk
   int64_t chunk = (chunk_mb << 20) / per_sig_bytes;
@@ -213,7 +253,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
                              si)) != cudaSuccess) { fail(e, "cudaMemcpyAsync(H2D)"); break; }
     if ((e = cudaEventRecord(ev_in[k], si)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
     if ((e = cudaStreamWaitEvent(sc, ev_in[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
-    rc = run_device(ctx, dev, sc, op, d_in[k], d_out[k], nb, n, levels, fp, L, flags);
+    rc = run_device(ctx, dev, sc, op, d_in[k], d_out[k], nb, n, levels, fp, L, flags, d2);
     if (rc != JWC_OK) break;
     if ((e = cudaEventRecord(ev_k[k], sc)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
     if ((e = cudaStreamWaitEvent(so, ev_k[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
@@ -242,16 +282,16 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
 }
 
 int run_host(jwc_ctx* ctx, Op op, const double* in, double* out, int64_t batch, int64_t n, int levels,
-             const double* f0, const double* f1, int L, unsigned flags) {
+             const double* f0, const double* f1, int L, unsigned flags, const Dim2& d2 = Dim2()) {
   if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
-  int rc = validate(op, in, out, batch, n, levels, f0, f1, L);
+  int rc = validate(op, in, out, batch, n, levels, f0, f1, L, d2);
   if (rc != JWC_OK) return rc;
   FilterPair fp;
   load_filters(fp, f0, f1, L);
   int64_t in_per, out_per;
-  io_sizes(op, n, levels, &in_per, &out_per);
+  io_sizes(op, n, levels, &in_per, &out_per, d2);
   const int nd = (int)ctx->slots.size();
-  if (nd == 1 || batch < 2) return run_host_slot(ctx, 0, op, in, out, batch, n, levels, fp, L, flags);
+  if (nd == 1 || batch < 2) return run_host_slot(ctx, 0, op, in, out, batch, n, levels, fp, L, flags, d2);
   // shard by signal: contiguous blocks, no data-path collective
   std::vector<std::thread> th;
   std::vector<int> rcs(nd, JWC_OK);
@@ -259,7 +299,7 @@ int run_host(jwc_ctx* ctx, Op op, const double* in, double* out, int64_t batch, 
   for (int s = 0; s < nd; s++) {
     const int64_t b0 = batch * s / nd, b1 = batch * (s + 1) / nd;
     th.emplace_back([=, &rcs, &errs, &fp]() {
-      rcs[s] = run_host_slot(ctx, s, op, in + b0 * in_per, out + b0 * out_per, b1 - b0, n, levels, fp, L, flags);
+      rcs[s] = run_host_slot(ctx, s, op, in + b0 * in_per, out + b0 * out_per, b1 - b0, n, levels, fp, L, flags, d2);
       if (rcs[s] != JWC_OK) errs[s] = g_err;
     });
   }
@@ -273,10 +313,10 @@ int run_host(jwc_ctx* ctx, Op op, const double* in, double* out, int64_t batch, 
 }
 
 int run_dev(jwc_ctx* ctx, int slot, void* stream, Op op, const double* d_in, double* d_out, int64_t batch, int64_t n,
-            int levels, const double* f0, const double* f1, int L, unsigned flags) {
+            int levels, const double* f0, const double* f1, int L, unsigned flags, const Dim2& d2 = Dim2()) {
   if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
   JWC_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), "device slot %d out of range", slot);
-  int rc = validate(op, d_in, d_out, batch, n, levels, f0, f1, L);
+  int rc = validate(op, d_in, d_out, batch, n, levels, f0, f1, L, d2);
   if (rc != JWC_OK) return rc;
   FilterPair fp;
   load_filters(fp, f0, f1, L);
@@ -284,7 +324,7 @@ int run_dev(jwc_ctx* ctx, int slot, void* stream, Op op, const double* d_in, dou
   DeviceGuard guard(dev.ordinal);
   if (!guard.ok) { set_error("cudaSetDevice(%d) failed", dev.ordinal); return JWC_ERR_CUDA; }
   cudaStream_t st = stream ? (cudaStream_t)stream : dev.stream;
-  return run_device(ctx, dev, st, op, d_in, d_out, batch, n, levels, fp, L, flags);
+  return run_device(ctx, dev, st, op, d_in, d_out, batch, n, levels, fp, L, flags, d2);
 }
 
 
@@ -566,6 +606,30 @@ JWC_DEFINE(fwt_forward, Op::FwtFwd)
 JWC_DEFINE(fwt_inverse, Op::FwtInv)
 JWC_DEFINE(wpt_forward, Op::WptFwd)
 JWC_DEFINE(wpt_inverse, Op::WptInv)
+
+#define JWC_DEFINE_2D(name, OP)                                                                                     \
+  JWC_API int jwc_##name(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t rows, int64_t cols,    \
+                         int lvl_m, int lvl_n, const double* f0, const double* f1, int L, unsigned flags) {         \
+    if (rows < 1) { set_error("matrix height must be >= 1 (got %lld)", (long long)rows); return JWC_ERR_INVALID; }  \
+    Dim2 d2;                                                                                                        \
+    d2.rows = rows;                                                                                                 \
+    d2.lvl_m = lvl_m;                                                                                               \
+    return run_host(ctx, OP, in, out, batch, cols, lvl_n, f0, f1, L, flags, d2);                                    \
+  }                                                                                                                 \
+  JWC_API int jwc_##name##_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,             \
+                               int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* f0,   \
+                               const double* f1, int L, unsigned flags) {                                           \
+    if (rows < 1) { set_error("matrix height must be >= 1 (got %lld)", (long long)rows); return JWC_ERR_INVALID; }  \
+    Dim2 d2;                                                                                                        \
+    d2.rows = rows;                                                                                                 \
+    d2.lvl_m = lvl_m;                                                                                               \
+    return run_dev(ctx, slot, stream, OP, d_in, d_out, batch, cols, lvl_n, f0, f1, L, flags, d2);                   \
+  }
+
+JWC_DEFINE_2D(fwt2d_forward, Op::FwtFwd)
+JWC_DEFINE_2D(fwt2d_inverse, Op::FwtInv)
+JWC_DEFINE_2D(wpt2d_forward, Op::WptFwd)
+JWC_DEFINE_2D(wpt2d_inverse, Op::WptInv)
 
 JWC_API int jwc_modwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_x_chunks, double* const* d_coeff_chunks,
                                         int64_t n, int levels, const double* g, const double* h, int L, unsigned flags) {

@@ -123,6 +123,15 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
 int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+// column passes of the 2-D FWT / WPT (jwc_dwt2d.cu); d_src / d_in must not overlap the destination
+int dwt2d_column_steps(int64_t rows, int levels);
+int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_src, double* d_out,
+                          int64_t batch, int64_t rows, int64_t cols, int levels, const FilterPair& f, int L, bool tree,
+                          bool exact);
+int dwt2d_columns_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_dst,
+                          int64_t batch, int64_t rows, int64_t cols, int levels, const FilterPair& f, int L, bool tree,
+                          bool exact);
+
 int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
                      int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree);
 int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,

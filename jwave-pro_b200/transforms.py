@@ -8,6 +8,7 @@ has a CPU path.
 
 Reference (relative to /root/reference/src/main/java/jwave/transforms/):
   BasicTransform.java:99-157,671-697        abstract 1-D API, isBinary, calcExponent
+  BasicTransform.java:330-474               2-D forward / reverse (rows then columns; columns then rows)
   WaveletTransform.java:77-182              full-depth defaults, decompose / recompose
   FastWaveletTransform.java:71-153          CudaFastWaveletTransform
   WaveletPacketTransform.java:73-191        CudaWaveletPacketTransform
@@ -90,7 +91,11 @@ class WaveletTransform(BasicTransform):
             raise RuntimeError("%s_dev failed (%d): %s" % (fn_name, rc, _native.last_error()))
 
     # ---- full-depth defaults (WaveletTransform.java:77-112) --------------------------------------------------
-    def forward(self, arrTime, level=None):
+    def forward(self, arrTime, level=None, lvlN=None):
+        """1-D: forward(arrTime[, level]).  A 2-D array selects the reference's matrix overloads
+        forward(double[][]) / forward(double[][], lvlM, lvlN) (BasicTransform.java:330-399)."""
+        if np.ndim(arrTime) == 2:
+            return self.forward2D(arrTime, level, lvlN)
         if level is None:
             if not self.isBinary(len(arrTime)):
                 raise JWaveFailure("WaveletTransform#forward - given array length is not 2^p | p E N ... = "
@@ -99,7 +104,9 @@ class WaveletTransform(BasicTransform):
             level = self.calcExponent(len(arrTime))
         return self._forward_level(arrTime, level)
 
-    def reverse(self, arrHilb, level=None):
+    def reverse(self, arrHilb, level=None, lvlN=None):
+        if np.ndim(arrHilb) == 2:
+            return self.reverse2D(arrHilb, level, lvlN)
         if level is None:
             if not self.isBinary(len(arrHilb)):
                 raise JWaveFailure("WaveletTransform#reverse - given array length is not 2^p | p E N ... = "
@@ -173,6 +180,72 @@ class _CudaPyramidBase(WaveletTransform):
         self._call(self._fn + "_inverse", C, out, B, N, level, self._wavelet.getScalingReConstruction(),
                    self._wavelet.getWaveletReConstruction(), flags)
         return out
+
+    # ---- 2-D (BasicTransform.java:330-474; ParallelTransform.java:70-91,222-271 is the same arithmetic) ------
+    def _levels2d(self, rows, cols, lvlM, lvlN, direction):
+        if lvlM is None:
+            lvlM = self.calcExponent(rows)    # BasicTransform.java:336-338 / :412-414
+        if lvlN is None:
+            lvlN = self.calcExponent(cols)
+        self._check(cols, lvlN, direction)    # the reference fails in the first row transform ...
+        self._check(rows, lvlM, direction)    # ... or in the first column transform
+        return lvlM, lvlN
+
+    def _call2d(self, fn_name, src, dst, batch, rows, cols, lvlM, lvlN, f0, f1, flags):
+        lib = _native.load()
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        rc = getattr(lib, fn_name)(self._context().handle, src.ctypes.data, dst.ctypes.data, batch, rows, cols, lvlM,
+                                   lvlN, _ptr(f0), _ptr(f1), len(f0), flags)
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (fn_name, rc, _native.last_error()))
+
+    def forward2DBatch(self, cubeTime, lvlM=None, lvlN=None, flags=0, out=None):
+        """[batch][rows][cols] -> same shape; every matrix as forward(double[][], lvlM, lvlN)."""
+        X = _as_f64(cubeTime)
+        B, rows, cols = X.shape
+        lvlM, lvlN = self._levels2d(rows, cols, lvlM, lvlN, "forward")
+        out = np.empty_like(X) if out is None else out
+        self._call2d(self._fn + "2d_forward", X, out, B, rows, cols, lvlM, lvlN,
+                     self._wavelet.getScalingDeComposition(), self._wavelet.getWaveletDeComposition(), flags)
+        return out
+
+    def reverse2DBatch(self, cubeHilb, lvlM=None, lvlN=None, flags=0, out=None):
+        C = _as_f64(cubeHilb)
+        B, rows, cols = C.shape
+        lvlM, lvlN = self._levels2d(rows, cols, lvlM, lvlN, "reverse")
+        out = np.empty_like(C) if out is None else out
+        self._call2d(self._fn + "2d_inverse", C, out, B, rows, cols, lvlM, lvlN,
+                     self._wavelet.getScalingReConstruction(), self._wavelet.getWaveletReConstruction(), flags)
+        return out
+
+    def forward2D(self, matTime, lvlM=None, lvlN=None, flags=0):
+        X = _as_f64(matTime)
+        return self.forward2DBatch(X[None, :, :], lvlM, lvlN, flags)[0]
+
+    def reverse2D(self, matHilb, lvlM=None, lvlN=None, flags=0):
+        C = _as_f64(matHilb)
+        return self.reverse2DBatch(C[None, :, :], lvlM, lvlN, flags)[0]
+
+    def _call2d_dev(self, fn_name, d_src, d_dst, batch, rows, cols, lvlM, lvlN, f0, f1, flags, stream, slot):
+        lib = _native.load()
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        rc = getattr(lib, fn_name + "_dev")(self._context().handle, slot, ctypes.c_void_p(stream if stream else 1),
+                                            ctypes.c_void_p(d_src), ctypes.c_void_p(d_dst), batch, rows, cols, lvlM,
+                                            lvlN, _ptr(f0), _ptr(f1), len(f0), flags)
+        if rc != 0:
+            raise RuntimeError("%s_dev failed (%d): %s" % (fn_name, rc, _native.last_error()))
+
+    def forward2DDevice(self, d_in, d_out, batch, rows, cols, lvlM, lvlN, stream=0, flags=0, slot=0):
+        lvlM, lvlN = self._levels2d(rows, cols, lvlM, lvlN, "forward")
+        self._call2d_dev(self._fn + "2d_forward", d_in, d_out, batch, rows, cols, lvlM, lvlN,
+                         self._wavelet.getScalingDeComposition(), self._wavelet.getWaveletDeComposition(), flags,
+                         stream, slot)
+
+    def reverse2DDevice(self, d_in, d_out, batch, rows, cols, lvlM, lvlN, stream=0, flags=0, slot=0):
+        lvlM, lvlN = self._levels2d(rows, cols, lvlM, lvlN, "reverse")
+        self._call2d_dev(self._fn + "2d_inverse", d_in, d_out, batch, rows, cols, lvlM, lvlN,
+                         self._wavelet.getScalingReConstruction(), self._wavelet.getWaveletReConstruction(), flags,
+                         stream, slot)
 
     # ---- device-resident (benchmarks, pipelines that keep data in HBM) ------------------------------------
     def forwardDevice(self, d_in, d_out, batch, n, level, stream=0, flags=0, slot=0):

@@ -155,3 +155,25 @@ def batch(op, x, level, f0, f1, nthreads=1):
     rc = lib().jwo_batch(code, _p(x), _p(out), B, N, level, _p(f0), _p(f1), len(f0), nthreads)
     assert rc == 0, rc
     return out
+
+
+def batch2d(kind, x, lvl_m, lvl_n, f0, f1, reverse=False, nthreads=1):
+    """2-D FWT / WPT of every matrix of x (batch, rows, cols), composed from the 1-D oracle exactly as the reference
+    composes it: transforms/BasicTransform.java:361-399 (forward: every row with lvl_n, then every column of the result
+    with lvl_m) and :436-474 (reverse: every column with lvl_m, then every row with lvl_n).  The reference copies each
+    column into a temporary array; a transpose is the same gather."""
+    x = _c(x)
+    B, rows, cols = x.shape
+    op = kind + ("_rev" if reverse else "_fwd")
+
+    def along_rows(a, lvl):
+        return batch(op, a.reshape(B * rows, cols), lvl, f0, f1, nthreads).reshape(B, rows, cols)
+
+    def along_cols(a, lvl):
+        t = np.ascontiguousarray(a.transpose(0, 2, 1)).reshape(B * cols, rows)
+        r = batch(op, t, lvl, f0, f1, nthreads).reshape(B, cols, rows)
+        return np.ascontiguousarray(r.transpose(0, 2, 1))
+
+    if not reverse:
+        return along_cols(along_rows(x, lvl_n), lvl_m)
+    return along_rows(along_cols(x, lvl_m), lvl_n)

@@ -177,3 +177,45 @@ def test_batch_driver_threads(W, oracle):
     assert np.array_equal(f[2], oracle.fwt_forward(X[2], 7, s, wv))
     p = oracle.batch("wpt_fwd", X, 4, s, wv, nthreads=2)
     assert np.array_equal(p[5], oracle.wpt_forward(X[5], 4, s, wv))
+
+
+def test_2d_composition_follows_the_reference_loops(W, oracle):
+    """batch2d against a literal restatement of BasicTransform.java:361-399 / :436-474 (copy a row or a column into a
+    temporary array, transform it with the numpy 1-D oracle, copy it back); the reference's tests hold no 2-D known
+    answers, so the 2-D oracle is the pinned 1-D oracle plus this composition order."""
+    for kind, fwd1, rev1 in (("fwt", np_oracle.fwt_forward, np_oracle.fwt_reverse),
+                             ("wpt", np_oracle.wpt_forward, np_oracle.wpt_reverse)):
+        for cls, rows, cols, lm, ln in (("Haar1", 4, 8, 2, 3), ("Daubechies4", 16, 8, 3, 2), ("Symlet8", 8, 32, 1, 5),
+                                        ("Daubechies2", 32, 4, 0, 2), ("Coiflet2", 2, 16, 1, 0)):
+            w = W.create(cls)
+            s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+            sr, wr = w.getScalingReConstruction(), w.getWaveletReConstruction()
+            x = splitmix_uniform(5 + rows, (rows, cols))
+            hilb = np.empty_like(x)
+            for i in range(rows):
+                hilb[i, :] = fwd1(x[i, :].copy(), ln, s, wv)
+            for j in range(cols):
+                hilb[:, j] = fwd1(hilb[:, j].copy(), lm, s, wv)
+            got = oracle.batch2d(kind, x[None], lm, ln, s, wv)[0]
+            assert np.array_equal(got, hilb), (kind, cls)
+            time = np.empty_like(x)
+            for j in range(cols):
+                time[:, j] = rev1(hilb[:, j].copy(), lm, sr, wr)
+            for i in range(rows):
+                time[i, :] = rev1(time[i, :].copy(), ln, sr, wr)
+            back = oracle.batch2d(kind, hilb[None], lm, ln, sr, wr, reverse=True)[0]
+            assert np.array_equal(back, time), (kind, cls)
+            assert np.max(np.abs(back - x)) <= 1e-10
+
+
+def test_2d_all_ones_concentrates_in_one_coefficient(W, oracle):
+    """2-D extension of the reference's all-ones ladders (SteppingTest.java:37-314): a constant rows x cols matrix
+    transforms at full depth to sqrt(rows*cols) in the top-left corner and zeros elsewhere."""
+    for cls in ("Haar1", "Daubechies4", "Symlet8", "Coiflet3"):
+        w = W.create(cls)
+        s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+        for rows, cols in ((4, 4), (8, 64)):
+            out = oracle.batch2d("fwt", np.ones((1, rows, cols)), int(math.log2(rows)), int(math.log2(cols)), s, wv)[0]
+            exp = np.zeros((rows, cols))
+            exp[0, 0] = math.sqrt(rows * cols)
+            np.testing.assert_allclose(out, exp, atol=1e-9)

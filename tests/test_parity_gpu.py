@@ -4,6 +4,7 @@ Bars (BASELINE.json north_star): max|err| <= 1e-12 * max|x| for the default (FMA
 <= 1e-10; in JWC_FLAG_EXACT mode (unfused mul/add in the reference's order) the result must equal the oracle
 bit for bit.  Nothing here reads /root/reference.
 """
+import ctypes
 import math
 import os
 import threading
@@ -446,3 +447,61 @@ def test_modwt_single_series_split_over_devices(jw, oracle, cls, n, J):
     assert np.array_equal(back, jw.CudaMODWTTransform(w).inverseMODWT(whole))
     assert _maxerr(back, x, x) <= PR_TOL
     ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# 2-D FWT / WPT: BasicTransform.java:330-474 rows-then-columns / columns-then-rows
+# ----------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+@pytest.mark.parametrize("cls,rows,cols,lvl_m,lvl_n,batch", [
+    ("Haar1", 8, 8, 3, 3, 1),
+    ("Daubechies4", 64, 128, 6, 7, 3),
+    ("Daubechies4", 256, 64, 3, 2, 2),
+    ("Daubechies8", 512, 1024, 9, 10, 2),
+    ("Symlet8", 1024, 256, 4, 0, 1),
+    ("Symlet8", 128, 2048, 0, 5, 2),
+    ("Daubechies20", 16, 32, 4, 5, 2),      # filter (40 taps) longer than both dimensions
+    ("Symlet10", 2, 4, 1, 2, 5),
+    ("Daubechies2", 1, 64, 0, 6, 2),        # a single row: the column pass has nothing to do
+    ("Daubechies3", 4096, 48 * 0 + 32, 12, 5, 1),
+])
+def test_2d_matches_oracle(jw, gpu_ctx, oracle, kind, cls, rows, cols, lvl_m, lvl_n, batch):
+    w = jw.wavelets.create(cls)
+    T = jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform
+    t = T(w)
+    X = splitmix_uniform(1234 + rows + cols, (batch, rows, cols))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.batch2d(kind, X, lvl_m, lvl_n, s, wv, nthreads=8)
+    got = t.forward2DBatch(X, lvl_m, lvl_n)
+    assert _maxerr(got, ref, X) <= TOL
+    exact = t.forward2DBatch(X, lvl_m, lvl_n, flags=jw.FLAG_EXACT)
+    assert np.array_equal(exact, ref)
+    rref = oracle.batch2d(kind, ref, lvl_m, lvl_n, w.getScalingReConstruction(), w.getWaveletReConstruction(),
+                          reverse=True, nthreads=8)
+    back = t.reverse2DBatch(ref, lvl_m, lvl_n)
+    assert _maxerr(back, rref, X) <= TOL
+    assert np.array_equal(t.reverse2DBatch(ref, lvl_m, lvl_n, flags=jw.FLAG_EXACT), rref)
+    assert _maxerr(t.reverse2DBatch(got, lvl_m, lvl_n), X, X) <= PR_TOL
+
+
+def test_2d_java_overloads_and_errors(jw, gpu_ctx, oracle):
+    """forward(double[][]) = full depth in both dimensions (BasicTransform.java:336-340); errors as the 1-D calls."""
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaFastWaveletTransform(w)
+    X = splitmix_uniform(99, (32, 64))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.batch2d("fwt", X[None], 5, 6, s, wv)[0]
+    assert _maxerr(t.forward(X), ref, X) <= TOL
+    assert _maxerr(t.forward(X, 5, 6), ref, X) <= TOL
+    assert _maxerr(t.reverse(t.forward(X)), X, X) <= PR_TOL
+    assert _maxerr(t.reverse(t.forward(X, 2, 3), 2, 3), X, X) <= PR_TOL
+    with pytest.raises(jw.JWaveFailure, match="2\\^p"):
+        t.forward(np.zeros((24, 64)))
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        t.forward(np.zeros((32, 64)), 6, 6)
+    lib = jw._native.load()
+    f = (ctypes.c_double * 2)(0.5, 0.5)
+    buf = np.zeros(64)
+    rc = lib.jwc_fwt2d_forward(gpu_ctx.handle, buf.ctypes.data, buf.ctypes.data, 1, 6, 8, 1, 1, f, f, 2, 0)
+    assert rc == -1 and b"2^p" in lib.jwc_last_error()
