@@ -114,9 +114,35 @@ class WaveletTransform : public BasicTransform {
     const int rc = fn(ctx_->handle(), in, out, batch, n, levels, f0.data(), f1.data(), (int)f0.size(), flags);
     if (rc != JWC_OK) throw std::runtime_error(std::string(what) + " failed: " + jwc_last_error());
   }
+  using Fn2 = int (*)(jwc_ctx*, const double*, double*, int64_t, int64_t, int64_t, int, int, const double*, const double*, int, unsigned);
+  void call2d(Fn2 fn, const char* what, const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, int lvlM,
+              int lvlN, const std::vector<double>& f0, const std::vector<double>& f1, unsigned flags = 0) const {
+    const int rc = fn(ctx_->handle(), in, out, batch, rows, cols, lvlM, lvlN, f0.data(), f1.data(), (int)f0.size(), flags);
+    if (rc != JWC_OK) throw std::runtime_error(std::string(what) + " failed: " + jwc_last_error());
+  }
   Wavelet wavelet_;
   std::shared_ptr<Context> ctx_;
 };
+
+using Matrix = std::vector<std::vector<double>>;
+
+namespace detail {
+inline std::vector<double> flatten(const Matrix& m) {
+  std::vector<double> flat;
+  if (m.empty()) return flat;
+  flat.reserve(m.size() * m[0].size());
+  for (const auto& r : m) {
+    if (r.size() != m[0].size()) throw JWaveFailure("BasicTransform - given matrix is not rectangular");
+    flat.insert(flat.end(), r.begin(), r.end());
+  }
+  return flat;
+}
+inline Matrix unflatten(const std::vector<double>& flat, size_t rows, size_t cols) {
+  Matrix m(rows, std::vector<double>(cols));
+  for (size_t i = 0; i < rows; i++) std::copy(flat.begin() + (long)(i * cols), flat.begin() + (long)((i + 1) * cols), m[i].begin());
+  return m;
+}
+}  // namespace detail
 
 namespace detail {
 inline void check_pyramid(const char* cls, const char* dir, int64_t len, int level) {
@@ -157,6 +183,36 @@ class CudaFastWaveletTransform : public WaveletTransform {
     detail::check_pyramid("FastWaveletTransform", "reverse", n, level);
     call(jwc_fwt_inverse, "jwc_fwt_inverse", in, out, batch, n, level, wavelet_.getScalingReConstruction(), wavelet_.getWaveletReConstruction());
   }
+  // 2-D: BasicTransform.java:336-399 forward(double[][][, lvlM, lvlN]) = rows (lvlN) then columns (lvlM);
+  //      :412-474 reverse = columns first, then rows.  [batch][rows][cols] row-major host buffers for the batch form.
+  void forward2DBatch(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, int lvlM, int lvlN) const {
+    detail::check_pyramid("FastWaveletTransform", "forward", cols, lvlN);
+    detail::check_pyramid("FastWaveletTransform", "forward", rows, lvlM);
+    call2d(jwc_fwt2d_forward, "jwc_fwt2d_forward", in, out, batch, rows, cols, lvlM, lvlN, wavelet_.getScalingDeComposition(), wavelet_.getWaveletDeComposition());
+  }
+  void reverse2DBatch(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, int lvlM, int lvlN) const {
+    detail::check_pyramid("FastWaveletTransform", "reverse", cols, lvlN);
+    detail::check_pyramid("FastWaveletTransform", "reverse", rows, lvlM);
+    call2d(jwc_fwt2d_inverse, "jwc_fwt2d_inverse", in, out, batch, rows, cols, lvlM, lvlN, wavelet_.getScalingReConstruction(), wavelet_.getWaveletReConstruction());
+  }
+  Matrix forward(const Matrix& matTime, int lvlM, int lvlN) const {
+    const std::vector<double> flat = detail::flatten(matTime);
+    std::vector<double> out(flat.size());
+    forward2DBatch(flat.data(), out.data(), 1, (int64_t)matTime.size(), (int64_t)matTime.at(0).size(), lvlM, lvlN);
+    return detail::unflatten(out, matTime.size(), matTime[0].size());
+  }
+  Matrix forward(const Matrix& matTime) const {
+    return forward(matTime, calcExponent((int64_t)matTime.size()), calcExponent((int64_t)matTime.at(0).size()));
+  }
+  Matrix reverse(const Matrix& matHilb, int lvlM, int lvlN) const {
+    const std::vector<double> flat = detail::flatten(matHilb);
+    std::vector<double> out(flat.size());
+    reverse2DBatch(flat.data(), out.data(), 1, (int64_t)matHilb.size(), (int64_t)matHilb.at(0).size(), lvlM, lvlN);
+    return detail::unflatten(out, matHilb.size(), matHilb[0].size());
+  }
+  Matrix reverse(const Matrix& matHilb) const {
+    return reverse(matHilb, calcExponent((int64_t)matHilb.size()), calcExponent((int64_t)matHilb.at(0).size()));
+  }
 };
 
 class CudaWaveletPacketTransform : public WaveletTransform {
@@ -187,6 +243,36 @@ class CudaWaveletPacketTransform : public WaveletTransform {
   void reverseBatch(const double* in, double* out, int64_t batch, int64_t n, int level) const {
     detail::check_pyramid("WaveletPacketTransform", "reverse", n, level);
     call(jwc_wpt_inverse, "jwc_wpt_inverse", in, out, batch, n, level, wavelet_.getScalingReConstruction(), wavelet_.getWaveletReConstruction());
+  }
+  // 2-D: BasicTransform.java:336-399 forward(double[][][, lvlM, lvlN]) = rows (lvlN) then columns (lvlM);
+  //      :412-474 reverse = columns first, then rows.  [batch][rows][cols] row-major host buffers for the batch form.
+  void forward2DBatch(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, int lvlM, int lvlN) const {
+    detail::check_pyramid("WaveletPacketTransform", "forward", cols, lvlN);
+    detail::check_pyramid("WaveletPacketTransform", "forward", rows, lvlM);
+    call2d(jwc_wpt2d_forward, "jwc_wpt2d_forward", in, out, batch, rows, cols, lvlM, lvlN, wavelet_.getScalingDeComposition(), wavelet_.getWaveletDeComposition());
+  }
+  void reverse2DBatch(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols, int lvlM, int lvlN) const {
+    detail::check_pyramid("WaveletPacketTransform", "reverse", cols, lvlN);
+    detail::check_pyramid("WaveletPacketTransform", "reverse", rows, lvlM);
+    call2d(jwc_wpt2d_inverse, "jwc_wpt2d_inverse", in, out, batch, rows, cols, lvlM, lvlN, wavelet_.getScalingReConstruction(), wavelet_.getWaveletReConstruction());
+  }
+  Matrix forward(const Matrix& matTime, int lvlM, int lvlN) const {
+    const std::vector<double> flat = detail::flatten(matTime);
+    std::vector<double> out(flat.size());
+    forward2DBatch(flat.data(), out.data(), 1, (int64_t)matTime.size(), (int64_t)matTime.at(0).size(), lvlM, lvlN);
+    return detail::unflatten(out, matTime.size(), matTime[0].size());
+  }
+  Matrix forward(const Matrix& matTime) const {
+    return forward(matTime, calcExponent((int64_t)matTime.size()), calcExponent((int64_t)matTime.at(0).size()));
+  }
+  Matrix reverse(const Matrix& matHilb, int lvlM, int lvlN) const {
+    const std::vector<double> flat = detail::flatten(matHilb);
+    std::vector<double> out(flat.size());
+    reverse2DBatch(flat.data(), out.data(), 1, (int64_t)matHilb.size(), (int64_t)matHilb.at(0).size(), lvlM, lvlN);
+    return detail::unflatten(out, matHilb.size(), matHilb[0].size());
+  }
+  Matrix reverse(const Matrix& matHilb) const {
+    return reverse(matHilb, calcExponent((int64_t)matHilb.size()), calcExponent((int64_t)matHilb.at(0).size()));
   }
 };
 

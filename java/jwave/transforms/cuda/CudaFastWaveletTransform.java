@@ -11,7 +11,8 @@ import jwave.transforms.wavelets.Wavelet;
  * Drop-in for {@link FastWaveletTransform}: same constructor, same _name ("Fast Wavelet Transform", so
  * TransformBuilder.identify keeps working), same validation and messages (FastWaveletTransform.java:74-83,122-131);
  * the level loops and Wavelet.forward/reverse run as CUDA kernels (jwc_fwt_forward / jwc_fwt_inverse).
- * Inherited decompose/recompose, Complex[], 2-D and 3-D drivers only call these 1-D methods and keep working.
+ * Inherited decompose/recompose, Complex[] and 3-D drivers only call these 1-D methods and keep working; the 2-D
+ * matrix overloads are overridden to run as one device call.
  */
 public class CudaFastWaveletTransform extends FastWaveletTransform {
 
@@ -41,6 +42,26 @@ public class CudaFastWaveletTransform extends FastWaveletTransform {
   public void reverse(MemorySegment in, MemorySegment out, long batch, int n, int level) throws JWaveException {
     check(n, level, "reverse");
     JwcNative.run(JwcNative.FWT_INVERSE, CudaContext.get(), in, out, batch, n, level,
+        _wavelet.getScalingReConstruction(), _wavelet.getWaveletReConstruction(), 0);
+  }
+
+  /**
+   * 2-D forward, BasicTransform.java:361-399: every row through forward(row, lvlN), then every column through
+   * forward(col, lvlM) -- here one row pass and an in-place column pass on the device (jwc_fwt2d_forward) instead of
+   * rows + cols separate 1-D calls.  forward(double[][]) (:336-340) delegates here with full depth.
+   */
+  @Override public double[][] forward(double[][] matTime, int lvlM, int lvlN) throws JWaveException {
+    check(matTime[0].length, lvlN, "forward");
+    check(matTime.length, lvlM, "forward");
+    return JwcNative.run2d(JwcNative.FWT2D_FORWARD, CudaContext.get(), matTime, lvlM, lvlN,
+        _wavelet.getScalingDeComposition(), _wavelet.getWaveletDeComposition(), 0);
+  }
+
+  /** 2-D reverse, BasicTransform.java:436-474: columns (lvlM) first, then rows (lvlN). */
+  @Override public double[][] reverse(double[][] matFreq, int lvlM, int lvlN) throws JWaveException {
+    check(matFreq[0].length, lvlN, "reverse");
+    check(matFreq.length, lvlM, "reverse");
+    return JwcNative.run2d(JwcNative.FWT2D_INVERSE, CudaContext.get(), matFreq, lvlM, lvlN,
         _wavelet.getScalingReConstruction(), _wavelet.getWaveletReConstruction(), 0);
   }
 

@@ -41,6 +41,26 @@ public class CudaWaveletPacketTransform extends WaveletPacketTransform {
         _wavelet.getScalingReConstruction(), _wavelet.getWaveletReConstruction(), 0);
   }
 
+  /**
+   * 2-D forward, BasicTransform.java:361-399: every row through forward(row, lvlN), then every column through
+   * forward(col, lvlM) -- here one row pass and an in-place column pass on the device (jwc_wpt2d_forward) instead of
+   * rows + cols separate 1-D calls.  forward(double[][]) (:336-340) delegates here with full depth.
+   */
+  @Override public double[][] forward(double[][] matTime, int lvlM, int lvlN) throws JWaveException {
+    check(matTime[0].length, lvlN, "forward");
+    check(matTime.length, lvlM, "forward");
+    return JwcNative.run2d(JwcNative.WPT2D_FORWARD, CudaContext.get(), matTime, lvlM, lvlN,
+        _wavelet.getScalingDeComposition(), _wavelet.getWaveletDeComposition(), 0);
+  }
+
+  /** 2-D reverse, BasicTransform.java:436-474: columns (lvlM) first, then rows (lvlN). */
+  @Override public double[][] reverse(double[][] matFreq, int lvlM, int lvlN) throws JWaveException {
+    check(matFreq[0].length, lvlN, "reverse");
+    check(matFreq.length, lvlM, "reverse");
+    return JwcNative.run2d(JwcNative.WPT2D_INVERSE, CudaContext.get(), matFreq, lvlM, lvlN,
+        _wavelet.getScalingReConstruction(), _wavelet.getWaveletReConstruction(), 0);
+  }
+
   private void check(int length, int level, String dir) throws JWaveException {
     if (!isBinary(length))
       throw new JWaveFailure("given array length is not 2^p | p E N ... = 1, 2, 4, 8, 16, 32, .. "

@@ -30,6 +30,10 @@ public final class JwcNative {
   private static final SymbolLookup LIB;
   private static final MethodHandle CREATE, DESTROY, LAST_ERROR, ALLOC_PINNED, FREE_PINNED;
   private static final MethodHandle[] TRANSFORMS = new MethodHandle[6];
+  private static final MethodHandle[] TRANSFORMS_2D = new MethodHandle[4];
+  private static final String[] NAMES_2D = {
+      "jwc_fwt2d_forward", "jwc_fwt2d_inverse", "jwc_wpt2d_forward", "jwc_wpt2d_inverse" };
+  public static final int FWT2D_FORWARD = 0, FWT2D_INVERSE = 1, WPT2D_FORWARD = 2, WPT2D_INVERSE = 3;
   private static final String[] NAMES = {
       "jwc_modwt_forward", "jwc_modwt_inverse", "jwc_fwt_forward", "jwc_fwt_inverse", "jwc_wpt_forward",
       "jwc_wpt_inverse" };
@@ -51,6 +55,11 @@ public final class JwcNative {
     FunctionDescriptor t = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT,
         ADDRESS, ADDRESS, JAVA_INT, JAVA_INT);
     for (int i = 0; i < NAMES.length; i++) TRANSFORMS[i] = handle(NAMES[i], t);
+    // int f(jwc_ctx*, const double* in, double* out, int64 batch, int64 rows, int64 cols, int lvlM, int lvlN,
+    //       const double* lo, const double* hi, int L, unsigned flags)
+    FunctionDescriptor t2 = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG,
+        JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT);
+    for (int i = 0; i < NAMES_2D.length; i++) TRANSFORMS_2D[i] = handle(NAMES_2D[i], t2);
   }
 
   private static MethodHandle handle(String name, FunctionDescriptor fd) {
@@ -126,6 +135,39 @@ public final class JwcNative {
       MemorySegment so = a.allocateArray(JAVA_DOUBLE, outLen);
       run(which, ctx, si, so, batch, n, levels, f0, f1, flags);
       return so.toArray(JAVA_DOUBLE);
+    }
+  }
+
+  /** 2-D transform of `batch` row-major rows x cols matrices held in off-heap segments. */
+  public static void run2d(int which, MemorySegment ctx, MemorySegment in, MemorySegment out, long batch, long rows,
+      long cols, int lvlM, int lvlN, double[] f0, double[] f1, int flags) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment s0 = a.allocateArray(JAVA_DOUBLE, f0);
+      MemorySegment s1 = a.allocateArray(JAVA_DOUBLE, f1);
+      int rc = (int) TRANSFORMS_2D[which].invokeExact(ctx, in, out, batch, rows, cols, lvlM, lvlN, s0, s1, f0.length,
+          flags);
+      if (rc != 0) throw new IllegalStateException(NAMES_2D[which] + " failed (" + rc + "): " + lastError());
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  /** double[][] convenience: flatten, transform, un-flatten (the reference allocates a fresh matrix as well). */
+  public static double[][] run2d(int which, MemorySegment ctx, double[][] mat, int lvlM, int lvlN, double[] f0,
+      double[] f1, int flags) {
+    int rows = mat.length, cols = mat[0].length;
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment si = a.allocateArray(JAVA_DOUBLE, (long) rows * cols);
+      MemorySegment so = a.allocateArray(JAVA_DOUBLE, (long) rows * cols);
+      for (int i = 0; i < rows; i++)
+        MemorySegment.copy(mat[i], 0, si, JAVA_DOUBLE, (long) i * cols * Double.BYTES, cols);
+      run2d(which, ctx, si, so, 1, rows, cols, lvlM, lvlN, f0, f1, flags);
+      double[][] out = new double[rows][cols];
+      for (int i = 0; i < rows; i++)
+        MemorySegment.copy(so, JAVA_DOUBLE, (long) i * cols * Double.BYTES, out[i], 0, cols);
+      return out;
     }
   }
 }

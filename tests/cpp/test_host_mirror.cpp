@@ -78,6 +78,27 @@ int main() {
     auto r = fwt.recompose(m, 3);
     for (double v : r) CHECK(std::fabs(v - 1.0) < 1e-8);
   }
+  {  // 2-D overloads (BasicTransform.java:336-474): constant 8 x 16 matrix -> sqrt(128) in the corner; round trip
+    CudaFastWaveletTransform fwt(make("Daubechies4"), ctx);
+    CudaWaveletPacketTransform wpt(make("Symlet8"), ctx);
+    Matrix ones(8, std::vector<double>(16, 1.0));
+    Matrix h = fwt.forward(ones);
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 16; j++) CHECK(std::fabs(h[i][j] - ((i == 0 && j == 0) ? std::sqrt(128.0) : 0.0)) < 1e-8);
+    Matrix ramp(8, std::vector<double>(16));
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 16; j++) ramp[i][j] = std::sin(0.37 * i + 0.11 * j * j);
+    Matrix back = fwt.reverse(fwt.forward(ramp, 2, 3), 2, 3);
+    Matrix back2 = wpt.reverse(wpt.forward(ramp));
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 16; j++) { CHECK(std::fabs(back[i][j] - ramp[i][j]) < 1e-10); CHECK(std::fabs(back2[i][j] - ramp[i][j]) < 1e-10); }
+    bool thrown = false;
+    try { fwt.forward(Matrix(6, std::vector<double>(16, 1.0))); } catch (const JWaveFailure& e) { thrown = true; }
+    CHECK(thrown);
+    thrown = false;
+    try { fwt.forward(ramp, 4, 3); } catch (const JWaveFailure& e) { thrown = strstr(e.what(), "out of range") != nullptr; }
+    CHECK(thrown);
+  }
   printf(fails ? "%d checks FAILED\n" : "host mirror ok\n", fails);
   return fails ? 1 : 0;
 }
