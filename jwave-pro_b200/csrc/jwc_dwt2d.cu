@@ -12,6 +12,7 @@
 //
 // Per-column arithmetic is Wavelet.java:236-260 (analysis) and :277-303 (synthesis) with `mod h` along the rows.
 #include "jwc_internal.cuh"
+#include "jwc_tma.cuh"
 
 namespace jwc {
 
@@ -195,6 +196,254 @@ __global__ void __launch_bounds__(kStrip* kGroups) col_syn_generic_kernel(const 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused column passes for the pyramid (FWT): K levels per launch through shared memory.
+//
+// Forward: a CTA stages T + (L-2)(2^K - 1) input rows of its 32-column strip (rows wrap mod h in the loader, 16-byte
+// cp.async, one 256-byte row segment per half warp), then runs the K analysis levels out of shared memory: level j
+// keeps T/2^j + (L-2)(2^(K-j) - 1) low-pass rows for the next level and writes the T/2^j high-pass rows of its own
+// region straight to their final place; only the last low-pass rows go back to HBM.  Column-pass traffic drops from
+// (2 reads + 2 writes) x matrix to about 1 + 1.
+// Inverse: mirror image.  The K synthesis levels need a LEFT halo that grows as G_s = G_(s-1)/2 + L/2 - 1 (kept even
+// so every level starts on a pair boundary); the low-pass rows of the intermediate levels live in shared memory, the
+// high-pass rows of every level are read from HBM where they lie, inside the sliding-window loads.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPad = 2 * kRun;   // slack rows behind every shared buffer: the last run of a level may read past its end
+
+struct ColFuseArgs {
+  const double* src;    // forward: A_l rows [0,h);  inverse: A at the deepest level of this launch, rows [0, h >> K)
+  const double* det;    // inverse: the coefficient matrix holding the detail rows (row half_s + i of a block of h)
+  double* dst;          // forward: A_(l+K), h >> K rows;  inverse: the synthesised rows [0, h)
+  double* out;          // forward: the coefficient matrix receiving the detail rows
+  int64_t src_mat, det_mat, dst_mat, out_mat;
+  int64_t ld, cols;
+  int64_t h;            // rows at the TOP of this launch (input height forward, output height inverse)
+  int64_t tiles, strips;
+};
+
+__host__ __device__ constexpr int fwd_halo(int L, int m) { return (L - 2) * ((1 << m) - 1); }
+__host__ __device__ constexpr int inv_halo(int L, int s, int K) {   // G_s
+  int g = 0;
+  for (int i = 1; i <= s; i++) {
+    g = g / 2 + (L / 2 - 1);
+    if (i < K) g += (g & 1);
+  }
+  return g;
+}
+
+template <int L, int K, int T>
+__global__ void __launch_bounds__(kStrip* kGroups) col_ana_fused_kernel(const __grid_constant__ ColFuseArgs a,
+                                                                        const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  constexpr int NA = T + fwd_halo(L, K);
+  double* A = sm;
+  double* B = sm + (NA + kPad) * kStrip;
+  int64_t id = blockIdx.x;
+  const int64_t strip = id % a.strips;
+  id /= a.strips;
+  const int64_t r0 = (id % a.tiles) * T, b = id / a.tiles;
+  const int64_t c0 = strip * kStrip;
+  const int ncol = (int)((a.cols - c0 < kStrip) ? a.cols - c0 : kStrip);
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kStrip + tx;
+  {
+    const double* src = a.src + b * a.src_mat + c0;
+    for (int idx = tid; idx < NA * (kStrip / 2); idx += kStrip * kGroups) {
+      const int row = idx / (kStrip / 2), seg = idx % (kStrip / 2);
+      if (2 * seg < ncol) ptx::cp_async16(&A[row * kStrip + 2 * seg], src + ((r0 + row) % a.h) * a.ld + 2 * seg);
+    }
+    ptx::cp_async_commit_wait_all();
+  }
+  __syncthreads();
+  const double* in = A;
+  double* nxt = B;
+#pragma unroll
+  for (int j = 1; j <= K; j++) {
+    const int n_lo = (T >> j) + fwd_halo(L, K - j);   // low-pass rows the next level needs
+    const int n_hi = T >> j;                          // rows of this tile's own region
+    double* g_hi = a.out + b * a.out_mat + ((a.h >> j) + (r0 >> j)) * a.ld + c0 + tx;
+    double* g_lo = a.dst + b * a.dst_mat + (r0 >> K) * a.ld + c0 + tx;
+    for (int i0 = ty * kRun; i0 < n_lo; i0 += kGroups * kRun) {
+      constexpr int W = L + 2 * kRun - 2;
+      double win[W];
+#pragma unroll
+      for (int t = 0; t < W; t++) win[t] = in[(2 * i0 + t) * kStrip + tx];
+#pragma unroll
+      for (int q = 0; q < kRun; q++) {
+        const int i = i0 + q;
+        if (i < n_lo) {
+          double sl = 0.0;
+#pragma unroll
+          for (int m = 0; m < L; m++) sl = fma(win[2 * q + m], f.f0[m], sl);
+          if (j < K) nxt[i * kStrip + tx] = sl;
+          else if (tx < ncol) g_lo[(int64_t)i * a.ld] = sl;
+          if (i < n_hi) {
+            double sh = 0.0;
+#pragma unroll
+            for (int m = 0; m < L; m++) sh = fma(win[2 * q + m], f.f1[m], sh);
+            if (tx < ncol) g_hi[(int64_t)i * a.ld] = sh;
+          }
+        }
+      }
+    }
+    if (j < K) {
+      __syncthreads();
+      in = nxt;
+      nxt = (j & 1) ? A : B;
+    }
+  }
+}
+
+template <int L, int K, int T>
+__global__ void __launch_bounds__(kStrip* kGroups) col_syn_fused_kernel(const __grid_constant__ ColFuseArgs a,
+                                                                        const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  constexpr int M = L / 2;
+  constexpr int N1 = (T >> 1) + inv_halo(L, 1, K);   // the largest intermediate level
+  double* X = sm;
+  double* Y = sm + (N1 + kPad) * kStrip;
+  int64_t id = blockIdx.x;
+  const int64_t strip = id % a.strips;
+  id /= a.strips;
+  const int64_t r0 = (id % a.tiles) * T, b = id / a.tiles;
+  const int64_t c0 = strip * kStrip;
+  const int ncol = (int)((a.cols - c0 < kStrip) ? a.cols - c0 : kStrip);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t cx = c0 + (tx < ncol ? tx : 0);   // idle lanes of a partial strip shadow column c0 (loads only)
+#pragma unroll
+  for (int s = K; s >= 1; s--) {
+    // step s: lo_(s-1) rows [0, n_out) (local) from lo_s / hi_s;  local row t of level s = global row
+    // ((r0 >> s) - G_s + t) mod half_s
+    const int Gs = inv_halo(L, s, K), Gp = inv_halo(L, s - 1, K);
+    const int n_out = (T >> (s - 1)) + Gp;          // even
+    const int off = Gs - Gp / 2 - (M - 1);          // first lo_s row used by output pair 0
+    const int64_t half = a.h >> s;
+    const double* g_lo = a.src + b * a.src_mat + cx;                      // used when s == K
+    const double* g_hi = a.det + b * a.det_mat + half * a.ld + cx;        // detail rows of the block of 2*half rows
+    const double* s_lo = ((K - s) & 1) ? X : Y;     // written by step s+1
+    double* s_out = ((K - s) & 1) ? Y : X;
+    double* g_out = a.dst + b * a.dst_mat + r0 * a.ld + c0 + tx;          // used when s == 1
+    for (int u0 = ty * kRun; u0 < n_out / 2; u0 += kGroups * kRun) {
+      constexpr int W = kRun + M - 1;
+      double wl[W], wh[W];
+      int64_t gr = ((r0 >> s) - Gs + off + u0) % half;
+      if (gr < 0) gr += half;
+#pragma unroll
+      for (int t = 0; t < W; t++) {
+        wh[t] = g_hi[gr * a.ld];
+        if (s == K) wl[t] = g_lo[gr * a.ld];
+        else wl[t] = s_lo[(off + u0 + t) * kStrip + tx];
+        if (++gr == half) gr = 0;
+      }
+#pragma unroll
+      for (int u = 0; u < kRun; u++) {
+        if (u0 + u < n_out / 2) {
+          double e = 0.0, o = 0.0;
+#pragma unroll
+          for (int m = M - 1; m >= 0; m--) {
+            const double cl = wl[u - m + M - 1], ch = wh[u - m + M - 1];
+            e = fma(ch, f.f1[2 * m], fma(cl, f.f0[2 * m], e));
+            o = fma(ch, f.f1[2 * m + 1], fma(cl, f.f0[2 * m + 1], o));
+          }
+          const int row = 2 * (u0 + u);
+          if (s > 1) {
+            s_out[row * kStrip + tx] = e;
+            s_out[(row + 1) * kStrip + tx] = o;
+          } else if (tx < ncol) {
+            g_out[(int64_t)row * a.ld] = e;
+            g_out[(int64_t)(row + 1) * a.ld] = o;
+          }
+        }
+      }
+    }
+    if (s > 1) __syncthreads();
+  }
+}
+
+template <int L>
+struct FuseCfg {
+  static constexpr int T = 128;
+  static constexpr int Kmax = (L <= 10) ? 3 : 2;
+};
+
+template <int L, int K>
+size_t ana_fused_smem() {
+  constexpr int T = FuseCfg<L>::T;
+  return (size_t)((T + fwd_halo(L, K) + kPad) + ((T >> 1) + fwd_halo(L, K - 1) + kPad)) * kStrip * sizeof(double);
+}
+template <int L, int K>
+size_t syn_fused_smem() {
+  constexpr int T = FuseCfg<L>::T;
+  return (size_t)(2 * ((T >> 1) + inv_halo(L, 1, K) + kPad)) * kStrip * sizeof(double);
+}
+
+template <int L, int K>
+int launch_fused(jwc_ctx* ctx, cudaStream_t st, ColFuseArgs a, const FilterPair& f, int64_t batch, bool inverse) {
+  constexpr int T = FuseCfg<L>::T;
+  a.strips = (a.cols + kStrip - 1) / kStrip;
+  a.tiles = a.h / T;
+  const int64_t ctas = a.strips * a.tiles * batch;
+  if (ctas > 0x7fffffffLL) { set_error("2-D transform too large for one launch"); return JWC_ERR_UNSUPPORTED; }
+  const dim3 grid((unsigned)ctas), block(kStrip, kGroups);
+  if (!inverse) {
+    const size_t smem = ana_fused_smem<L, K>();
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+      JWC_CUDA_CHECK(cudaFuncSetAttribute(col_ana_fused_kernel<L, K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_dev = dev;
+    }
+    col_ana_fused_kernel<L, K, T><<<grid, block, smem, st>>>(a, f);
+  } else {
+    const size_t smem = syn_fused_smem<L, K>();
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+      JWC_CUDA_CHECK(cudaFuncSetAttribute(col_syn_fused_kernel<L, K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_dev = dev;
+    }
+    col_syn_fused_kernel<L, K, T><<<grid, block, smem, st>>>(a, f);
+  }
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+#define JWC_FUSE_L(X) X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20)
+
+// how many levels the next fused launch takes (< 2: use the per-level kernel for one level)
+int fused_levels_fwd(int L, int64_t h, int64_t cols, int remaining) {
+  if (L < 2 || L > 20 || (L & 1) || (cols & 1) || h < 128) return 0;
+  const int kmax = (L <= 10) ? 3 : 2;
+  return remaining < kmax ? remaining : kmax;
+}
+// inverse: hcur = rows of the deepest low-pass block the launch starts from; it produces hcur << k rows
+int fused_levels_inv(int L, int64_t hcur, int64_t cols, int remaining) {
+  if (L < 2 || L > 20 || (L & 1) || (cols & 1)) return 0;
+  const int kmax = (L <= 10) ? 3 : 2;
+  for (int k = remaining < kmax ? remaining : kmax; k >= 2; k--)
+    if ((hcur << k) >= 128 && hcur >= inv_halo(L, k, k) && hcur >= L / 2) return k;   // half_k is the tightest level
+  return 0;
+}
+
+int run_fused(jwc_ctx* ctx, cudaStream_t st, const ColFuseArgs& a, const FilterPair& f, int64_t batch, int L, int K,
+              bool inverse) {
+  switch (L) {
+#define X(LL)                                                                                   \
+  case LL:                                                                                      \
+    if (K == 2) return launch_fused<LL, 2>(ctx, st, a, f, batch, inverse);                      \
+    if (K == 3 && FuseCfg<LL>::Kmax >= 3) return launch_fused<LL, (FuseCfg<LL>::Kmax >= 3 ? 3 : 2)>(ctx, st, a, f, batch, inverse); \
+    break;
+    JWC_FUSE_L(X)
+#undef X
+    default: break;
+  }
+  set_error("no fused column kernel for L=%d K=%d", L, K);
+  return JWC_ERR_UNSUPPORTED;
+}
+
 template <int L>
 void launch_ana(const ColArgs& a, const FilterPair& f, dim3 grid, dim3 block, cudaStream_t st, bool exact) {
   if (exact) col_ana_kernel<L, true><<<grid, block, 0, st>>>(a, f);
@@ -284,32 +533,53 @@ int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
     }
     return JWC_OK;
   }
-  // pyramid: detail rows go straight to their final place in d_out, approximations ping-pong through scratch
+  // pyramid: detail rows go straight to their final place in d_out, approximations ping-pong through scratch.
+  // Schedule first (fused launches of 2-3 levels where the shape allows, single levels otherwise), then allocate.
+  std::vector<int> sched;
+  for (int l = 0; l < steps;) {
+    int k = exact ? 0 : fused_levels_fwd(L, rows >> l, cols, steps - l);
+    if (k < 2) k = 1;
+    sched.push_back(k);
+    l += k;
+  }
   double* abuf[2] = {nullptr, nullptr};
-  if (steps >= 2) {
+  if (sched.size() >= 2) {
     abuf[0] = ws.get((size_t)batch * (mat >> 1));
     if (!abuf[0]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
-  if (steps >= 3) {
+  if (sched.size() >= 3) {
     abuf[1] = ws.get((size_t)batch * (mat >> 2));
     if (!abuf[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const double* src = d_src;
   int64_t src_mat = mat;
   int64_t h = rows;
-  for (int l = 0; l < steps; l++, h >>= 1) {
-    ColArgs a{};
-    a.src_lo = src; a.src_lo_mat = src_mat;
-    if (l == steps - 1) { a.dst_lo = d_out; a.dst_lo_mat = mat; }
-    else { a.dst_lo = abuf[l & 1]; a.dst_lo_mat = (h >> 1) * cols; }
-    a.dst_hi = d_out + (h >> 1) * cols; a.dst_hi_mat = mat;
-    a.ld = cols; a.cols = cols; a.h = h; a.blocks = 1; a.L = L;
-    const int rc = col_step(ctx, st, a, f, batch, false, exact);
+  for (size_t i = 0; i < sched.size(); i++) {
+    const int k = sched[i];
+    const bool last = (i + 1 == sched.size());
+    double* dst = last ? d_out : abuf[i & 1];
+    const int64_t dst_mat = last ? mat : (h >> k) * cols;
+    int rc;
+    if (k >= 2) {
+      ColFuseArgs a{};
+      a.src = src; a.src_mat = src_mat;
+      a.dst = dst; a.dst_mat = dst_mat;
+      a.out = d_out; a.out_mat = mat;
+      a.ld = cols; a.cols = cols; a.h = h;
+      rc = run_fused(ctx, st, a, f, batch, L, k, false);
+    } else {
+      ColArgs a{};
+      a.src_lo = src; a.src_lo_mat = src_mat;
+      a.dst_lo = dst; a.dst_lo_mat = dst_mat;
+      a.dst_hi = d_out + (h >> 1) * cols; a.dst_hi_mat = mat;
+      a.ld = cols; a.cols = cols; a.h = h; a.blocks = 1; a.L = L;
+      rc = col_step(ctx, st, a, f, batch, false, exact);
+    }
     if (rc != JWC_OK) return rc;
-    src = a.dst_lo;
-    src_mat = a.dst_lo_mat;
+    src = dst;
+    src_mat = dst_mat;
+    h >>= k;
   }
-  // rows the column pass never touches do not exist: step 0 always covers all `rows` rows
   return JWC_OK;
 }
 
@@ -341,32 +611,57 @@ int dwt2d_columns_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
     }
     return JWC_OK;
   }
-  // pyramid: A_l from scratch (or the input for the first step), D_l from the input; the rows above the deepest
-  // block that the steps never rebuild are the detail rows consumed later, so every row of d_dst is written by the
-  // last step (h = rows).
+  // pyramid: A from scratch (or the input for the first launch), detail rows from the input where they lie.  The last
+  // launch writes all `rows` rows of d_dst.
+  std::vector<int> sched;
+  {
+    int64_t hcur = rows >> steps;
+    for (int done = 0; done < steps;) {
+      int k = exact ? 0 : fused_levels_inv(L, hcur, cols, steps - done);
+      if (k < 2) k = 1;
+      sched.push_back(k);
+      done += k;
+      hcur <<= k;
+    }
+  }
   double* abuf[2] = {nullptr, nullptr};
-  if (steps >= 2) {
+  if (sched.size() >= 2) {
     abuf[0] = ws.get((size_t)batch * (mat >> 1));
     if (!abuf[0]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
-  if (steps >= 3) {
+  if (sched.size() >= 3) {
     abuf[1] = ws.get((size_t)batch * (mat >> 2));
     if (!abuf[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const double* alo = d_in;
   int64_t alo_mat = mat;
-  int64_t h = rows >> (steps - 1);
-  for (int l = 0; l < steps; l++, h <<= 1) {
-    ColArgs a{};
-    a.src_lo = alo; a.src_lo_mat = alo_mat;
-    a.src_hi = d_in + (h >> 1) * cols; a.src_hi_mat = mat;
-    if (l == steps - 1) { a.dst_lo = d_dst; a.dst_lo_mat = mat; }
-    else { a.dst_lo = abuf[(steps - l) & 1]; a.dst_lo_mat = h * cols; }
-    a.ld = cols; a.cols = cols; a.h = h; a.blocks = 1; a.L = L;
-    const int rc = col_step(ctx, st, a, f, batch, true, exact);
+  int64_t hcur = rows >> steps;
+  for (size_t i = 0; i < sched.size(); i++) {
+    const int k = sched[i];
+    const size_t e = sched.size() - 1 - i;   // launches still to come after this one
+    const int64_t htop = hcur << k;
+    double* dst = (e == 0) ? d_dst : abuf[(e & 1) ? 0 : 1];
+    const int64_t dst_mat = (e == 0) ? mat : htop * cols;
+    int rc;
+    if (k >= 2) {
+      ColFuseArgs a{};
+      a.src = alo; a.src_mat = alo_mat;
+      a.det = d_in; a.det_mat = mat;
+      a.dst = dst; a.dst_mat = dst_mat;
+      a.ld = cols; a.cols = cols; a.h = htop;
+      rc = run_fused(ctx, st, a, f, batch, L, k, true);
+    } else {
+      ColArgs a{};
+      a.src_lo = alo; a.src_lo_mat = alo_mat;
+      a.src_hi = d_in + (htop >> 1) * cols; a.src_hi_mat = mat;
+      a.dst_lo = dst; a.dst_lo_mat = dst_mat;
+      a.ld = cols; a.cols = cols; a.h = htop; a.blocks = 1; a.L = L;
+      rc = col_step(ctx, st, a, f, batch, true, exact);
+    }
     if (rc != JWC_OK) return rc;
-    alo = a.dst_lo;
-    alo_mat = a.dst_lo_mat;
+    alo = dst;
+    alo_mat = dst_mat;
+    hcur = htop;
   }
   (void)dev;
   return JWC_OK;

@@ -611,11 +611,20 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);
   if (steps == 0) return JWC_ERR_UNSUPPORTED;   // plain copy: the generic path handles it
-  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, steps, L, tree, false);
+  // short signals: levels below kDwtTailLen samples go to the warp-per-signal tail kernel (jwc_dwt_tail.cu)
+  const int lt = (!tree && ctx->tune.dwt_tail >= 0) ? dwt_tail_start(n, steps) : -1;
+  if (lt == 0) return dwt_tail_forward(ctx, st, d_in, n, d_out, n, (int)n, steps, batch, f, L);
+  const int plan_steps = lt > 0 ? lt : steps;
+  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, false);
   if (!plan.ok) return JWC_ERR_UNSUPPORTED;
   debug_dwt_plan("forward", plan, n, levels, L, tree);
   Scratch ws(st);
   const int npass = (int)plan.passes.size();
+  double* tail_a = nullptr;
+  if (lt > 0) {
+    tail_a = ws.get((size_t)batch * (n >> lt));
+    if (!tail_a) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+  }
   double* tmp[2] = {nullptr, nullptr};
   if (npass >= 2) {
     if (tree) {
@@ -644,7 +653,8 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     } else {
       a.nodes = 1;
       a.out = d_out; a.out_sig = n;                                  // D's at their final place
-      if (lastp) { a.aout = d_out; a.aout_sig = n; }
+      if (lastp && lt > 0) { a.aout = tail_a; a.aout_sig = n >> lt; }
+      else if (lastp) { a.aout = d_out; a.aout_sig = n; }
       else { a.aout = tmp[pi & 1]; a.aout_sig = n >> (p.l0 + p.k); }
     }
     const int64_t nblocks = (int64_t)a.tiles * a.nodes * batch;
@@ -657,6 +667,7 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     if (tree) { src = a.out; src_sig = n; }
     else { src = a.aout; src_sig = a.aout_sig; }
   }
+  if (lt > 0) return dwt_tail_forward(ctx, st, tail_a, n >> lt, d_out, n, (int)(n >> lt), steps - lt, batch, f, L);
   return JWC_OK;
 }
 
@@ -666,11 +677,22 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);   // the reverse loops undo exactly the forward's steps
   if (steps == 0) return JWC_ERR_UNSUPPORTED;
-  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, steps, L, tree, true);
+  const int lt = (!tree && ctx->tune.dwt_tail >= 0) ? dwt_tail_start(n, steps) : -1;
+  if (lt == 0) return dwt_tail_inverse(ctx, st, d_in, n, d_out, n, (int)n, steps, batch, f, L);
+  const int plan_steps = lt > 0 ? lt : steps;
+  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, true);
   if (!plan.ok) return JWC_ERR_UNSUPPORTED;
   debug_dwt_plan("inverse", plan, n, levels, L, tree);
   Scratch ws(st);
   const int npass = (int)plan.passes.size();
+  double* tail_a = nullptr;
+  if (lt > 0) {
+    // the tail rebuilds A at level lt from the deepest approximation and the detail blocks below it
+    tail_a = ws.get((size_t)batch * (n >> lt));
+    if (!tail_a) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+    const int rc = dwt_tail_inverse(ctx, st, d_in, n, tail_a, n >> lt, (int)(n >> lt), steps - lt, batch, f, L);
+    if (rc != JWC_OK) return rc;
+  }
   double* tmp[2] = {nullptr, nullptr};
   if (npass >= 2) {
     if (tree) {
@@ -685,6 +707,7 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   }
   const double* asrc = d_in;     // FWT: A_{steps} is the prefix of the coefficient array; WPT: the whole array
   int64_t asrc_sig = n;
+  if (lt > 0) { asrc = tail_a; asrc_sig = n >> lt; }
   for (int pi = npass - 1, step = 0; pi >= 0; --pi, ++step) {   // deepest pass first
     const DwtPass& p = plan.passes[pi];
     DwtPassArgs a{};

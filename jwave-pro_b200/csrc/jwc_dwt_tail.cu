@@ -1,0 +1,137 @@
+// jwc_dwt_tail.cu -- the deep end of the FWT pyramid for SHORT signals: one warp per signal, all remaining levels in
+// one launch.
+//
+// The tile kernels of jwc_dwt_fast.cu give every (signal, tile) its own CTA.  For a large batch of short signals
+// (rows of an image, analysis windows) the levels below ~256 samples are then a launch of one tiny CTA per signal --
+// 131 072 CTAs that each move a few hundred bytes and spend their time in block barriers (measured: 0.5 - 0.8 ms per
+// such pass on B200 while touching < 1 % of the data).  Here a warp keeps its signal's current approximation in its
+// own slice of shared memory and walks the remaining levels with __syncwarp only; 8 signals per CTA.
+//
+// Arithmetic: Wavelet.java:236-260 (analysis) and :277-303 (synthesis, gather form), level loops
+// FastWaveletTransform.java:85-99 / :133-151.  The block length h is a power of two, so `mod h` is a mask and blocks
+// shorter than the filter wrap several times without special cases.
+#include "jwc_internal.cuh"
+
+namespace jwc {
+
+namespace {
+
+constexpr int kWarps = 8;
+
+struct TailArgs {
+  const double* src;   // forward: A at the first tail level, signal stride src_sig; inverse: the coefficient array
+  double* dst;         // forward: the coefficient array (stride n); inverse: A at the top of the tail (stride dst_sig)
+  int64_t src_sig, dst_sig;
+  int64_t n;           // length of the whole signal = stride of the coefficient array
+  int64_t batch;
+  int h0;              // block length at the top of the tail (power of two, <= kDwtTailLen)
+  int nlev;            // levels done here
+  int L;
+};
+
+__global__ void __launch_bounds__(kWarps * 32) tail_fwd_kernel(const __grid_constant__ TailArgs a,
+                                                                const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t sig = (int64_t)blockIdx.x * kWarps + warp;
+  if (sig >= a.batch) return;   // warps are independent: no block-wide barrier below
+  double* cur = sm + (size_t)warp * (a.h0 + a.h0 / 2);
+  double* nxt = cur + a.h0;
+  const double* x = a.src + sig * a.src_sig;
+  for (int t = lane; t < a.h0; t += 32) cur[t] = x[t];
+  __syncwarp();
+  double* out = a.dst + sig * a.n;
+  int h = a.h0;
+  for (int lev = 0; lev < a.nlev; lev++) {
+    const int half = h >> 1, mask = h - 1;
+    const bool last = (lev == a.nlev - 1);
+    for (int i = lane; i < half; i += 32) {
+      double lo = 0.0, hi = 0.0;
+      for (int j = 0; j < a.L; j++) {
+        const double v = cur[(2 * i + j) & mask];
+        lo = fma(v, f.f0[j], lo);
+        hi = fma(v, f.f1[j], hi);
+      }
+      out[half + i] = hi;
+      if (last) out[i] = lo;
+      else nxt[i] = lo;
+    }
+    __syncwarp();
+    double* t = cur; cur = nxt; nxt = t;
+    h = half;
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32) tail_inv_kernel(const __grid_constant__ TailArgs a,
+                                                                const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t sig = (int64_t)blockIdx.x * kWarps + warp;
+  if (sig >= a.batch) return;
+  double* cur = sm + (size_t)warp * 2 * a.h0;   // [A (half) | D (half)] of the level being synthesised
+  double* nxt = cur + a.h0;
+  const double* c = a.src + sig * a.n;
+  double* dst = a.dst + sig * a.dst_sig;
+  int half = a.h0 >> a.nlev;                    // length of the deepest approximation (>= 1)
+  for (int t = lane; t < half; t += 32) cur[t] = c[t];
+  for (int lev = 0; lev < a.nlev; lev++) {
+    const int h = half << 1, mask = half - 1;
+    const bool last = (lev == a.nlev - 1);
+    for (int t = lane; t < half; t += 32) cur[half + t] = c[half + t];
+    __syncwarp();
+    for (int k = lane; k < h; k += 32) {
+      double acc = 0.0;
+      for (int j = k & 1; j < a.L; j += 2) {
+        const int i = ((k - j) >> 1) & mask;    // (2i + j) mod h == k
+        acc = fma(cur[half + i], f.f1[j], fma(cur[i], f.f0[j], acc));
+      }
+      if (last) dst[k] = acc;
+      else nxt[k] = acc;
+    }
+    __syncwarp();
+    double* t = cur; cur = nxt; nxt = t;
+    half = h;
+  }
+}
+
+int launch_tail(jwc_ctx* ctx, cudaStream_t st, const TailArgs& a, const FilterPair& f, bool inverse) {
+  const int64_t ctas = (a.batch + kWarps - 1) / kWarps;
+  if (ctas <= 0) return JWC_OK;
+  if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)kWarps * (inverse ? 2 * a.h0 : a.h0 + a.h0 / 2) * sizeof(double);
+  if (inverse) tail_inv_kernel<<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);
+  else         tail_fwd_kernel<<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+}  // namespace
+
+// First level of the pyramid that the tail kernels take over for a signal of length n with `steps` levels to do:
+// the first level whose block is <= kDwtTailLen samples.  -1: no tail (long signals keep their deep levels inside the
+// last tile pass; nothing to gain there).
+int dwt_tail_start(int64_t n, int steps) {
+  if (n > kDwtTailMaxN) return -1;
+  int l = 0;
+  while ((n >> l) > kDwtTailLen) l++;
+  return l < steps ? l : -1;
+}
+
+int dwt_tail_forward(jwc_ctx* ctx, cudaStream_t st, const double* src, int64_t src_sig, double* d_out, int64_t n,
+                     int h0, int nlev, int64_t batch, const FilterPair& f, int L) {
+  TailArgs a{};
+  a.src = src; a.src_sig = src_sig; a.dst = d_out; a.dst_sig = n; a.n = n; a.batch = batch; a.h0 = h0; a.nlev = nlev;
+  a.L = L;
+  return launch_tail(ctx, st, a, f, false);
+}
+
+int dwt_tail_inverse(jwc_ctx* ctx, cudaStream_t st, const double* d_in, int64_t n, double* dst, int64_t dst_sig, int h0,
+                     int nlev, int64_t batch, const FilterPair& f, int L) {
+  TailArgs a{};
+  a.src = d_in; a.src_sig = n; a.dst = dst; a.dst_sig = dst_sig; a.n = n; a.batch = batch; a.h0 = h0; a.nlev = nlev;
+  a.L = L;
+  return launch_tail(ctx, st, a, f, true);
+}
+
+}  // namespace jwc

@@ -49,6 +49,7 @@ struct Tuning {
   int dwt_smem = 0;
   int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
+  int dwt_tail = 0;         // warp-per-signal pyramid tail for short signals: 0 = auto, -1 = off
   int h2d_buffers = 0;      // host pipeline staging depth (1..4), 0 = auto
   int force_generic = 0;
   int l2_prefetch = 0;      // 0 = auto (one wave of CTAs ahead), -1 = off, > 0 = distance in CTAs
@@ -123,6 +124,15 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
 int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+// warp-per-signal deep end of the FWT pyramid for short signals (jwc_dwt_tail.cu)
+constexpr int kDwtTailLen = 256;        // block length at which the tail takes over
+constexpr int64_t kDwtTailMaxN = 16384; // longest signal that uses it
+int dwt_tail_start(int64_t n, int steps);
+int dwt_tail_forward(jwc_ctx* ctx, cudaStream_t st, const double* src, int64_t src_sig, double* d_out, int64_t n,
+                     int h0, int nlev, int64_t batch, const FilterPair& f, int L);
+int dwt_tail_inverse(jwc_ctx* ctx, cudaStream_t st, const double* d_in, int64_t n, double* dst, int64_t dst_sig, int h0,
+                     int nlev, int64_t batch, const FilterPair& f, int L);
+
 // column passes of the 2-D FWT / WPT (jwc_dwt2d.cu); d_src / d_in must not overlap the destination
 int dwt2d_column_steps(int64_t rows, int levels);
 int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_src, double* d_out,

@@ -281,6 +281,58 @@ class CudaWaveletPacketTransform(_CudaPyramidBase):
         self._name = "Wavelet Packet Transform"
 
 
+class ArrayView:
+    """transforms/EfficientMODWTTransform.java:88-117 -- read-only window on a backing array, no copy."""
+
+    def __init__(self, array, offset, length):
+        self._array, self._offset, self._length = array, offset, length
+
+    def get(self, index):
+        if index < 0 or index >= self._length:
+            raise IndexError("Index: %d, Length: %d" % (index, self._length))
+        return float(self._array[self._offset + index])
+
+    def length(self):
+        return self._length
+
+    def toArray(self):
+        return np.array(self._array[self._offset:self._offset + self._length])
+
+
+class MODWTCoefficients:
+    """transforms/EfficientMODWTTransform.java:28-86 -- the single-backing-array coefficient format
+    [W_1 | ... | W_J | V_J].  It is exactly the row layout the device writes (and what forward(double[], level)
+    returns, MODWTTransform.java:406-416), so wrapping a GPU result costs nothing."""
+
+    def __init__(self, backingArray, signalLength, levels):
+        self._backing = np.asarray(backingArray, dtype=np.float64).reshape(-1)
+        if self._backing.size != (levels + 1) * signalLength:
+            raise IllegalArgumentException("backing array length %d != (levels + 1) * signalLength"
+                                           % self._backing.size)
+        self._n, self._levels = signalLength, levels
+
+    def getDetails(self, level):
+        if level < 1 or level > self._levels:
+            raise IllegalArgumentException("Invalid level: %d" % level)
+        off = (level - 1) * self._n
+        return np.array(self._backing[off:off + self._n])
+
+    def getApproximation(self):
+        off = self._levels * self._n
+        return np.array(self._backing[off:off + self._n])
+
+    def getView(self, level):
+        if level < 1 or level > self._levels + 1:
+            raise IllegalArgumentException("Invalid level: %d" % level)
+        return ArrayView(self._backing, (level - 1) * self._n, self._n)
+
+    def getTotalSize(self):
+        return int(self._backing.size)
+
+    def backingArray(self):
+        return self._backing
+
+
 class CudaMODWTTransform(WaveletTransform):
     """Drop-in for transforms/MODWTTransform.java."""
 
@@ -422,6 +474,17 @@ class CudaMODWTTransform(WaveletTransform):
                 raise JWaveFailure("MODWTTransform#reverse - Coefficient array length does not match expected size "
                                    "for given level")
         return self.inverseMODWT(_as_f64(arrHilb).reshape(levels + 1, N))
+
+    def forwardMODWTCoefficients(self, data, maxLevel, flags=0):
+        """The result of forwardMODWT in the MODWTCoefficients wire format (one backing array, level views).  Rows
+        carry forwardMODWT's meaning (W_j = h~ conv V, V_J last); the reference's forwardMODWTEfficient
+        (EfficientMODWTTransform.java:151-170) labels the two branches the other way round and is covered by none of
+        its tests, so it is not reproduced."""
+        c = self.forwardMODWT(data, maxLevel, flags=flags)
+        return MODWTCoefficients(c.reshape(-1), c.shape[1], maxLevel)
+
+    def inverseMODWTCoefficients(self, coeffs, flags=0):
+        return self.inverseMODWT(coeffs.backingArray().reshape(coeffs._levels + 1, coeffs._n), flags=flags)
 
     # ---- batched host-buffer entry points ------------------------------------------------------------------
     def forwardMODWTBatch(self, matTime, maxLevel, flags=0, out=None):

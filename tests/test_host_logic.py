@@ -98,3 +98,24 @@ def test_getters_return_copies(jw):
     assert w.getScalingDeComposition()[0] != 99.0
     assert w.getMotherWavelength() == 16 and w.getTransformWavelength() == 2
     assert jw.wavelets.create("Daubechies 20").getMotherWavelength() == 40
+
+
+def test_modwt_coefficients_wire_format(jw):
+    """EfficientMODWTTransform.java:28-117: one backing array [W_1|...|W_J|V_J], level views without copies."""
+    n, J = 8, 2
+    backing = np.arange((J + 1) * n, dtype=np.float64)
+    c = jw.MODWTCoefficients(backing, n, J)
+    assert c.getTotalSize() == 24
+    assert np.array_equal(c.getDetails(1), backing[:8]) and np.array_equal(c.getDetails(2), backing[8:16])
+    assert np.array_equal(c.getApproximation(), backing[16:])
+    v = c.getView(3)
+    assert v.length() == 8 and v.get(0) == 16.0 and np.array_equal(v.toArray(), backing[16:])
+    with pytest.raises(IndexError):
+        v.get(8)
+    for bad in (0, 3):
+        with pytest.raises(jw.IllegalArgumentException, match="Invalid level"):
+            c.getDetails(bad)
+    with pytest.raises(jw.IllegalArgumentException, match="Invalid level"):
+        c.getView(4)
+    backing[16] = -1.0          # a view reads the backing array, a copy does not
+    assert v.get(0) == -1.0

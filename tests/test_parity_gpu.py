@@ -464,7 +464,12 @@ def test_modwt_single_series_split_over_devices(jw, oracle, cls, n, J):
     ("Daubechies20", 16, 32, 4, 5, 2),      # filter (40 taps) longer than both dimensions
     ("Symlet10", 2, 4, 1, 2, 5),
     ("Daubechies2", 1, 64, 0, 6, 2),        # a single row: the column pass has nothing to do
-    ("Daubechies3", 4096, 48 * 0 + 32, 12, 5, 1),
+    ("Daubechies3", 4096, 32, 12, 5, 1),
+    ("Haar1", 512, 8, 9, 3, 3),             # fused column launches on a partial 32-column strip
+    ("Daubechies2", 1024, 2, 10, 1, 2),
+    ("Symlet10", 256, 96 // 3, 5, 2, 2),    # L = 20: two fused levels at a time
+    ("Daubechies5", 128, 64, 7, 6, 2),      # smallest height the fused launches take
+    ("Daubechies10", 2048, 64, 2, 6, 1),
 ])
 def test_2d_matches_oracle(jw, gpu_ctx, oracle, kind, cls, rows, cols, lvl_m, lvl_n, batch):
     w = jw.wavelets.create(cls)
@@ -505,3 +510,24 @@ def test_2d_java_overloads_and_errors(jw, gpu_ctx, oracle):
     buf = np.zeros(64)
     rc = lib.jwc_fwt2d_forward(gpu_ctx.handle, buf.ctypes.data, buf.ctypes.data, 1, 6, 8, 1, 1, f, f, 2, 0)
     assert rc == -1 and b"2^p" in lib.jwc_last_error()
+
+
+def test_modwt_coefficients_format_from_device_layout(jw, gpu_ctx, oracle):
+    """the device's row layout IS the MODWTCoefficients backing array and the flat forward() format."""
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaMODWTTransform(w)
+    x = splitmix_uniform(31, (1024,))
+    g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+    ref = oracle.modwt_forward(x, 3, g, h)
+    c = t.forwardMODWTCoefficients(x, 3)
+    assert c.getTotalSize() == 4 * 1024
+    for lvl in (1, 2, 3):
+        assert _maxerr(c.getDetails(lvl), ref[lvl - 1], x) <= TOL
+        assert _maxerr(c.getView(lvl).toArray(), ref[lvl - 1], x) <= TOL
+    assert _maxerr(c.getApproximation(), ref[3], x) <= TOL
+    assert np.array_equal(c.backingArray(), t.forward(x, 3))
+    assert _maxerr(t.inverseMODWTCoefficients(c), x, x) <= PR_TOL
+    assert _maxerr(t.reverse(c.backingArray(), 3), x, x) <= PR_TOL
+    # the level-less reverse searches the SMALLEST 2^p N with total/N - 1 <= log2 N (MODWTTransform.java:888-897):
+    # for 4 x 1024 coefficients that is N = 512, J = 7, not the shape that produced them -- same as the reference
+    assert len(t.reverse(c.backingArray())) == 512
