@@ -35,22 +35,30 @@ struct ColArgs {
   int64_t blocks;   // blocks per matrix (1 for the pyramid)
   int64_t tiles;    // row tiles per block
   int64_t strips;   // column strips
+  int lg_strips, lg_tiles, lg_blocks;   // all three counts are powers of two (rows and cols are)
   int L;
 };
+
+inline int ilog2_exact(int64_t v) {   // log2 of a power of two, -1 otherwise
+  if (v < 1 || (v & (v - 1))) return -1;
+  int p = 0;
+  while (((int64_t)1 << p) < v) p++;
+  return p;
+}
 
 struct Where {
   int64_t c, t, p, b;   // column, row tile, block, matrix
 };
 __device__ __forceinline__ Where locate(const ColArgs& a) {
   Where w;
-  int64_t id = blockIdx.x;
-  const int64_t s = id % a.strips;
-  id /= a.strips;
-  w.t = id % a.tiles;
-  id /= a.tiles;
-  w.p = id % a.blocks;
-  w.b = id / a.blocks;
-  w.c = s * kStrip + threadIdx.x;
+  unsigned id = blockIdx.x;
+  const unsigned s = id & ((1u << a.lg_strips) - 1);
+  id >>= a.lg_strips;
+  w.t = id & ((1u << a.lg_tiles) - 1);
+  id >>= a.lg_tiles;
+  w.p = id & ((1u << a.lg_blocks) - 1);
+  w.b = id >> a.lg_blocks;
+  w.c = (int64_t)s * kStrip + threadIdx.x;
   return w;
 }
 
@@ -218,8 +226,9 @@ struct ColFuseArgs {
   double* out;          // forward: the coefficient matrix receiving the detail rows
   int64_t src_mat, det_mat, dst_mat, out_mat;
   int64_t ld, cols;
-  int64_t h;            // rows at the TOP of this launch (input height forward, output height inverse)
+  int64_t h;            // rows at the TOP of this launch (input height forward, output height inverse), 2^p
   int64_t tiles, strips;
+  int lg_strips, lg_tiles;
 };
 
 __host__ __device__ constexpr int fwd_halo(int L, int m) { return (L - 2) * ((1 << m) - 1); }
@@ -239,18 +248,18 @@ __global__ void __launch_bounds__(kStrip* kGroups) col_ana_fused_kernel(const __
   constexpr int NA = T + fwd_halo(L, K);
   double* A = sm;
   double* B = sm + (NA + kPad) * kStrip;
-  int64_t id = blockIdx.x;
-  const int64_t strip = id % a.strips;
-  id /= a.strips;
-  const int64_t r0 = (id % a.tiles) * T, b = id / a.tiles;
-  const int64_t c0 = strip * kStrip;
+  unsigned id = blockIdx.x;
+  const unsigned strip = id & ((1u << a.lg_strips) - 1);
+  id >>= a.lg_strips;
+  const int64_t r0 = (int64_t)(id & ((1u << a.lg_tiles) - 1)) * T, b = id >> a.lg_tiles;
+  const int64_t c0 = (int64_t)strip * kStrip;
   const int ncol = (int)((a.cols - c0 < kStrip) ? a.cols - c0 : kStrip);
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kStrip + tx;
   {
     const double* src = a.src + b * a.src_mat + c0;
     for (int idx = tid; idx < NA * (kStrip / 2); idx += kStrip * kGroups) {
       const int row = idx / (kStrip / 2), seg = idx % (kStrip / 2);
-      if (2 * seg < ncol) ptx::cp_async16(&A[row * kStrip + 2 * seg], src + ((r0 + row) % a.h) * a.ld + 2 * seg);
+      if (2 * seg < ncol) ptx::cp_async16(&A[row * kStrip + 2 * seg], src + ((r0 + row) & (a.h - 1)) * a.ld + 2 * seg);
     }
     ptx::cp_async_commit_wait_all();
   }
@@ -268,21 +277,31 @@ __global__ void __launch_bounds__(kStrip* kGroups) col_ana_fused_kernel(const __
       double win[W];
 #pragma unroll
       for (int t = 0; t < W; t++) win[t] = in[(2 * i0 + t) * kStrip + tx];
+      // kRun independent accumulator chains; rows past n_lo read the slack rows and are dropped at the store
+      double sl[kRun];
+#pragma unroll
+      for (int q = 0; q < kRun; q++) sl[q] = 0.0;
+#pragma unroll
+      for (int m = 0; m < L; m++)
+#pragma unroll
+        for (int q = 0; q < kRun; q++) sl[q] = fma(win[2 * q + m], f.f0[m], sl[q]);
 #pragma unroll
       for (int q = 0; q < kRun; q++) {
         const int i = i0 + q;
-        if (i < n_lo) {
-          double sl = 0.0;
+        if (j < K) { if (i < n_lo) nxt[i * kStrip + tx] = sl[q]; }
+        else if (tx < ncol) g_lo[(int64_t)i * a.ld] = sl[q];      // n_lo = T >> K is a multiple of kRun
+      }
+      if (i0 < n_hi) {   // n_hi is a multiple of kRun: the whole run is inside or outside
+        double sh[kRun];
 #pragma unroll
-          for (int m = 0; m < L; m++) sl = fma(win[2 * q + m], f.f0[m], sl);
-          if (j < K) nxt[i * kStrip + tx] = sl;
-          else if (tx < ncol) g_lo[(int64_t)i * a.ld] = sl;
-          if (i < n_hi) {
-            double sh = 0.0;
+        for (int q = 0; q < kRun; q++) sh[q] = 0.0;
 #pragma unroll
-            for (int m = 0; m < L; m++) sh = fma(win[2 * q + m], f.f1[m], sh);
-            if (tx < ncol) g_hi[(int64_t)i * a.ld] = sh;
-          }
+        for (int m = 0; m < L; m++)
+#pragma unroll
+          for (int q = 0; q < kRun; q++) sh[q] = fma(win[2 * q + m], f.f1[m], sh[q]);
+        if (tx < ncol) {
+#pragma unroll
+          for (int q = 0; q < kRun; q++) g_hi[(int64_t)(i0 + q) * a.ld] = sh[q];
         }
       }
     }
@@ -302,11 +321,11 @@ __global__ void __launch_bounds__(kStrip* kGroups) col_syn_fused_kernel(const __
   constexpr int N1 = (T >> 1) + inv_halo(L, 1, K);   // the largest intermediate level
   double* X = sm;
   double* Y = sm + (N1 + kPad) * kStrip;
-  int64_t id = blockIdx.x;
-  const int64_t strip = id % a.strips;
-  id /= a.strips;
-  const int64_t r0 = (id % a.tiles) * T, b = id / a.tiles;
-  const int64_t c0 = strip * kStrip;
+  unsigned id = blockIdx.x;
+  const unsigned strip = id & ((1u << a.lg_strips) - 1);
+  id >>= a.lg_strips;
+  const int64_t r0 = (int64_t)(id & ((1u << a.lg_tiles) - 1)) * T, b = id >> a.lg_tiles;
+  const int64_t c0 = (int64_t)strip * kStrip;
   const int ncol = (int)((a.cols - c0 < kStrip) ? a.cols - c0 : kStrip);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t cx = c0 + (tx < ncol ? tx : 0);   // idle lanes of a partial strip shadow column c0 (loads only)
@@ -326,8 +345,7 @@ __global__ void __launch_bounds__(kStrip* kGroups) col_syn_fused_kernel(const __
     for (int u0 = ty * kRun; u0 < n_out / 2; u0 += kGroups * kRun) {
       constexpr int W = kRun + M - 1;
       double wl[W], wh[W];
-      int64_t gr = ((r0 >> s) - Gs + off + u0) % half;
-      if (gr < 0) gr += half;
+      int64_t gr = ((r0 >> s) - Gs + off + u0) & (half - 1);   // half is a power of two: two's-complement mask = mod
 #pragma unroll
       for (int t = 0; t < W; t++) {
         wh[t] = g_hi[gr * a.ld];
@@ -335,23 +353,27 @@ __global__ void __launch_bounds__(kStrip* kGroups) col_syn_fused_kernel(const __
         else wl[t] = s_lo[(off + u0 + t) * kStrip + tx];
         if (++gr == half) gr = 0;
       }
+      double e[kRun], o[kRun];
+#pragma unroll
+      for (int u = 0; u < kRun; u++) e[u] = o[u] = 0.0;
+#pragma unroll
+      for (int m = M - 1; m >= 0; m--)
+#pragma unroll
+        for (int u = 0; u < kRun; u++) {
+          const double cl = wl[u - m + M - 1], ch = wh[u - m + M - 1];
+          e[u] = fma(ch, f.f1[2 * m], fma(cl, f.f0[2 * m], e[u]));
+          o[u] = fma(ch, f.f1[2 * m + 1], fma(cl, f.f0[2 * m + 1], o[u]));
+        }
 #pragma unroll
       for (int u = 0; u < kRun; u++) {
         if (u0 + u < n_out / 2) {
-          double e = 0.0, o = 0.0;
-#pragma unroll
-          for (int m = M - 1; m >= 0; m--) {
-            const double cl = wl[u - m + M - 1], ch = wh[u - m + M - 1];
-            e = fma(ch, f.f1[2 * m], fma(cl, f.f0[2 * m], e));
-            o = fma(ch, f.f1[2 * m + 1], fma(cl, f.f0[2 * m + 1], o));
-          }
           const int row = 2 * (u0 + u);
           if (s > 1) {
-            s_out[row * kStrip + tx] = e;
-            s_out[(row + 1) * kStrip + tx] = o;
+            s_out[row * kStrip + tx] = e[u];
+            s_out[(row + 1) * kStrip + tx] = o[u];
           } else if (tx < ncol) {
-            g_out[(int64_t)row * a.ld] = e;
-            g_out[(int64_t)(row + 1) * a.ld] = o;
+            g_out[(int64_t)row * a.ld] = e[u];
+            g_out[(int64_t)(row + 1) * a.ld] = o[u];
           }
         }
       }
@@ -382,6 +404,9 @@ int launch_fused(jwc_ctx* ctx, cudaStream_t st, ColFuseArgs a, const FilterPair&
   constexpr int T = FuseCfg<L>::T;
   a.strips = (a.cols + kStrip - 1) / kStrip;
   a.tiles = a.h / T;
+  a.lg_strips = ilog2_exact(a.strips);
+  a.lg_tiles = ilog2_exact(a.tiles);
+  if (a.lg_strips < 0 || a.lg_tiles < 0) { set_error("2-D shape is not a power of two"); return JWC_ERR_INVALID; }
   const int64_t ctas = a.strips * a.tiles * batch;
   if (ctas > 0x7fffffffLL) { set_error("2-D transform too large for one launch"); return JWC_ERR_UNSUPPORTED; }
   const dim3 grid((unsigned)ctas), block(kStrip, kGroups);
@@ -457,6 +482,10 @@ int col_step(jwc_ctx* ctx, cudaStream_t st, ColArgs a, const FilterPair& f, int6
   const int64_t half = a.h >> 1;
   a.strips = (a.cols + kStrip - 1) / kStrip;
   a.tiles = (half + kGroups * kRun - 1) / (kGroups * kRun);
+  a.lg_strips = ilog2_exact(a.strips);
+  a.lg_tiles = ilog2_exact(a.tiles);
+  a.lg_blocks = ilog2_exact(a.blocks);
+  if (a.lg_strips < 0 || a.lg_tiles < 0 || a.lg_blocks < 0) { set_error("2-D shape is not a power of two"); return JWC_ERR_INVALID; }
   const int64_t ctas = a.strips * a.tiles * a.blocks * batch;
   if (ctas <= 0) return JWC_OK;
   if (ctas > 0x7fffffffLL) { set_error("2-D transform too large for one launch"); return JWC_ERR_UNSUPPORTED; }

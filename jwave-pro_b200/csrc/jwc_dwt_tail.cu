@@ -5,7 +5,7 @@
 // (rows of an image, analysis windows) the levels below ~256 samples are then a launch of one tiny CTA per signal --
 // 131 072 CTAs that each move a few hundred bytes and spend their time in block barriers (measured: 0.5 - 0.8 ms per
 // such pass on B200 while touching < 1 % of the data).  Here a warp keeps its signal's current approximation in its
-// own slice of shared memory and walks the remaining levels with __syncwarp only; 8 signals per CTA.
+// own slice of shared memory and walks the remaining levels with __syncwarp only; 4 signals per CTA.
 //
 // Arithmetic: Wavelet.java:236-260 (analysis) and :277-303 (synthesis, gather form), level loops
 // FastWaveletTransform.java:85-99 / :133-151.  The block length h is a power of two, so `mod h` is a mask and blocks
@@ -16,7 +16,7 @@ namespace jwc {
 
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;
 
 struct TailArgs {
   const double* src;   // forward: A at the first tail level, signal stride src_sig; inverse: the coefficient array
@@ -68,27 +68,32 @@ __global__ void __launch_bounds__(kWarps * 32) tail_inv_kernel(const __grid_cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t sig = (int64_t)blockIdx.x * kWarps + warp;
   if (sig >= a.batch) return;
-  double* cur = sm + (size_t)warp * 2 * a.h0;   // [A (half) | D (half)] of the level being synthesised
-  double* nxt = cur + a.h0;
+  // the coefficients of all tail levels are one contiguous prefix [A_deep | D_deep | ... | D_top] of the signal's
+  // array: fetch it once (one global-memory latency for the whole tail), then ping-pong the approximations
+  double* coef = sm + (size_t)warp * 2 * a.h0;
+  double* cur = coef + a.h0;
+  double* nxt = cur + a.h0 / 2;
   const double* c = a.src + sig * a.n;
   double* dst = a.dst + sig * a.dst_sig;
+  for (int t = lane; t < a.h0; t += 32) coef[t] = c[t];
+  __syncwarp();
   int half = a.h0 >> a.nlev;                    // length of the deepest approximation (>= 1)
-  for (int t = lane; t < half; t += 32) cur[t] = c[t];
+  const double* lo = coef;
   for (int lev = 0; lev < a.nlev; lev++) {
     const int h = half << 1, mask = half - 1;
     const bool last = (lev == a.nlev - 1);
-    for (int t = lane; t < half; t += 32) cur[half + t] = c[half + t];
-    __syncwarp();
+    const double* hi = coef + half;
     for (int k = lane; k < h; k += 32) {
       double acc = 0.0;
       for (int j = k & 1; j < a.L; j += 2) {
         const int i = ((k - j) >> 1) & mask;    // (2i + j) mod h == k
-        acc = fma(cur[half + i], f.f1[j], fma(cur[i], f.f0[j], acc));
+        acc = fma(hi[i], f.f1[j], fma(lo[i], f.f0[j], acc));
       }
       if (last) dst[k] = acc;
       else nxt[k] = acc;
     }
     __syncwarp();
+    lo = nxt;
     double* t = cur; cur = nxt; nxt = t;
     half = h;
   }

@@ -125,7 +125,7 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
 int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
 // warp-per-signal deep end of the FWT pyramid for short signals (jwc_dwt_tail.cu)
-constexpr int kDwtTailLen = 256;        // block length at which the tail takes over
+constexpr int kDwtTailLen = 512;        // block length at which the tail takes over
 constexpr int64_t kDwtTailMaxN = 16384; // longest signal that uses it
 int dwt_tail_start(int64_t n, int steps);
 int dwt_tail_forward(jwc_ctx* ctx, cudaStream_t st, const double* src, int64_t src_sig, double* d_out, int64_t n,
