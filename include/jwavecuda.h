@@ -175,6 +175,29 @@ JWC_API int jwc_wpt2d_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const do
                                   int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* lo,
                                   const double* hi, int L, unsigned flags);
 
+/* ---- arbitrary-length FWT / WPT: Ancient-Egyptian decomposition -----------------------------------------
+ * transforms/AncientEgyptianDecomposition.java:97-181 with tools/MathToolKit.java:57-84 decompose(): a signal of any
+ * length n >= 1 is cut into blocks of descending powers of two (42 = 32 | 8 | 2); every block is transformed on its own
+ * by the wrapped transform at FULL depth (forward(double[]) of a 2^p block = p levels; a block of length 1 is copied)
+ * and written back at its position.  in, out: [batch][n]; every block is one batched launch sequence over all signals
+ * (row stride n), nothing is gathered or copied.  lo/hi as for the 1-D calls. */
+JWC_API int jwc_fwt_aed_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n,
+                                const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt_aed_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n,
+                                const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_aed_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n,
+                                const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_aed_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n,
+                                const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt_aed_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                    int64_t batch, int64_t n, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt_aed_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                    int64_t batch, int64_t n, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_aed_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                    int64_t batch, int64_t n, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_aed_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                    int64_t batch, int64_t n, const double* lo, const double* hi, int L, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

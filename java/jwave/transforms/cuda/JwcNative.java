@@ -34,6 +34,10 @@ public final class JwcNative {
   private static final String[] NAMES_2D = {
       "jwc_fwt2d_forward", "jwc_fwt2d_inverse", "jwc_wpt2d_forward", "jwc_wpt2d_inverse" };
   public static final int FWT2D_FORWARD = 0, FWT2D_INVERSE = 1, WPT2D_FORWARD = 2, WPT2D_INVERSE = 3;
+  private static final MethodHandle[] TRANSFORMS_AED = new MethodHandle[4];
+  private static final String[] NAMES_AED = {
+      "jwc_fwt_aed_forward", "jwc_fwt_aed_inverse", "jwc_wpt_aed_forward", "jwc_wpt_aed_inverse" };
+  public static final int FWT_AED_FORWARD = 0, FWT_AED_INVERSE = 1, WPT_AED_FORWARD = 2, WPT_AED_INVERSE = 3;
   private static final String[] NAMES = {
       "jwc_modwt_forward", "jwc_modwt_inverse", "jwc_fwt_forward", "jwc_fwt_inverse", "jwc_wpt_forward",
       "jwc_wpt_inverse" };
@@ -60,6 +64,11 @@ public final class JwcNative {
     FunctionDescriptor t2 = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG,
         JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT);
     for (int i = 0; i < NAMES_2D.length; i++) TRANSFORMS_2D[i] = handle(NAMES_2D[i], t2);
+    // int f(jwc_ctx*, const double* in, double* out, int64 batch, int64 n, const double* lo, const double* hi, int L,
+    //       unsigned flags)   -- n arbitrary (Ancient-Egyptian blocks)
+    FunctionDescriptor ta = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS,
+        ADDRESS, JAVA_INT, JAVA_INT);
+    for (int i = 0; i < NAMES_AED.length; i++) TRANSFORMS_AED[i] = handle(NAMES_AED[i], ta);
   }
 
   private static MethodHandle handle(String name, FunctionDescriptor fd) {
@@ -168,6 +177,30 @@ public final class JwcNative {
       for (int i = 0; i < rows; i++)
         MemorySegment.copy(so, JAVA_DOUBLE, (long) i * cols * Double.BYTES, out[i], 0, cols);
       return out;
+    }
+  }
+
+  /** Arbitrary-length batch [batch][n] through the Ancient-Egyptian block decomposition, one native call. */
+  public static void runAed(int which, MemorySegment ctx, MemorySegment in, MemorySegment out, long batch, long n,
+      double[] f0, double[] f1, int flags) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment s0 = a.allocateArray(JAVA_DOUBLE, f0);
+      MemorySegment s1 = a.allocateArray(JAVA_DOUBLE, f1);
+      int rc = (int) TRANSFORMS_AED[which].invokeExact(ctx, in, out, batch, n, s0, s1, f0.length, flags);
+      if (rc != 0) throw new IllegalStateException(NAMES_AED[which] + " failed (" + rc + "): " + lastError());
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  public static double[] runAed(int which, MemorySegment ctx, double[] in, double[] f0, double[] f1, int flags) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment si = a.allocateArray(JAVA_DOUBLE, in);
+      MemorySegment so = a.allocateArray(JAVA_DOUBLE, in.length);
+      runAed(which, ctx, si, so, 1, in.length, f0, f1, flags);
+      return so.toArray(JAVA_DOUBLE);
     }
   }
 }

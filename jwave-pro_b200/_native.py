@@ -23,13 +23,15 @@ MAX_TAPS = 64
 
 # every exported symbol of include/jwavecuda.h (tests/test_abi.py checks the .so against this list and the header)
 _TRANSFORMS = ["modwt_forward", "modwt_inverse", "fwt_forward", "fwt_inverse", "wpt_forward", "wpt_inverse"]
+_TRANSFORMS_AED = ["fwt_aed_forward", "fwt_aed_inverse", "wpt_aed_forward", "wpt_aed_inverse"]
 _TRANSFORMS_2D = ["fwt2d_forward", "fwt2d_inverse", "wpt2d_forward", "wpt2d_inverse"]
 SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal", "jwc_last_error", "jwc_version",
             "jwc_launch_count", "jwc_set_tuning", "jwc_get_tuning", "jwc_alloc_pinned", "jwc_free_pinned",
             "jwc_alloc_device", "jwc_free_device", "jwc_copy_to_device", "jwc_copy_to_host", "jwc_synchronize"]
            + ["jwc_" + t for t in _TRANSFORMS] + ["jwc_" + t + "_dev" for t in _TRANSFORMS]
            + ["jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"]
-           + ["jwc_" + t for t in _TRANSFORMS_2D] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_2D])
+           + ["jwc_" + t for t in _TRANSFORMS_2D] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_2D]
+           + ["jwc_" + t for t in _TRANSFORMS_AED] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_AED])
 
 _lib = None
 _lock = threading.Lock()
@@ -87,6 +89,13 @@ def load():
             fn.restype = _int
             fn = getattr(lib, "jwc_" + t + "_dev")
             fn.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _dp, _dp, _int, _u32]
+            fn.restype = _int
+        for t in _TRANSFORMS_AED:
+            fn = getattr(lib, "jwc_" + t)
+            fn.argtypes = [_vp, _vp, _vp, _i64, _i64, _dp, _dp, _int, _u32]
+            fn.restype = _int
+            fn = getattr(lib, "jwc_" + t + "_dev")
+            fn.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _dp, _dp, _int, _u32]
             fn.restype = _int
         for t in _TRANSFORMS_2D:
             fn = getattr(lib, "jwc_" + t)

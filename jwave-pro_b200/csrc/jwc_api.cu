@@ -39,6 +39,7 @@ enum class Op { ModwtFwd, ModwtInv, FwtFwd, FwtInv, WptFwd, WptInv };
 struct Dim2 {
   int64_t rows = 0;
   int lvl_m = 0;
+  bool aed = false;   // Ancient-Egyptian decomposition of arbitrary-length signals (levels ignored: full depth per block)
 };
 
 bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -64,7 +65,10 @@ int validate(Op op, const void* in, const void* out, int64_t batch, int64_t n, i
   JWC_REQUIRE(n >= 1, "signal length must be >= 1 (got %lld)", (long long)n);
   JWC_REQUIRE(n < ((int64_t)1 << 40), "signal length %lld too large", (long long)n);
   JWC_REQUIRE(L >= 1 && L <= JWC_MAX_TAPS, "filter length %d outside 1..%d", L, JWC_MAX_TAPS);
-  if (op == Op::ModwtFwd || op == Op::ModwtInv) {
+  if (d2.aed) {
+    JWC_REQUIRE(op != Op::ModwtFwd && op != Op::ModwtInv, "no Ancient-Egyptian MODWT");
+    JWC_REQUIRE(n < ((int64_t)1 << 31), "signal length %lld too large", (long long)n);
+  } else if (op == Op::ModwtFwd || op == Op::ModwtInv) {
     JWC_REQUIRE(levels >= 1 && levels <= 40, "MODWT level %d out of range", levels);
   } else {
     JWC_REQUIRE(is_pow2(n), "given array length is not 2^p (got %lld)", (long long)n);
@@ -86,6 +90,32 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
                const Dim2& d2 = Dim2()) {
   if (batch == 0) return JWC_OK;
   const bool exact = (flags & JWC_FLAG_EXACT) != 0;
+  if (d2.aed) {
+    // transforms/AncientEgyptianDecomposition.java:97-181 + tools/MathToolKit.java:57-84: n = sum of descending powers
+    // of two; every block [off, off + 2^p) of every signal goes through the wrapped transform at full depth (p levels)
+    // on its own.  Here each block is ONE batched launch sequence over all signals (row stride n), no copies; a block
+    // of length 1 is the identity.
+    const bool tree = (op == Op::WptFwd || op == Op::WptInv);
+    const bool fwd = (op == Op::FwtFwd || op == Op::WptFwd);
+    const bool generic = exact || (flags & JWC_FLAG_FORCE_GENERIC) != 0 || ctx->tune.force_generic != 0;
+    int64_t off = 0;
+    for (int p = 30; p >= 0; p--) {
+      const int64_t len = (int64_t)1 << p;
+      if (!(n & len)) continue;
+      const double* src = d_in + off;
+      double* dst = d_out + off;
+      int rc = JWC_ERR_UNSUPPORTED;
+      if (!generic && p > 0)
+        rc = fwd ? fast_dwt_forward(ctx, dev, st, src, dst, batch, len, p, fp, L, tree, n)
+                 : fast_dwt_inverse(ctx, dev, st, src, dst, batch, len, p, fp, L, tree, n);
+      if (rc == JWC_ERR_UNSUPPORTED)
+        rc = fwd ? generic_dwt_forward(ctx, dev, st, src, dst, batch, len, p, fp, L, tree, exact, n)
+                 : generic_dwt_inverse(ctx, dev, st, src, dst, batch, len, p, fp, L, tree, exact, n);
+      if (rc != JWC_OK) return rc;
+      off += len;
+    }
+    return JWC_OK;
+  }
   if (d2.rows != 0) {
     // BasicTransform.java:361-399 forward: rows (lvlN) then columns (lvlM); :436-474 reverse: columns, then rows.
     const bool tree = (op == Op::WptFwd || op == Op::WptInv);
@@ -626,6 +656,26 @@ JWC_DEFINE(wpt_inverse, Op::WptInv)
     d2.lvl_m = lvl_m;                                                                                               \
     return run_dev(ctx, slot, stream, OP, d_in, d_out, batch, cols, lvl_n, f0, f1, L, flags, d2);                   \
   }
+
+#define JWC_DEFINE_AED(name, OP)                                                                                    \
+  JWC_API int jwc_##name(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, const double* f0,   \
+                         const double* f1, int L, unsigned flags) {                                                 \
+    Dim2 d2;                                                                                                        \
+    d2.aed = true;                                                                                                  \
+    return run_host(ctx, OP, in, out, batch, n, 0, f0, f1, L, flags, d2);                                           \
+  }                                                                                                                 \
+  JWC_API int jwc_##name##_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,             \
+                               int64_t batch, int64_t n, const double* f0, const double* f1, int L,                 \
+                               unsigned flags) {                                                                    \
+    Dim2 d2;                                                                                                        \
+    d2.aed = true;                                                                                                  \
+    return run_dev(ctx, slot, stream, OP, d_in, d_out, batch, n, 0, f0, f1, L, flags, d2);                          \
+  }
+
+JWC_DEFINE_AED(fwt_aed_forward, Op::FwtFwd)
+JWC_DEFINE_AED(fwt_aed_inverse, Op::FwtInv)
+JWC_DEFINE_AED(wpt_aed_forward, Op::WptFwd)
+JWC_DEFINE_AED(wpt_aed_inverse, Op::WptInv)
 
 JWC_DEFINE_2D(fwt2d_forward, Op::FwtFwd)
 JWC_DEFINE_2D(fwt2d_inverse, Op::FwtInv)

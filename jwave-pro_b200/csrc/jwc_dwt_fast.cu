@@ -589,10 +589,10 @@ int dwt_prefetch_distance(jwc_ctx* ctx, const DeviceSlot& dev, size_t smem, int 
 }
 
 DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const void* p1, int64_t n, int steps, int L,
-                  bool tree, bool inverse) {
+                  bool tree, bool inverse, int64_t ld) {
   DwtPlanInput pin{};
   pin.n = n; pin.levels = steps; pin.L = L; pin.tree = tree; pin.inverse = inverse;
-  pin.aligned16 = ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
+  pin.aligned16 = ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0 && (ld & 1) == 0;
   pin.smem_budget = ctx->tune.dwt_smem > 0 ? ctx->tune.dwt_smem : 45000;
   if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
   pin.tile_override = ctx->tune.dwt_tile; pin.group_override = ctx->tune.dwt_group;
@@ -606,16 +606,17 @@ DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const voi
 }  // namespace
 
 int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree) {
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, int64_t ld) {
+  if (ld <= 0) ld = n;
   if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);
   if (steps == 0) return JWC_ERR_UNSUPPORTED;   // plain copy: the generic path handles it
   // short signals: levels below kDwtTailLen samples go to the warp-per-signal tail kernel (jwc_dwt_tail.cu)
   const int lt = (!tree && ctx->tune.dwt_tail >= 0) ? dwt_tail_start(n, steps) : -1;
-  if (lt == 0) return dwt_tail_forward(ctx, st, d_in, n, d_out, n, (int)n, steps, batch, f, L);
+  if (lt == 0) return dwt_tail_forward(ctx, st, d_in, ld, d_out, ld, (int)n, steps, batch, f, L);
   const int plan_steps = lt > 0 ? lt : steps;
-  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, false);
+  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, false, ld);
   if (!plan.ok) return JWC_ERR_UNSUPPORTED;
   debug_dwt_plan("forward", plan, n, levels, L, tree);
   Scratch ws(st);
@@ -637,7 +638,7 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     if (!tmp[0] || !tmp[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const double* src = d_in;
-  int64_t src_sig = n;
+  int64_t src_sig = ld;
   for (int pi = 0; pi < npass; pi++) {
     const DwtPass& p = plan.passes[pi];
     const bool lastp = (pi == npass - 1);
@@ -649,12 +650,12 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
       a.nodes = 1 << p.l0;
       // whole-array ping-pong so that the last pass lands in d_out
       double* dst = (((npass - 1 - pi) & 1) == 0) ? d_out : tmp[0];
-      a.out = dst; a.out_sig = n;
+      a.out = dst; a.out_sig = (dst == d_out) ? ld : n;
     } else {
       a.nodes = 1;
-      a.out = d_out; a.out_sig = n;                                  // D's at their final place
+      a.out = d_out; a.out_sig = ld;                                 // D's at their final place
       if (lastp && lt > 0) { a.aout = tail_a; a.aout_sig = n >> lt; }
-      else if (lastp) { a.aout = d_out; a.aout_sig = n; }
+      else if (lastp) { a.aout = d_out; a.aout_sig = ld; }
       else { a.aout = tmp[pi & 1]; a.aout_sig = n >> (p.l0 + p.k); }
     }
     const int64_t nblocks = (int64_t)a.tiles * a.nodes * batch;
@@ -664,23 +665,24 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     int rc = tree ? dispatch_dwt_pass<true, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks)
                   : dispatch_dwt_pass<false, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks);
     if (rc != JWC_OK) return rc;
-    if (tree) { src = a.out; src_sig = n; }
+    if (tree) { src = a.out; src_sig = a.out_sig; }
     else { src = a.aout; src_sig = a.aout_sig; }
   }
-  if (lt > 0) return dwt_tail_forward(ctx, st, tail_a, n >> lt, d_out, n, (int)(n >> lt), steps - lt, batch, f, L);
+  if (lt > 0) return dwt_tail_forward(ctx, st, tail_a, n >> lt, d_out, ld, (int)(n >> lt), steps - lt, batch, f, L);
   return JWC_OK;
 }
 
 int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree) {
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, int64_t ld) {
+  if (ld <= 0) ld = n;
   if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);   // the reverse loops undo exactly the forward's steps
   if (steps == 0) return JWC_ERR_UNSUPPORTED;
   const int lt = (!tree && ctx->tune.dwt_tail >= 0) ? dwt_tail_start(n, steps) : -1;
-  if (lt == 0) return dwt_tail_inverse(ctx, st, d_in, n, d_out, n, (int)n, steps, batch, f, L);
+  if (lt == 0) return dwt_tail_inverse(ctx, st, d_in, ld, d_out, ld, (int)n, steps, batch, f, L);
   const int plan_steps = lt > 0 ? lt : steps;
-  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, true);
+  const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, true, ld);
   if (!plan.ok) return JWC_ERR_UNSUPPORTED;
   debug_dwt_plan("inverse", plan, n, levels, L, tree);
   Scratch ws(st);
@@ -690,7 +692,7 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     // the tail rebuilds A at level lt from the deepest approximation and the detail blocks below it
     tail_a = ws.get((size_t)batch * (n >> lt));
     if (!tail_a) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
-    const int rc = dwt_tail_inverse(ctx, st, d_in, n, tail_a, n >> lt, (int)(n >> lt), steps - lt, batch, f, L);
+    const int rc = dwt_tail_inverse(ctx, st, d_in, ld, tail_a, n >> lt, (int)(n >> lt), steps - lt, batch, f, L);
     if (rc != JWC_OK) return rc;
   }
   double* tmp[2] = {nullptr, nullptr};
@@ -706,7 +708,7 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     if (!tmp[0] || !tmp[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const double* asrc = d_in;     // FWT: A_{steps} is the prefix of the coefficient array; WPT: the whole array
-  int64_t asrc_sig = n;
+  int64_t asrc_sig = ld;
   if (lt > 0) { asrc = tail_a; asrc_sig = n >> lt; }
   for (int pi = npass - 1, step = 0; pi >= 0; --pi, ++step) {   // deepest pass first
     const DwtPass& p = plan.passes[pi];
@@ -716,14 +718,14 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     for (int jj = 0; jj < 16; jj++) a.hl[jj] = (int)dwt_inv_halo(L, jj);
     if (tree) {
       a.nodes = 1 << p.l0;
-      a.in = asrc; a.in_sig = n;
+      a.in = asrc; a.in_sig = asrc_sig;
       double* dst = (((pi) & 1) == 0) ? d_out : tmp[0];   // pass 0 (executed last) lands in d_out
-      a.out = dst; a.out_sig = n;
+      a.out = dst; a.out_sig = (dst == d_out) ? ld : n;
     } else {
       a.nodes = 1;
-      a.in = d_in; a.in_sig = n;                 // D blocks always come from the coefficient array
+      a.in = d_in; a.in_sig = ld;                // D blocks always come from the coefficient array
       a.ain = asrc; a.ain_sig = asrc_sig;
-      if (pi == 0) { a.out = d_out; a.out_sig = n; }
+      if (pi == 0) { a.out = d_out; a.out_sig = ld; }
       else { a.out = tmp[(pi - 1) & 1]; a.out_sig = n >> p.l0; }
     }
     const int64_t nblocks = (int64_t)a.tiles * a.nodes * batch;

@@ -278,10 +278,13 @@ int generic_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
 // FWT: level l (0-based) analyses the prefix of length h = n >> l of A_l:  lo -> A_{l+1}, hi -> out[h/2 .. h) (final).
 // WPT: level l analyses every block of length h; whole-array ping-pong.
 int generic_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact) {
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact,
+                        int64_t ld) {
+  if (ld <= 0) ld = n;
+  auto sig_of = [&](const double* p) { return (p == d_in || p == d_out) ? ld : n; };   // scratch is dense
   int steps = 0;  // number of analysis steps actually performed (reference loop: while h >= 2 && l < level)
   for (int64_t h = n; h >= 2 && steps < levels; h >>= 1) steps++;
-  if (steps == 0) return copy_rows(ctx, dev, st, d_in, d_out, n, n, n, batch);
+  if (steps == 0) return copy_rows(ctx, dev, st, d_in, d_out, ld, ld, n, batch);
   Scratch ws(st);
   if (tree) {
     double* tmp = nullptr;
@@ -294,9 +297,9 @@ int generic_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
     for (int l = 0; l < steps; l++, h >>= 1) {
       double* dst = (((steps - 1 - l) & 1) == 0) ? d_out : tmp;  // last step lands in d_out
       DwtStepArgs a{};
-      a.src_lo = src; a.src_lo_sig = n; a.src_lo_blk = h;
-      a.dst_lo = dst; a.dst_lo_sig = n; a.dst_lo_blk = h;
-      a.dst_hi = dst + (h >> 1); a.dst_hi_sig = n; a.dst_hi_blk = h;
+      a.src_lo = src; a.src_lo_sig = sig_of(src); a.src_lo_blk = h;
+      a.dst_lo = dst; a.dst_lo_sig = sig_of(dst); a.dst_lo_blk = h;
+      a.dst_hi = dst + (h >> 1); a.dst_hi_sig = sig_of(dst); a.dst_hi_blk = h;
       a.h = h; a.blocks = n / h; a.batch = batch; a.L = L;
       const int grid = grid_for(dev, (n >> 1) * batch);
       if (exact) dwt_step_fwd_kernel<true><<<grid, kThreads, 0, st>>>(a, f);
@@ -319,14 +322,14 @@ int generic_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
     if (!abuf[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const double* src = d_in;
-  int64_t src_sig = n;
+  int64_t src_sig = ld;
   int64_t h = n;
   for (int l = 0; l < steps; l++, h >>= 1) {
     DwtStepArgs a{};
     a.src_lo = src; a.src_lo_sig = src_sig; a.src_lo_blk = 0;
-    if (l == steps - 1) { a.dst_lo = d_out; a.dst_lo_sig = n; }
+    if (l == steps - 1) { a.dst_lo = d_out; a.dst_lo_sig = ld; }
     else { a.dst_lo = abuf[l & 1]; a.dst_lo_sig = h >> 1; }
-    a.dst_hi = d_out + (h >> 1); a.dst_hi_sig = n;
+    a.dst_hi = d_out + (h >> 1); a.dst_hi_sig = ld;
     a.h = h; a.blocks = 1; a.batch = batch; a.L = L;
     const int grid = grid_for(dev, (h >> 1) * batch);
     if (exact) dwt_step_fwd_kernel<true><<<grid, kThreads, 0, st>>>(a, f);
@@ -340,14 +343,17 @@ int generic_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
 }
 
 int generic_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact) {
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact,
+                        int64_t ld) {
+  if (ld <= 0) ld = n;
+  auto sig_of = [&](const double* p) { return (p == d_in || p == d_out) ? ld : n; };
   // reference: h starts at 2 << (log2 n - level) and doubles while h <= n  (FastWaveletTransform.java:137-151)
   int p = 0;
   while (((int64_t)1 << p) < n) p++;
   int64_t h0 = (int64_t)2 << (p - levels);
   int steps = 0;
   for (int64_t h = h0; h <= n && h >= 2; h <<= 1) steps++;
-  if (steps == 0) return copy_rows(ctx, dev, st, d_in, d_out, n, n, n, batch);
+  if (steps == 0) return copy_rows(ctx, dev, st, d_in, d_out, ld, ld, n, batch);
   Scratch ws(st);
   if (tree) {
     double* tmp = nullptr;
@@ -360,9 +366,9 @@ int generic_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
     for (int l = 0; l < steps; l++, h <<= 1) {
       double* dst = (((steps - 1 - l) & 1) == 0) ? d_out : tmp;
       DwtStepArgs a{};
-      a.src_lo = src; a.src_lo_sig = n; a.src_lo_blk = h;
-      a.src_hi = src + (h >> 1); a.src_hi_sig = n; a.src_hi_blk = h;
-      a.dst_lo = dst; a.dst_lo_sig = n; a.dst_lo_blk = h;
+      a.src_lo = src; a.src_lo_sig = sig_of(src); a.src_lo_blk = h;
+      a.src_hi = src + (h >> 1); a.src_hi_sig = sig_of(src); a.src_hi_blk = h;
+      a.dst_lo = dst; a.dst_lo_sig = sig_of(dst); a.dst_lo_blk = h;
       a.h = h; a.blocks = n / h; a.batch = batch; a.L = L;
       const int grid = grid_for(dev, n * batch);
       if (exact) dwt_step_inv_kernel<true><<<grid, kThreads, 0, st>>>(a, f);
@@ -386,13 +392,13 @@ int generic_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
     if (!abuf[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const double* src = d_in;
-  int64_t src_sig = n;
+  int64_t src_sig = ld;
   int64_t h = h0;
   for (int l = 0; l < steps; l++, h <<= 1) {
     DwtStepArgs a{};
     a.src_lo = src; a.src_lo_sig = src_sig; a.src_lo_blk = 0;
-    a.src_hi = d_in + (h >> 1); a.src_hi_sig = n; a.src_hi_blk = 0;
-    if (l == steps - 1) { a.dst_lo = d_out; a.dst_lo_sig = n; }
+    a.src_hi = d_in + (h >> 1); a.src_hi_sig = ld; a.src_hi_blk = 0;
+    if (l == steps - 1) { a.dst_lo = d_out; a.dst_lo_sig = ld; }
     else {
       // ping-pong so that the larger buffer receives the larger result: remaining steps r = steps-1-l,
       // result length h = n >> r

@@ -113,10 +113,14 @@ int generic_modwt_forward_from(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t
 int generic_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                           int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact);
 // tree = false: FWT (only the length-h prefix is transformed each level); tree = true: WPT (every block).
+// ld = distance in doubles between consecutive signals in d_in and in d_out (0 = dense, ld = n): lets a transform run
+// on a column block of a wider array (Ancient-Egyptian blocks of arbitrary-length signals).
 int generic_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact);
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact,
+                        int64_t ld = 0);
 int generic_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact);
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, bool exact,
+                        int64_t ld = 0);
 
 // ---- fused tile kernels: jwc_modwt_fast.cu / jwc_dwt_fast.cu --------------------------------------------
 // each returns JWC_ERR_UNSUPPORTED (without setting an error) when the shape is outside its fast path.
@@ -143,9 +147,9 @@ int dwt2d_columns_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
                           bool exact);
 
 int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree);
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, int64_t ld = 0);
 int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
-                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree);
+                     int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, int64_t ld = 0);
 
 inline void count_launch(jwc_ctx* ctx, uint64_t k = 1) { ctx->launches.fetch_add(k, std::memory_order_relaxed); }
 

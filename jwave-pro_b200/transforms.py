@@ -281,6 +281,63 @@ class CudaWaveletPacketTransform(_CudaPyramidBase):
         self._name = "Wavelet Packet Transform"
 
 
+class AncientEgyptianDecomposition(BasicTransform):
+    """transforms/AncientEgyptianDecomposition.java:42 -- arbitrary-length wrapper: the signal is cut into blocks of
+    descending powers of two (tools/MathToolKit.java:57-84), each block goes through the wrapped transform at full
+    depth and lands at its own position.  The wrapped transform must be one of the CUDA pyramid transforms; all blocks
+    of all signals of a batch are transformed on the device without gathering them (jwc_{fwt,wpt}_aed_*)."""
+
+    def __init__(self, basicTransform, initialWaveletSpaceSize=0):
+        if not isinstance(basicTransform, _CudaPyramidBase):
+            raise JWaveFailure("AncientEgyptianDecomposition - the CUDA path wraps CudaFastWaveletTransform or "
+                               "CudaWaveletPacketTransform")
+        self._basicTransform = basicTransform
+        self._initialWaveletSpaceSize = initialWaveletSpaceSize
+        self._name = basicTransform.getName()
+
+    @staticmethod
+    def decompose(number):
+        """MathToolKit.decompose: 42 -> [5, 3, 1]."""
+        if number < 1:
+            raise JWaveFailure("the supported number for decomposition is smaller than one")
+        out = []
+        while number >= 1:
+            p = int(number).bit_length() - 1
+            out.append(p)
+            number -= 1 << p
+        return out
+
+    def _run(self, direction, mat, flags, out):
+        t = self._basicTransform
+        X = _as_f64(mat)
+        B, N = X.shape
+        out = np.empty_like(X) if out is None else out
+        if N == 0 or B == 0:
+            return out
+        w = t._wavelet
+        f0, f1 = ((w.getScalingDeComposition(), w.getWaveletDeComposition()) if direction == "forward"
+                  else (w.getScalingReConstruction(), w.getWaveletReConstruction()))
+        lib = _native.load()
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        fn = getattr(lib, "%s_aed_%s" % (t._fn, direction if direction == "forward" else "inverse"))
+        rc = fn(t._context().handle, X.ctypes.data, out.ctypes.data, B, N, _ptr(f0), _ptr(f1), len(f0), flags)
+        if rc != 0:
+            raise RuntimeError("aed %s failed (%d): %s" % (direction, rc, _native.last_error()))
+        return out
+
+    def forward(self, arrTime, flags=0):
+        return self._run("forward", _as_f64(arrTime)[None, :], flags, None)[0]
+
+    def reverse(self, arrHilb, flags=0):
+        return self._run("reverse", _as_f64(arrHilb)[None, :], flags, None)[0]
+
+    def forwardBatch(self, matTime, flags=0, out=None):
+        return self._run("forward", matTime, flags, out)
+
+    def reverseBatch(self, matHilb, flags=0, out=None):
+        return self._run("reverse", matHilb, flags, out)
+
+
 class ArrayView:
     """transforms/EfficientMODWTTransform.java:88-117 -- read-only window on a backing array, no copy."""
 

@@ -177,3 +177,28 @@ def batch2d(kind, x, lvl_m, lvl_n, f0, f1, reverse=False, nthreads=1):
     if not reverse:
         return along_cols(along_rows(x, lvl_n), lvl_m)
     return along_rows(along_cols(x, lvl_m), lvl_n)
+
+
+def aed_blocks(n):
+    """tools/MathToolKit.java:57-84 decompose(): exponents of the descending powers of two that sum to n (42 -> 5, 3, 1)."""
+    assert n >= 1
+    out = []
+    cur = n
+    while cur >= 1:
+        p = cur.bit_length() - 1
+        out.append(p)
+        cur -= 1 << p
+    return out
+
+
+def aed(kind, x, f0, f1, reverse=False, nthreads=1):
+    """transforms/AncientEgyptianDecomposition.java:97-181: every 2^p block of every signal of x (batch, n), n arbitrary,
+    through the wrapped transform's forward(double[]) / reverse(double[]) = full depth p; results at the same positions."""
+    x = _c(x)
+    out = np.empty_like(x)
+    off = 0
+    for p in aed_blocks(x.shape[1]):
+        ln = 1 << p
+        out[:, off:off + ln] = batch(kind + ("_rev" if reverse else "_fwd"), x[:, off:off + ln], p, f0, f1, nthreads)
+        off += ln
+    return out

@@ -119,3 +119,15 @@ def test_modwt_coefficients_wire_format(jw):
         c.getView(4)
     backing[16] = -1.0          # a view reads the backing array, a copy does not
     assert v.get(0) == -1.0
+
+
+def test_ancient_egyptian_multipliers(jw, oracle):
+    """tools/MathToolKit.java:57-84 decompose (e.g. 42 = 2^5 + 2^3 + 2^1; the javadoc's 127 = 64|32|16|8|4|2|1)."""
+    dec = jw.AncientEgyptianDecomposition.decompose
+    assert dec(42) == [5, 3, 1]
+    assert dec(127) == [6, 5, 4, 3, 2, 1, 0]
+    assert dec(1) == [0] and dec(1 << 20) == [20]
+    for n in (3, 17, 1000, 65537, 2 ** 31 - 1):
+        assert sum(1 << p for p in dec(n)) == n and dec(n) == oracle.aed_blocks(n)
+    with pytest.raises(jw.JWaveFailure):
+        dec(0)

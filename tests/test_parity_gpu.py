@@ -531,3 +531,36 @@ def test_modwt_coefficients_format_from_device_layout(jw, gpu_ctx, oracle):
     # the level-less reverse searches the SMALLEST 2^p N with total/N - 1 <= log2 N (MODWTTransform.java:888-897):
     # for 4 x 1024 coefficients that is N = 512, J = 7, not the shape that produced them -- same as the reference
     assert len(t.reverse(c.backingArray())) == 512
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# arbitrary length: Ancient-Egyptian decomposition
+# ----------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+@pytest.mark.parametrize("cls,n,batch", [
+    ("Haar1", 42, 3),                 # 32 | 8 | 2
+    ("Daubechies4", 127, 5),          # 64 | 32 | 16 | 8 | 4 | 2 | 1: odd row stride, every block misaligned
+    ("Daubechies8", 1000, 4),         # 512 | 256 | 128 | 64 | 32 | 8
+    ("Symlet8", 65536 + 4096 + 6, 3),
+    ("Daubechies20", 3 * 4096, 2),    # 8192 | 4096, filter longer than nothing here but L = 40 kernels
+    ("Coiflet2", 1, 4),
+    ("Daubechies2", 1 << 12, 2),      # a power of two: one block, identical to the plain transform
+    ("Daubechies3", 200000, 2),       # blocks above and below the short-signal tail threshold
+])
+def test_ancient_egyptian_decomposition(jw, gpu_ctx, oracle, kind, cls, n, batch):
+    w = jw.wavelets.create(cls)
+    T = jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform
+    aed = jw.AncientEgyptianDecomposition(T(w))
+    X = splitmix_uniform(4242 + n, (batch, n))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.aed(kind, X, s, wv, nthreads=8)
+    got = aed.forwardBatch(X)
+    assert _maxerr(got, ref, X) <= TOL
+    assert np.array_equal(aed.forwardBatch(X, flags=jw.FLAG_EXACT), ref)
+    rref = oracle.aed(kind, ref, w.getScalingReConstruction(), w.getWaveletReConstruction(), reverse=True, nthreads=8)
+    assert _maxerr(aed.reverseBatch(ref), rref, X) <= TOL
+    assert np.array_equal(aed.reverseBatch(ref, flags=jw.FLAG_EXACT), rref)
+    assert _maxerr(aed.reverse(aed.forward(X[0])), X[0], X) <= PR_TOL
+    if n & (n - 1) == 0 and n > 1:
+        assert np.array_equal(got, T(w).forwardBatch(X))
