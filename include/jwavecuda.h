@@ -115,6 +115,17 @@ JWC_API int jwc_modwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_x_c
 JWC_API int jwc_modwt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_coeff_chunks, double* const* d_x_chunks,
                                         int64_t n, int levels, const double* g, const double* h, int L, unsigned flags);
 
+/* Sliding-window analysis (the reference's motivating workload, test/.../MODWTSlidingWindowTest.java:20-70: 512-sample
+ * windows, 8 levels, step 64): window w = series[w*hop .. w*hop + window), w = 0 .. (series_len - window)/hop, each
+ * through forwardMODWT.  The windows are never materialised: the kernels read window w at series + w*hop.
+ * coeffs: [nwin][levels+1][window].  An odd hop forces the element-wise loaders (no 16-byte alignment). */
+JWC_API int jwc_modwt_forward_windows(jwc_ctx* ctx, const double* series, double* coeffs, int64_t series_len,
+                                      int64_t window, int64_t hop, int levels, const double* g, const double* h, int L,
+                                      unsigned flags);
+JWC_API int jwc_modwt_forward_windows_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_series, double* d_coeffs,
+                                          int64_t series_len, int64_t window, int64_t hop, int levels, const double* g,
+                                          const double* h, int L, unsigned flags);
+
 /* ---- FWT --------------------------------------------------------------------------------------------
  * lo, hi: scalingDeCom / waveletDeCom for forward, scalingReCon / waveletReCon for inverse (Wavelet.java:178-219).
  * n must be 2^p, 0 <= levels <= p (FastWaveletTransform.java:74-83); levels = 0 copies.
@@ -174,6 +185,17 @@ JWC_API int jwc_wpt2d_forward_dev(jwc_ctx* ctx, int slot, void* stream, const do
 JWC_API int jwc_wpt2d_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
                                   int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* lo,
                                   const double* hi, int L, unsigned flags);
+
+/* ---- magnitude thresholding of a coefficient buffer ---------------------------------------------------------
+ * compressions/CompressorMagnitude.java:78-140 + compressions/Compressor.java:97-170: magnitude = mean |c| over all
+ * `count` values (array, matrix or space alike); out[i] = in[i] if |in[i]| >= magnitude * threshold, else 0.
+ * threshold > 0.  The device variant leaves the magnitude in *d_magnitude (device memory) and may run in place
+ * (d_out == d_in); chained after a *_dev transform on the same stream it costs one read for the sum and one read +
+ * write for the select, with no host round trip. */
+JWC_API int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
+                                   double* magnitude);
+JWC_API int jwc_compress_magnitude_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                       int64_t count, double threshold, double* d_magnitude);
 
 /* ---- arbitrary-length FWT / WPT: Ancient-Egyptian decomposition -----------------------------------------
  * transforms/AncientEgyptianDecomposition.java:97-181 with tools/MathToolKit.java:57-84 decompose(): a signal of any

@@ -30,6 +30,8 @@ SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal"
             "jwc_alloc_device", "jwc_free_device", "jwc_copy_to_device", "jwc_copy_to_host", "jwc_synchronize"]
            + ["jwc_" + t for t in _TRANSFORMS] + ["jwc_" + t + "_dev" for t in _TRANSFORMS]
            + ["jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"]
+           + ["jwc_modwt_forward_windows", "jwc_modwt_forward_windows_dev", "jwc_compress_magnitude",
+              "jwc_compress_magnitude_dev"]
            + ["jwc_" + t for t in _TRANSFORMS_2D] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_2D]
            + ["jwc_" + t for t in _TRANSFORMS_AED] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_AED])
 
@@ -90,6 +92,15 @@ def load():
             fn = getattr(lib, "jwc_" + t + "_dev")
             fn.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _dp, _dp, _int, _u32]
             fn.restype = _int
+        lib.jwc_modwt_forward_windows.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _int, _dp, _dp, _int, _u32]
+        lib.jwc_modwt_forward_windows.restype = _int
+        lib.jwc_modwt_forward_windows_dev.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _int, _dp, _dp, _int,
+                                                      _u32]
+        lib.jwc_modwt_forward_windows_dev.restype = _int
+        lib.jwc_compress_magnitude.argtypes = [_vp, _vp, _vp, _i64, ctypes.c_double, _dp]
+        lib.jwc_compress_magnitude.restype = _int
+        lib.jwc_compress_magnitude_dev.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, ctypes.c_double, _vp]
+        lib.jwc_compress_magnitude_dev.restype = _int
         for t in _TRANSFORMS_AED:
             fn = getattr(lib, "jwc_" + t)
             fn.argtypes = [_vp, _vp, _vp, _i64, _i64, _dp, _dp, _int, _u32]

@@ -1,6 +1,7 @@
 """Public surface of the package (imported by the `jwave_pro_b200` shim and by __init__)."""
 from . import wavelets
 from ._native import FLAG_EXACT, FLAG_FORCE_GENERIC, Context, default_context
+from .compressions import CompressorMagnitude
 from .exceptions import (IllegalArgumentException, JWaveError, JWaveException, JWaveFailure, NativeLibraryError)
 from .transforms import (AncientEgyptianDecomposition, ArrayView, BasicTransform, CudaFastWaveletTransform, CudaMODWTTransform,
                          CudaWaveletPacketTransform, MODWTCoefficients, WaveletTransform)
@@ -8,5 +9,5 @@ from .wavelets import Wavelet
 
 __all__ = ["wavelets", "Wavelet", "Context", "default_context", "FLAG_EXACT", "FLAG_FORCE_GENERIC",
            "BasicTransform", "WaveletTransform", "CudaFastWaveletTransform", "CudaWaveletPacketTransform",
-           "CudaMODWTTransform", "MODWTCoefficients", "ArrayView", "AncientEgyptianDecomposition", "JWaveException", "JWaveFailure", "JWaveError", "IllegalArgumentException",
+           "CudaMODWTTransform", "MODWTCoefficients", "ArrayView", "CompressorMagnitude", "AncientEgyptianDecomposition", "JWaveException", "JWaveFailure", "JWaveError", "IllegalArgumentException",
            "NativeLibraryError"]

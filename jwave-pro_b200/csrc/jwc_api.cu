@@ -40,6 +40,7 @@ struct Dim2 {
   int64_t rows = 0;
   int lvl_m = 0;
   bool aed = false;   // Ancient-Egyptian decomposition of arbitrary-length signals (levels ignored: full depth per block)
+  int64_t hop = 0;    // > 0: forward MODWT of overlapping windows of ONE series; window b starts at b * hop
 };
 
 bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -65,6 +66,10 @@ int validate(Op op, const void* in, const void* out, int64_t batch, int64_t n, i
   JWC_REQUIRE(n >= 1, "signal length must be >= 1 (got %lld)", (long long)n);
   JWC_REQUIRE(n < ((int64_t)1 << 40), "signal length %lld too large", (long long)n);
   JWC_REQUIRE(L >= 1 && L <= JWC_MAX_TAPS, "filter length %d outside 1..%d", L, JWC_MAX_TAPS);
+  if (d2.hop != 0) {
+    JWC_REQUIRE(op == Op::ModwtFwd, "sliding windows exist for the forward MODWT only");
+    JWC_REQUIRE(d2.hop >= 1, "window hop must be >= 1 (got %lld)", (long long)d2.hop);
+  }
   if (d2.aed) {
     JWC_REQUIRE(op != Op::ModwtFwd && op != Op::ModwtInv, "no Ancient-Egyptian MODWT");
     JWC_REQUIRE(n < ((int64_t)1 << 31), "signal length %lld too large", (long long)n);
@@ -143,7 +148,7 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
   int rc = JWC_ERR_UNSUPPORTED;
   if (!generic) {
     switch (op) {
-      case Op::ModwtFwd: rc = fast_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L); break;
+      case Op::ModwtFwd: rc = fast_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, d2.hop); break;
       case Op::ModwtInv: rc = fast_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L); break;
       case Op::FwtFwd: rc = fast_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
       case Op::FwtInv: rc = fast_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
@@ -153,7 +158,8 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
     if (rc != JWC_ERR_UNSUPPORTED) return rc;
   }
   switch (op) {
-    case Op::ModwtFwd: return generic_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, exact);
+    case Op::ModwtFwd:
+      return generic_modwt_forward_from(ctx, dev, st, d_in, d2.hop > 0 ? d2.hop : n, 1, d_out, batch, n, levels, fp, L, exact);
     case Op::ModwtInv: return generic_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, exact);
     case Op::FwtFwd: return generic_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false, exact);
     case Op::FwtInv: return generic_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false, exact);
@@ -167,6 +173,7 @@ void io_sizes(Op op, int64_t n, int levels, int64_t* in_per, int64_t* out_per, c
   *in_per = n;
   *out_per = n;
   if (d2.rows != 0) *in_per = *out_per = n * d2.rows;
+  // sliding windows: *in_per stays n (one window); consecutive windows start d2.hop apart (see in_step below)
   if (op == Op::ModwtFwd) *out_per = (int64_t)(levels + 1) * n;
   if (op == Op::ModwtInv) *in_per = (int64_t)(levels + 1) * n;
 }
@@ -216,7 +223,11 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
   if (!lane_acquire(ctx, slot, &lane)) { set_error("cannot create streams on device %d", dev.ordinal); return JWC_ERR_CUDA; }
   int64_t in_per, out_per;
   io_sizes(op, n, levels, &in_per, &out_per, d2);
-  const int64_t per_sig_bytes = (in_per + out_per) * (int64_t)sizeof(double);
+  // sliding windows: unit b of the input starts at b * hop and is in_per long, so a chunk of nb units spans
+  // (nb - 1) * hop + in_per input samples; everywhere else units are dense (in_step == in_per)
+  const int64_t in_step = d2.hop > 0 ? d2.hop : in_per;
+  auto in_span = [&](int64_t nb) { return (nb - 1) * in_step + in_per; };
+  const int64_t per_sig_bytes = (in_step + out_per) * (int64_t)sizeof(double);
   int64_t chunk_mb = ctx->tune.h2d_chunk_mb > 0 ? ctx->tune.h2d_chunk_mb : 128;   // in + out bytes per chunk
   int64_t chunk = (chunk_mb << 20) / per_sig_bytes;
   if (chunk < 1) chunk = 1;
@@ -249,7 +260,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
   };
   cudaError_t e;
   for (int i = 0; i < nbuf && rc == JWC_OK; i++) {
-    if ((e = cudaMallocAsync((void**)&d_in[i], (size_t)(chunk * in_per) * sizeof(double), sc)) != cudaSuccess ||
+    if ((e = cudaMallocAsync((void**)&d_in[i], (size_t)in_span(chunk) * sizeof(double), sc)) != cudaSuccess ||
         (e = cudaMallocAsync((void**)&d_out[i], (size_t)(chunk * out_per) * sizeof(double), sc)) != cudaSuccess) {
       (void)cudaGetLastError();
       set_error("device staging allocation of %lld MiB failed: %s",
@@ -279,7 +290,7 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
       if ((e = cudaStreamWaitEvent(sc, ev_out[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
     }
     if (c > 0 && pace_in && ctx->host_calls.load() > 1) cudaEventSynchronize(ev_in[(c - 1) % nbuf]);
-    if ((e = cudaMemcpyAsync(d_in[k], in + b0 * in_per, (size_t)(nb * in_per) * sizeof(double), cudaMemcpyHostToDevice,
+    if ((e = cudaMemcpyAsync(d_in[k], in + b0 * in_step, (size_t)in_span(nb) * sizeof(double), cudaMemcpyHostToDevice,
                              si)) != cudaSuccess) { fail(e, "cudaMemcpyAsync(H2D)"); break; }
     if ((e = cudaEventRecord(ev_in[k], si)) != cudaSuccess) { fail(e, "cudaEventRecord"); break; }
     if ((e = cudaStreamWaitEvent(sc, ev_in[k], 0)) != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
@@ -329,7 +340,8 @@ int run_host(jwc_ctx* ctx, Op op, const double* in, double* out, int64_t batch, 
   for (int s = 0; s < nd; s++) {
     const int64_t b0 = batch * s / nd, b1 = batch * (s + 1) / nd;
     th.emplace_back([=, &rcs, &errs, &fp]() {
-      rcs[s] = run_host_slot(ctx, s, op, in + b0 * in_per, out + b0 * out_per, b1 - b0, n, levels, fp, L, flags, d2);
+      rcs[s] = run_host_slot(ctx, s, op, in + b0 * (d2.hop > 0 ? d2.hop : in_per), out + b0 * out_per, b1 - b0, n, levels,
+                             fp, L, flags, d2);
       if (rcs[s] != JWC_OK) errs[s] = g_err;
     });
   }
@@ -656,6 +668,94 @@ JWC_DEFINE(wpt_inverse, Op::WptInv)
     d2.lvl_m = lvl_m;                                                                                               \
     return run_dev(ctx, slot, stream, OP, d_in, d_out, batch, cols, lvl_n, f0, f1, L, flags, d2);                   \
   }
+
+// CompressorMagnitude.compress: out = in where |in| >= mean|in| * threshold, else 0; *magnitude = mean|in|
+JWC_API int jwc_compress_magnitude_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
+                                       int64_t count, double threshold, double* d_magnitude) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  JWC_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), "device slot %d out of range", slot);
+  JWC_REQUIRE(d_in != nullptr && d_out != nullptr && d_magnitude != nullptr, "NULL pointer");
+  JWC_REQUIRE(count >= 0, "count must be >= 0");
+  JWC_REQUIRE(threshold > 0.0, "Compressor - given threshold should be larger than zero!");
+  const DeviceSlot& dev = ctx->slots[slot];
+  DeviceGuard guard(dev.ordinal);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", dev.ordinal); return JWC_ERR_CUDA; }
+  cudaStream_t st = stream ? (cudaStream_t)stream : dev.stream;
+  return compress_magnitude(ctx, dev, st, d_in, d_out, count, threshold, d_magnitude);
+}
+JWC_API int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
+                                   double* magnitude) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  JWC_REQUIRE(in != nullptr && out != nullptr, "NULL pointer");
+  JWC_REQUIRE(count >= 0, "count must be >= 0");
+  JWC_REQUIRE(threshold > 0.0, "Compressor - given threshold should be larger than zero!");
+  if (magnitude) *magnitude = 0.0;
+  if (count == 0) return JWC_OK;
+  const DeviceSlot& dev = ctx->slots[0];   // a global mean: one device
+  DeviceGuard guard(dev.ordinal);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", dev.ordinal); return JWC_ERR_CUDA; }
+  Lane lane;
+  if (!lane_acquire(ctx, 0, &lane)) { set_error("cannot create streams on device %d", dev.ordinal); return JWC_ERR_CUDA; }
+  cudaStream_t st = lane.compute;
+  double *d_x = nullptr, *d_mag = nullptr;
+  int rc = JWC_OK;
+  cudaError_t e;
+  if ((e = cudaMallocAsync((void**)&d_x, (size_t)count * sizeof(double), st)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&d_mag, sizeof(double), st)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("device staging allocation failed: %s", cudaGetErrorString(e));
+    rc = JWC_ERR_NOMEM;
+  }
+  double mag = 0.0;
+  if (rc == JWC_OK) {
+    if ((e = cudaMemcpyAsync(d_x, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+      set_error("cudaMemcpyAsync(H2D) failed: %s", cudaGetErrorString(e));
+      rc = JWC_ERR_CUDA;
+    }
+  }
+  if (rc == JWC_OK) rc = compress_magnitude(ctx, dev, st, d_x, d_x, count, threshold, d_mag);   // in place
+  if (rc == JWC_OK) {
+    if ((e = cudaMemcpyAsync(out, d_x, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(&mag, d_mag, sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
+      set_error("cudaMemcpyAsync(D2H) failed: %s", cudaGetErrorString(e));
+      rc = JWC_ERR_CUDA;
+    }
+  }
+  e = cudaStreamSynchronize(st);
+  if (rc == JWC_OK && e != cudaSuccess) { set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e)); rc = JWC_ERR_CUDA; }
+  if (d_x) cudaFreeAsync(d_x, st);
+  if (d_mag) cudaFreeAsync(d_mag, st);
+  lane_release(ctx, 0, lane);
+  if (rc == JWC_OK && magnitude) *magnitude = mag;
+  return rc;
+}
+
+// MODWTSlidingWindowTest.java:20-70: overlapping windows of one long series, each through forwardMODWT
+JWC_API int jwc_modwt_forward_windows(jwc_ctx* ctx, const double* series, double* coeffs, int64_t series_len,
+                                      int64_t window, int64_t hop, int levels, const double* g, const double* h, int L,
+                                      unsigned flags) {
+  if (window < 1 || hop < 1 || series_len < window) {
+    set_error("need 1 <= window <= series length and hop >= 1 (window %lld, hop %lld, series %lld)", (long long)window,
+              (long long)hop, (long long)series_len);
+    return JWC_ERR_INVALID;
+  }
+  Dim2 d2;
+  d2.hop = hop;
+  return run_host(ctx, Op::ModwtFwd, series, coeffs, (series_len - window) / hop + 1, window, levels, g, h, L, flags, d2);
+}
+JWC_API int jwc_modwt_forward_windows_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_series, double* d_coeffs,
+                                          int64_t series_len, int64_t window, int64_t hop, int levels, const double* g,
+                                          const double* h, int L, unsigned flags) {
+  if (window < 1 || hop < 1 || series_len < window) {
+    set_error("need 1 <= window <= series length and hop >= 1 (window %lld, hop %lld, series %lld)", (long long)window,
+              (long long)hop, (long long)series_len);
+    return JWC_ERR_INVALID;
+  }
+  Dim2 d2;
+  d2.hop = hop;
+  return run_dev(ctx, slot, stream, Op::ModwtFwd, d_series, d_coeffs, (series_len - window) / hop + 1, window, levels, g,
+                 h, L, flags, d2);
+}
 
 #define JWC_DEFINE_AED(name, OP)                                                                                    \
   JWC_API int jwc_##name(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, const double* f0,   \

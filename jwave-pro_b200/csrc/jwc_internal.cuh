@@ -124,8 +124,10 @@ int generic_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
 
 // ---- fused tile kernels: jwc_modwt_fast.cu / jwc_dwt_fast.cu --------------------------------------------
 // each returns JWC_ERR_UNSUPPORTED (without setting an error) when the shape is outside its fast path.
+// x_sig: distance between consecutive input signals (0 = n); x_sig < n makes the batch a set of overlapping windows of
+// one series (sliding-window analysis without materialising the windows)
 int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
-                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);
 int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
 // warp-per-signal deep end of the FWT pyramid for short signals (jwc_dwt_tail.cu)
@@ -136,6 +138,10 @@ int dwt_tail_forward(jwc_ctx* ctx, cudaStream_t st, const double* src, int64_t s
                      int h0, int nlev, int64_t batch, const FilterPair& f, int L);
 int dwt_tail_inverse(jwc_ctx* ctx, cudaStream_t st, const double* d_in, int64_t n, double* dst, int64_t dst_sig, int h0,
                      int nlev, int64_t batch, const FilterPair& f, int L);
+
+// magnitude thresholding of a coefficient buffer (jwc_compress.cu); d_mag = one device double for the magnitude
+int compress_magnitude(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                       int64_t count, double threshold, double* d_mag);
 
 // column passes of the 2-D FWT / WPT (jwc_dwt2d.cu); d_src / d_in must not overlap the destination
 int dwt2d_column_steps(int64_t rows, int levels);

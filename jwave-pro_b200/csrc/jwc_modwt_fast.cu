@@ -325,12 +325,13 @@ int dispatch_fwd_pass(jwc_ctx* ctx, cudaStream_t st, const FwdPassArgs& a, const
 }  // namespace
 
 int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
-                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L) {
+                       int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig) {
+  if (x_sig <= 0) x_sig = n;
   if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
   if (levels > 30 || n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   ModwtPlanInput pin{};
   pin.n = n; pin.J = levels; pin.L = L;
-  pin.aligned16 = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_coeffs)) & 15) == 0;
+  pin.aligned16 = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_coeffs)) & 15) == 0 && (x_sig & 1) == 0;
   // measured on B200 (C2): forward best with 2 large CTAs per SM (113 KB), inverse best with 3 (75 KB)
   // (fp64-bound long filters prefer 3 CTAs per SM: db20 J8 34.9 ms at 75 KB vs 37.3 ms at 113 KB)
   pin.smem_budget = ctx->tune.modwt_smem > 0 ? ctx->tune.modwt_smem : (L <= 10 ? 113000 : 75776);
@@ -353,7 +354,7 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     if (!vbuf[0] || !vbuf[1]) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
   }
   const double* vin = d_x;
-  int64_t vin_sig = n;
+  int64_t vin_sig = x_sig;
   for (int pi = 0; pi < npass; pi++) {
     const ModwtPass& p = plan.passes[pi];
     const bool last = plan.all_fused && pi == npass - 1;

@@ -532,6 +532,25 @@ class CudaMODWTTransform(WaveletTransform):
                                    "for given level")
         return self.inverseMODWT(_as_f64(arrHilb).reshape(levels + 1, N))
 
+    def forwardMODWTWindows(self, series, window, hop, maxLevel, flags=0, out=None):
+        """Sliding-window analysis (MODWTSlidingWindowTest.java:20-70): forwardMODWT of every window
+        series[w*hop : w*hop + window]; returns [nwin][maxLevel+1][window].  One device pass over the series; the
+        windows are read in place."""
+        x = _as_f64(series)
+        if x.ndim != 1 or window < 1 or hop < 1 or len(x) < window:
+            raise IllegalArgumentException("need a 1-D series with 1 <= window <= len(series) and hop >= 1")
+        self._check_levels(maxLevel, window)
+        nwin = (len(x) - window) // hop + 1
+        out = np.empty((nwin, maxLevel + 1, window)) if out is None else out
+        g, h = self._filters()
+        lib = _native.load()
+        g, h = _as_f64(g), _as_f64(h)
+        rc = lib.jwc_modwt_forward_windows(self._context().handle, x.ctypes.data, out.ctypes.data, len(x), window, hop,
+                                           maxLevel, _ptr(g), _ptr(h), len(g), flags)
+        if rc != 0:
+            raise RuntimeError("jwc_modwt_forward_windows failed (%d): %s" % (rc, _native.last_error()))
+        return out
+
     def forwardMODWTCoefficients(self, data, maxLevel, flags=0):
         """The result of forwardMODWT in the MODWTCoefficients wire format (one backing array, level views).  Rows
         carry forwardMODWT's meaning (W_j = h~ conv V, V_J last); the reference's forwardMODWTEfficient

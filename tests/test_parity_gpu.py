@@ -564,3 +564,87 @@ def test_ancient_egyptian_decomposition(jw, gpu_ctx, oracle, kind, cls, n, batch
     assert _maxerr(aed.reverse(aed.forward(X[0])), X[0], X) <= PR_TOL
     if n & (n - 1) == 0 and n > 1:
         assert np.array_equal(got, T(w).forwardBatch(X))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# sliding windows of one series (MODWTSlidingWindowTest.java:20-70)
+# ----------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cls,total,window,hop,J", [
+    ("Haar1", 10000, 512, 64, 8),            # the reference test's configuration
+    ("Daubechies4", 10000, 512, 64, 8),
+    ("Daubechies4", 70000, 4096, 1000, 6),
+    ("Symlet8", 5000, 300, 7, 4),            # window not a power of two, odd hop: element-wise loaders
+    ("Daubechies2", 300000, 65536, 32768, 9),
+    ("Daubechies20", 9000, 1024, 512, 5),
+    ("Daubechies3", 64, 64, 5, 3),           # a single window
+])
+def test_modwt_sliding_windows(jw, oracle, cls, total, window, hop, J):
+    ctx = jw.Context([0])
+    ctx.set_tuning("h2d_chunk_mb", 1)        # several pipeline chunks: overlapping input spans per chunk
+    w = jw.wavelets.create(cls)
+    t = jw.CudaMODWTTransform(w, context=ctx)
+    x = chirp(1, total)[0] + 0.25 * splitmix_uniform(total + hop, (total,))
+    nwin = (total - window) // hop + 1
+    wins = np.lib.stride_tricks.sliding_window_view(x, window)[::hop][:nwin]
+    ref, _ = _modwt_oracle(oracle, w, np.ascontiguousarray(wins), J)
+    got = t.forwardMODWTWindows(x, window, hop, J)
+    assert got.shape == (nwin, J + 1, window)
+    assert _maxerr(got, ref, x) <= TOL
+    assert np.array_equal(t.forwardMODWTWindows(x, window, hop, J, flags=jw.FLAG_EXACT), ref)
+    assert _maxerr(t.inverseMODWTBatch(got), wins, x) <= PR_TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("shape,thr", [((1000,), 1.0), ((64, 513), 0.5), ((3, 7, 4096), 2.0), ((1,), 1.0),
+                                       ((5_000_000,), 1.3)])
+def test_compressor_magnitude(jw, gpu_ctx, shape, thr):
+    """CompressorMagnitude.java:78-140 + Compressor.java:97-110: keep |c| >= mean|c| * threshold, zero the rest."""
+    x = splitmix_uniform(17 + len(shape), shape) * 3.0
+    c = jw.CompressorMagnitude(thr)
+    y = c.compress(x)
+    mag = float(np.mean(np.abs(x)))
+    assert abs(c.getMagnitude() - mag) <= 1e-13 * mag
+    cut = mag * thr
+    sure = np.abs(np.abs(x) - cut) > 1e-12 * max(cut, 1.0)     # the summation order differs from the JVM's by O(1e-16)
+    exp = np.where(np.abs(x) >= cut, x, 0.0)
+    assert np.array_equal(y[sure], exp[sure])
+    assert np.all((y == x) | (y == 0.0))
+    assert c.calcCompressionRate(y) == pytest.approx(100.0 * np.count_nonzero(y == 0.0) / y.size)
+    assert jw.CompressorMagnitude(-1.0).getThreshold() == 1.0
+
+
+def test_windows_then_compressor_on_device(jw, gpu_ctx, oracle):
+    """The reference's motivating chain on device buffers: sliding-window MODWT, then magnitude thresholding, one stream."""
+    import torch
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaMODWTTransform(w)
+    total, window, hop, J = 20000, 512, 64, 8
+    x = chirp(1, total)[0]
+    nwin = (total - window) // hop + 1
+    dx = torch.from_numpy(x).cuda()
+    dc = torch.empty((nwin, J + 1, window), dtype=torch.float64, device="cuda")
+    dm = torch.zeros(1, dtype=torch.float64, device="cuda")
+    lib = jw._native.load()
+    g, h = t._filters()
+    g = np.ascontiguousarray(g)
+    h = np.ascontiguousarray(h)
+    dp = ctypes.POINTER(ctypes.c_double)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+    rc = lib.jwc_modwt_forward_windows_dev(gpu_ctx.handle, 0, st, ctypes.c_void_p(dx.data_ptr()),
+                                           ctypes.c_void_p(dc.data_ptr()), total, window, hop, J,
+                                           g.ctypes.data_as(dp), h.ctypes.data_as(dp), len(g), 0)
+    assert rc == 0, lib.jwc_last_error()
+    raw = dc.clone()
+    rc = lib.jwc_compress_magnitude_dev(gpu_ctx.handle, 0, st, ctypes.c_void_p(dc.data_ptr()),
+                                        ctypes.c_void_p(dc.data_ptr()), dc.numel(), 1.0, ctypes.c_void_p(dm.data_ptr()))
+    assert rc == 0, lib.jwc_last_error()
+    torch.cuda.synchronize()
+    wins = np.lib.stride_tricks.sliding_window_view(x, window)[::hop][:nwin]
+    ref, _ = _modwt_oracle(oracle, w, np.ascontiguousarray(wins), J)
+    assert _maxerr(raw.cpu().numpy(), ref, x) <= TOL
+    mag = float(np.mean(np.abs(ref)))
+    assert abs(float(dm.item()) - mag) <= 1e-12 * mag
+    y = dc.cpu().numpy()
+    sure = np.abs(np.abs(ref) - mag) > 1e-9
+    assert np.array_equal(y[sure] != 0.0, (np.abs(ref) >= mag)[sure])
