@@ -148,7 +148,10 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
   int rc = JWC_ERR_UNSUPPORTED;
   if (!generic) {
     switch (op) {
-      case Op::ModwtFwd: rc = fast_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, d2.hop); break;
+      case Op::ModwtFwd:
+        rc = small_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, d2.hop);
+        if (rc == JWC_ERR_UNSUPPORTED) rc = fast_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, d2.hop);
+        break;
       case Op::ModwtInv: rc = fast_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L); break;
       case Op::FwtFwd: rc = fast_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
       case Op::FwtInv: rc = fast_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
@@ -564,6 +567,7 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "h2d_chunk_mb")) return &t.h2d_chunk_mb;
   if (!strcmp(key, "h2d_buffers")) return &t.h2d_buffers;
   if (!strcmp(key, "dwt_tail")) return &t.dwt_tail;
+  if (!strcmp(key, "modwt_small")) return &t.modwt_small;
   if (!strcmp(key, "force_generic")) return &t.force_generic;
   if (!strcmp(key, "l2_prefetch")) return &t.l2_prefetch;
   return nullptr;

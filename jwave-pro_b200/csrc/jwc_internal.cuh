@@ -49,6 +49,7 @@ struct Tuning {
   int dwt_smem = 0;
   int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
+  int modwt_small = 0;      // whole-signal forward MODWT kernel for n <= 2048: 0 = auto, -1 = off, 1 = whenever it fits
   int dwt_tail = 0;         // warp-per-signal pyramid tail for short signals: 0 = auto, -1 = off
   int h2d_buffers = 0;      // host pipeline staging depth (1..4), 0 = auto
   int force_generic = 0;
@@ -130,6 +131,9 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);
 int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+// whole-signal-in-shared-memory forward MODWT for short signals / analysis windows (jwc_modwt_small.cu)
+int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);
 // warp-per-signal deep end of the FWT pyramid for short signals (jwc_dwt_tail.cu)
 constexpr int kDwtTailLen = 512;        // block length at which the tail takes over
 constexpr int64_t kDwtTailMaxN = 16384; // longest signal that uses it

@@ -128,6 +128,10 @@ inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP,
   const double flops = 4.0 * in.L * k * (1.0 + avg_hrem / T) / std::max(eff, 0.3);
   const double tm = bytes / 5.5, tc = flops / 32.0;
   *est_time = std::max(tm, tc) + 0.35 * std::min(tm, tc) + 2.0;
+  // a CTA costs about 4 ns of GPU time whatever it does (launch, barriers, mbarrier round trips): measured on windows
+  // of 512 samples, where a phase-split pass with 32-sample CTAs ran at 127 ps/sample; the per-level kernels win there
+  const double cta_samples = (double)P * T;
+  if (cta_samples < 1024.0) *est_time += 4000.0 / cta_samples;
   return true;
 }
 

@@ -1,0 +1,148 @@
+// jwc_modwt_small.cu -- forward MODWT of SHORT signals (analysis windows): the whole signal lives in shared memory.
+//
+// The tile kernels of jwc_modwt_fast.cu carry a halo of (L-1)(2^J - 1) samples; for a 512-sample window at J = 8 that
+// halo is 1785 samples (db4) -- 3.5x the signal, all of it recomputed.  A short signal needs no halo at all: the CTA
+// keeps V_(j-1) of its signals in shared memory, indexes it circularly (any n, not only 2^p) and writes W_j straight
+// to its row; HBM traffic is the algorithmic minimum (n read, (J+1) n written) and the arithmetic is exactly
+// 2 L J n multiply-adds.  128 threads per CTA, S = 4, 2 or 1 signals per CTA (32..128 threads per signal).
+//
+// Arithmetic: MODWTTransform.java:290-304 + circularConvolve :677-690,
+//   W_j[t] = sum_m h[m] V_(j-1)[(t - m 2^(j-1)) mod n],  V_j likewise with g (m ascending, FMA).
+#include "jwc_internal.cuh"
+
+namespace jwc {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+struct SmallArgs {
+  const double* x;
+  double* coeffs;
+  int64_t x_sig;     // distance between consecutive input signals (windows may overlap)
+  int64_t batch;
+  int n, J, L;
+  int per_cta;       // signals per CTA
+};
+
+constexpr int kChain = 4;   // outputs per work item of the register-blocked path
+
+// LT = compile-time filter length (taps become constant-bank operands, the chain loop unrolls), 0 = run-time length.
+// Register-blocked path (LT > 0, n divisible by kChain * stride): a thread produces the kChain outputs
+// t0, t0 + s, ..., t0 + (kChain-1) s, which share their inputs -- kChain + L - 1 shared-memory loads instead of
+// kChain * L.  Other shapes (any n, any L) take the one-output-at-a-time loop.
+template <int LT>
+__global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_constant__ SmallArgs a,
+                                                                   const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  const int tps = kThreads / a.per_cta;            // threads per signal
+  const int s_local = threadIdx.x / tps, r = threadIdx.x % tps;
+  const int64_t sig = (int64_t)blockIdx.x * a.per_cta + s_local;
+  const bool live = sig < a.batch;
+  const int n = a.n;
+  double* cur = sm + (size_t)s_local * 2 * n;
+  double* nxt = cur + n;
+  if (live) {
+    const double* x = a.x + sig * a.x_sig;
+    for (int t = r; t < n; t += tps) cur[t] = x[t];
+  }
+  __syncthreads();
+  double* co = a.coeffs + (live ? sig : 0) * (int64_t)(a.J + 1) * n;
+  for (int j = 1; j <= a.J; j++) {
+    // stride 2^(j-1) mod n without overflow (n < 2^31, j <= 30)
+    const int step = (int)((((int64_t)1) << (j - 1)) % n);
+    const bool last = (j == a.J);
+    if (live) {
+      double* w_row = co + (int64_t)(j - 1) * n;
+      double* v_row = co + (int64_t)a.J * n;
+      bool done = false;
+      if constexpr (LT > 0) {
+        if (step > 0 && n % (step * kChain) == 0) {
+          const int items = n / kChain;
+          int back = ((LT - 1) * step) % n;          // inputs start (L-1) strides before the first output
+          for (int it = r; it < items; it += tps) {
+            const int a0 = it % step, grp = it / step;
+            const int t0 = a0 + grp * kChain * step;
+            int idx = t0 - back;
+            if (idx < 0) idx += n;
+            double aw[kChain], av[kChain];
+#pragma unroll
+            for (int q = 0; q < kChain; q++) aw[q] = av[q] = 0.0;
+#pragma unroll
+            for (int u = -(LT - 1); u <= kChain - 1; u++) {
+              const double v = cur[idx];
+#pragma unroll
+              for (int q = 0; q < kChain; q++) {
+                const int m = q - u;                 // output t0 + q s takes input t0 + u s with tap m
+                if (m >= 0 && m < LT) {
+                  aw[q] = fma(v, f.f1[m], aw[q]);
+                  av[q] = fma(v, f.f0[m], av[q]);
+                }
+              }
+              idx += step;
+              if (idx >= n) idx -= n;
+            }
+#pragma unroll
+            for (int q = 0; q < kChain; q++) {
+              const int t = t0 + q * step;
+              w_row[t] = aw[q];
+              if (last) v_row[t] = av[q];
+              else nxt[t] = av[q];
+            }
+          }
+          done = true;
+        }
+      }
+      if (!done) {
+        for (int t = r; t < n; t += tps) {
+          double sw = 0.0, sv = 0.0;
+          int idx = t;
+          for (int m = 0; m < a.L; m++) {
+            const double v = cur[idx];
+            sw = fma(v, f.f1[m], sw);
+            sv = fma(v, f.f0[m], sv);
+            idx -= step;
+            if (idx < 0) idx += n;
+          }
+          w_row[t] = sw;
+          if (last) v_row[t] = sv;
+          else nxt[t] = sv;
+        }
+      }
+    }
+    __syncthreads();
+    double* tmp = cur; cur = nxt; nxt = tmp;
+  }
+}
+
+}  // namespace
+
+// Returns JWC_ERR_UNSUPPORTED when the shape is not one this kernel is meant for.
+int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig) {
+  (void)dev;
+  if (x_sig <= 0) x_sig = n;
+  const int mode = ctx->tune.modwt_small;
+  if (mode < 0 || n > 2048 || n < 1 || levels > 30 || L < 1) return JWC_ERR_UNSUPPORTED;
+  // worth it once the tile kernels' halo is comparable to the signal itself
+  const int64_t halo = (int64_t)(L - 1) * ((((int64_t)1) << levels) - 1);
+  if (mode == 0 && 3 * halo <= n) return JWC_ERR_UNSUPPORTED;   // measured: Haar J8 on 512 (halo 255) small 1.98 ms vs 2.46; db4 J3 (halo 49) 1.83 vs 1.16
+  SmallArgs a{};
+  a.x = d_x; a.coeffs = d_coeffs; a.x_sig = x_sig; a.batch = batch; a.n = (int)n; a.J = levels; a.L = L;
+  a.per_cta = n <= 512 ? 4 : (n <= 1024 ? 2 : 1);
+  const int64_t ctas = (batch + a.per_cta - 1) / a.per_cta;
+  if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)a.per_cta * 2 * (size_t)n * sizeof(double);
+  switch (L) {
+#define JWC_SCASE(LL) case LL: modwt_small_fwd_kernel<LL><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+    JWC_SCASE(2) JWC_SCASE(4) JWC_SCASE(6) JWC_SCASE(8) JWC_SCASE(10) JWC_SCASE(12) JWC_SCASE(14) JWC_SCASE(16)
+    JWC_SCASE(18) JWC_SCASE(20)
+#undef JWC_SCASE
+    default: modwt_small_fwd_kernel<0><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+  }
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+}  // namespace jwc
