@@ -29,6 +29,8 @@ struct TailArgs {
   int L;
 };
 
+// LT = compile-time filter length (taps become constant-bank operands, tap loops unroll); 0 = run-time length
+template <int LT>
 __global__ void __launch_bounds__(kWarps * 32) tail_fwd_kernel(const __grid_constant__ TailArgs a,
                                                                 const __grid_constant__ FilterPair f) {
   extern __shared__ double sm[];
@@ -47,10 +49,19 @@ __global__ void __launch_bounds__(kWarps * 32) tail_fwd_kernel(const __grid_cons
     const bool last = (lev == a.nlev - 1);
     for (int i = lane; i < half; i += 32) {
       double lo = 0.0, hi = 0.0;
-      for (int j = 0; j < a.L; j++) {
-        const double v = cur[(2 * i + j) & mask];
-        lo = fma(v, f.f0[j], lo);
-        hi = fma(v, f.f1[j], hi);
+      if constexpr (LT > 0) {
+#pragma unroll
+        for (int j = 0; j < LT; j++) {
+          const double v = cur[(2 * i + j) & mask];
+          lo = fma(v, f.f0[j], lo);
+          hi = fma(v, f.f1[j], hi);
+        }
+      } else {
+        for (int j = 0; j < a.L; j++) {
+          const double v = cur[(2 * i + j) & mask];
+          lo = fma(v, f.f0[j], lo);
+          hi = fma(v, f.f1[j], hi);
+        }
       }
       out[half + i] = hi;
       if (last) out[i] = lo;
@@ -62,6 +73,7 @@ __global__ void __launch_bounds__(kWarps * 32) tail_fwd_kernel(const __grid_cons
   }
 }
 
+template <int LT>
 __global__ void __launch_bounds__(kWarps * 32) tail_inv_kernel(const __grid_constant__ TailArgs a,
                                                                 const __grid_constant__ FilterPair f) {
   extern __shared__ double sm[];
@@ -83,14 +95,30 @@ __global__ void __launch_bounds__(kWarps * 32) tail_inv_kernel(const __grid_cons
     const int h = half << 1, mask = half - 1;
     const bool last = (lev == a.nlev - 1);
     const double* hi = coef + half;
-    for (int k = lane; k < h; k += 32) {
-      double acc = 0.0;
-      for (int j = k & 1; j < a.L; j += 2) {
-        const int i = ((k - j) >> 1) & mask;    // (2i + j) mod h == k
-        acc = fma(hi[i], f.f1[j], fma(lo[i], f.f0[j], acc));
+    if constexpr (LT > 0) {
+      // one output PAIR (2q, 2q+1) per step: both use the coefficient rows q - m, m < L/2
+      for (int q = lane; q < half; q += 32) {
+        double e = 0.0, o = 0.0;
+#pragma unroll
+        for (int m = 0; m < LT / 2; m++) {
+          const int i = (q - m) & mask;
+          const double cl = lo[i], ch = hi[i];
+          e = fma(ch, f.f1[2 * m], fma(cl, f.f0[2 * m], e));
+          o = fma(ch, f.f1[2 * m + 1], fma(cl, f.f0[2 * m + 1], o));
+        }
+        if (last) { dst[2 * q] = e; dst[2 * q + 1] = o; }
+        else { nxt[2 * q] = e; nxt[2 * q + 1] = o; }
       }
-      if (last) dst[k] = acc;
-      else nxt[k] = acc;
+    } else {
+      for (int k = lane; k < h; k += 32) {
+        double acc = 0.0;
+        for (int j = k & 1; j < a.L; j += 2) {
+          const int i = ((k - j) >> 1) & mask;    // (2i + j) mod h == k
+          acc = fma(hi[i], f.f1[j], fma(lo[i], f.f0[j], acc));
+        }
+        if (last) dst[k] = acc;
+        else nxt[k] = acc;
+      }
     }
     __syncwarp();
     lo = nxt;
@@ -104,8 +132,20 @@ int launch_tail(jwc_ctx* ctx, cudaStream_t st, const TailArgs& a, const FilterPa
   if (ctas <= 0) return JWC_OK;
   if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
   const size_t smem = (size_t)kWarps * (inverse ? 2 * a.h0 : a.h0 + a.h0 / 2) * sizeof(double);
-  if (inverse) tail_inv_kernel<<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);
-  else         tail_fwd_kernel<<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);
+  switch ((a.L & 1) ? 0 : a.L) {
+#define JWC_TCASE(LL)                                                                          \
+  case LL:                                                                                     \
+    if (inverse) tail_inv_kernel<LL><<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);         \
+    else         tail_fwd_kernel<LL><<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);         \
+    break;
+    JWC_TCASE(2) JWC_TCASE(4) JWC_TCASE(6) JWC_TCASE(8) JWC_TCASE(10) JWC_TCASE(12) JWC_TCASE(14) JWC_TCASE(16)
+    JWC_TCASE(18) JWC_TCASE(20)
+#undef JWC_TCASE
+    default:
+      if (inverse) tail_inv_kernel<0><<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);
+      else         tail_fwd_kernel<0><<<(unsigned)ctas, kWarps * 32, smem, st>>>(a, f);
+      break;
+  }
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());
   return JWC_OK;
