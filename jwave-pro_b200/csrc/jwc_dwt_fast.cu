@@ -612,6 +612,11 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);
   if (steps == 0) return JWC_ERR_UNSUPPORTED;   // plain copy: the generic path handles it
+  if (!tree) {   // 512 < n <= 4096: the whole signal in shared memory, levels in place (jwc_dwt_whole.cu)
+    // (forward: only when it takes every level -- for a deep transform the first tile pass + the warp tail measured
+    // faster than this kernel + the tail, 1.73 vs 1.83 ms on 131 072 rows of 4096; the inverse is the other way round)
+    if (whole_dwt_levels(ctx, n, steps, L) == steps) return whole_dwt(ctx, st, d_in, d_out, batch, n, steps, f, L, ld, false);
+  }
   // short signals: levels below kDwtTailLen samples go to the warp-per-signal tail kernel (jwc_dwt_tail.cu)
   const int lt = (!tree && ctx->tune.dwt_tail >= 0) ? dwt_tail_start(n, steps) : -1;
   if (lt == 0) return dwt_tail_forward(ctx, st, d_in, ld, d_out, ld, (int)n, steps, batch, f, L);
@@ -679,6 +684,20 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);   // the reverse loops undo exactly the forward's steps
   if (steps == 0) return JWC_ERR_UNSUPPORTED;
+  if (!tree) {
+    const int top = whole_dwt_levels(ctx, n, steps, L);
+    if (top == steps) return whole_dwt(ctx, st, d_in, d_out, batch, n, steps, f, L, ld, true);
+    if (top > 0) {
+      // deep end first (warp per signal) into scratch, then the big levels with that approximation as their head
+      Scratch ws(st);
+      const int64_t h0 = n >> top;
+      double* a_top = ws.get((size_t)batch * h0);
+      if (!a_top) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+      const int rc = dwt_tail_inverse(ctx, st, d_in, ld, a_top, h0, (int)h0, steps - top, batch, f, L);
+      if (rc != JWC_OK) return rc;
+      return whole_dwt(ctx, st, d_in, d_out, batch, n, top, f, L, ld, true, a_top, h0);
+    }
+  }
   const int lt = (!tree && ctx->tune.dwt_tail >= 0) ? dwt_tail_start(n, steps) : -1;
   if (lt == 0) return dwt_tail_inverse(ctx, st, d_in, ld, d_out, ld, (int)n, steps, batch, f, L);
   const int plan_steps = lt > 0 ? lt : steps;

@@ -11,6 +11,7 @@
 // FastWaveletTransform.java:85-99 / :133-151.  The block length h is a power of two, so `mod h` is a mask and blocks
 // shorter than the filter wrap several times without special cases.
 #include "jwc_internal.cuh"
+#include "jwc_tma.cuh"
 
 namespace jwc {
 
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(kWarps * 32) tail_fwd_kernel(const __grid_cons
   double* cur = sm + (size_t)warp * (a.h0 + a.h0 / 2);
   double* nxt = cur + a.h0;
   const double* x = a.src + sig * a.src_sig;
-  for (int t = lane; t < a.h0; t += 32) cur[t] = x[t];
+  for (int t = lane; t < a.h0; t += 32) ptx::cp_async8(cur + t, x + t);   // all pieces in flight together
+  ptx::cp_async_commit_wait_all();
   __syncwarp();
   double* out = a.dst + sig * a.n;
   int h = a.h0;
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(kWarps * 32) tail_inv_kernel(const __grid_cons
   double* nxt = cur + a.h0 / 2;
   const double* c = a.src + sig * a.n;
   double* dst = a.dst + sig * a.dst_sig;
-  for (int t = lane; t < a.h0; t += 32) coef[t] = c[t];
+  for (int t = lane; t < a.h0; t += 32) ptx::cp_async8(coef + t, c + t);
+  ptx::cp_async_commit_wait_all();
   __syncwarp();
   int half = a.h0 >> a.nlev;                    // length of the deepest approximation (>= 1)
   const double* lo = coef;

@@ -1,0 +1,214 @@
+// jwc_dwt_whole.cu -- FWT of signals of 1024..4096 samples (image rows, analysis windows): the whole signal in shared
+// memory, every level in place, one launch.
+//
+// For short signals the tile kernels of jwc_dwt_fast.cu need a second launch with one tiny CTA per signal for the deep
+// levels and their inverse reads the detail blocks level by level.  Here a CTA owns one signal: it loads the n
+// samples (forward) or the n coefficients (inverse) once, coalesced, runs all levels IN PLACE in shared memory -- the
+// pyramid layout [A_J | D_J | ... | D_1] is exactly what in-place analysis of a shrinking prefix produces, and what
+// in-place synthesis of a growing prefix consumes -- and stores the n results once, coalesced.  HBM traffic is the
+// algorithmic 16 B/sample; no halo, no scratch.
+//
+// Work split inside a level: a thread owns R consecutive outputs (analysis: R low/high pairs from 2R + L - 2 inputs,
+// read as R + L/2 - 1 double2; synthesis: R output pairs from R + L/2 - 1 rows of each half).  R is odd, so the
+// threads' windows start R double2 (or R doubles) apart and a warp's shared loads fall into distinct banks.  Results
+// stay in registers across the barrier that separates the level's reads from its in-place writes.
+//
+// Arithmetic: Wavelet.java:236-260 / :277-303 (fused multiply-add), loops FastWaveletTransform.java:85-99 / :133-151.
+#include "jwc_internal.cuh"
+#include "jwc_tma.cuh"
+
+namespace jwc {
+
+namespace {
+
+struct WholeArgs {
+  const double* src;
+  const double* prefix;   // inverse only: A at the deepest level of this launch when it comes from another buffer
+  double* dst;
+  int64_t src_sig, dst_sig, prefix_sig;
+  int prefix_len;
+  int n, steps;
+  int vec;   // 1: rows are 16-byte aligned (double2 copies in and out)
+};
+
+// asynchronous copies: every thread's pieces are in flight together (a plain load/store loop pays one global-memory
+// latency per iteration)
+__device__ __forceinline__ void load_row(double* sm, const double* x, int n, int vec) {
+  if (vec) {
+    for (int t = 2 * threadIdx.x; t < n; t += 2 * blockDim.x) ptx::cp_async16(sm + t, x + t);
+  } else {
+    for (int t = threadIdx.x; t < n; t += blockDim.x) ptx::cp_async8(sm + t, x + t);
+  }
+  ptx::cp_async_commit_wait_all();
+}
+// the same, but samples [0, plen) come from `pre` (the approximation rebuilt by the tail kernel)
+__device__ __forceinline__ void load_row_split(double* sm, const double* x, const double* pre, int plen, int n, int vec) {
+  if (vec) {
+    for (int t = 2 * threadIdx.x; t < n; t += 2 * blockDim.x) ptx::cp_async16(sm + t, (t < plen ? pre : x) + t);
+  } else {
+    for (int t = threadIdx.x; t < n; t += blockDim.x) ptx::cp_async8(sm + t, (t < plen ? pre : x) + t);
+  }
+  ptx::cp_async_commit_wait_all();
+}
+__device__ __forceinline__ void store_row(double* y, const double* sm, int n, int vec) {
+  if (vec) {
+    for (int t = 2 * threadIdx.x; t < n; t += 2 * blockDim.x)
+      *reinterpret_cast<double2*>(y + t) = *reinterpret_cast<const double2*>(sm + t);
+  } else {
+    for (int t = threadIdx.x; t < n; t += blockDim.x) y[t] = sm[t];
+  }
+}
+
+// One analysis level in place on sm[0..h).
+template <int L, int R>
+__device__ __forceinline__ void fwd_level(double* sm, int h, const FilterPair& f) {
+  const int half = h >> 1, mask = h - 1;
+  const int i0 = threadIdx.x * R;
+  double lo[R], hi[R];
+  const bool active = i0 < half;
+  if (active) {
+    constexpr int W = R + L / 2 - 1;
+    double2 win[W];
+#pragma unroll
+    for (int t = 0; t < W; t++) win[t] = *reinterpret_cast<const double2*>(sm + ((2 * i0 + 2 * t) & mask));
+#pragma unroll
+    for (int q = 0; q < R; q++) lo[q] = hi[q] = 0.0;
+#pragma unroll
+    for (int m = 0; m < L; m++)
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const double v = (m & 1) ? win[q + m / 2].y : win[q + m / 2].x;   // x[2(i0+q) + m]
+        lo[q] = fma(v, f.f0[m], lo[q]);
+        hi[q] = fma(v, f.f1[m], hi[q]);
+      }
+  }
+  __syncthreads();   // every read of this level is done: write [lo | hi] over the prefix
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < R; q++)
+      if (i0 + q < half) {
+        sm[i0 + q] = lo[q];
+        sm[half + i0 + q] = hi[q];
+      }
+  }
+  __syncthreads();
+}
+
+template <int L, int R>
+__device__ __forceinline__ void inv_level(double* sm, int h, const FilterPair& f) {
+  constexpr int M = L / 2;
+  const int half = h >> 1, mask = half - 1;
+  const int q0 = threadIdx.x * R;
+  double e[R], o[R];
+  const bool active = q0 < half;
+  if (active) {
+    constexpr int W = R + M - 1;
+    double wl[W], wh[W];
+#pragma unroll
+    for (int t = 0; t < W; t++) {
+      const int i = (q0 - (M - 1) + t) & mask;   // two's-complement mask = mod half (also when L/2 > half)
+      wl[t] = sm[i];
+      wh[t] = sm[half + i];
+    }
+#pragma unroll
+    for (int u = 0; u < R; u++) e[u] = o[u] = 0.0;
+#pragma unroll
+    for (int m = M - 1; m >= 0; m--)
+#pragma unroll
+      for (int u = 0; u < R; u++) {
+        const double cl = wl[u - m + M - 1], ch = wh[u - m + M - 1];
+        e[u] = fma(ch, f.f1[2 * m], fma(cl, f.f0[2 * m], e[u]));
+        o[u] = fma(ch, f.f1[2 * m + 1], fma(cl, f.f0[2 * m + 1], o[u]));
+      }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < R; u++)
+      if (q0 + u < half) {
+        sm[2 * (q0 + u)] = e[u];
+        sm[2 * (q0 + u) + 1] = o[u];
+      }
+  }
+  __syncthreads();
+}
+
+template <int L, int R>
+__global__ void __launch_bounds__(448) whole_fwd_kernel(const __grid_constant__ WholeArgs a,
+                                                        const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  const int n = a.n;
+  load_row(sm, a.src + (int64_t)blockIdx.x * a.src_sig, n, a.vec);
+  __syncthreads();
+  int h = n;
+  for (int lev = 0; lev < a.steps; lev++, h >>= 1) fwd_level<L, R>(sm, h, f);
+  store_row(a.dst + (int64_t)blockIdx.x * a.dst_sig, sm, n, a.vec);
+}
+
+template <int L, int R>
+__global__ void __launch_bounds__(448) whole_inv_kernel(const __grid_constant__ WholeArgs a,
+                                                        const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  const int n = a.n;
+  if (a.prefix)
+    load_row_split(sm, a.src + (int64_t)blockIdx.x * a.src_sig, a.prefix + (int64_t)blockIdx.x * a.prefix_sig,
+                   a.prefix_len, n, a.vec);
+  else
+    load_row(sm, a.src + (int64_t)blockIdx.x * a.src_sig, n, a.vec);
+  __syncthreads();
+  int h = n >> (a.steps - 1);
+  for (int lev = 0; lev < a.steps; lev++, h <<= 1) inv_level<L, R>(sm, h, f);
+  store_row(a.dst + (int64_t)blockIdx.x * a.dst_sig, sm, n, a.vec);
+}
+
+template <int L>
+int launch_whole(jwc_ctx* ctx, cudaStream_t st, const WholeArgs& a, const FilterPair& f, int64_t batch, bool inverse) {
+  constexpr int R = (L <= 10) ? 7 : 5;
+  int threads = ((a.n / 2 + R - 1) / R + 31) / 32 * 32;   // one thread per run of the largest level
+  if (threads > 448) return JWC_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)a.n * sizeof(double);
+  if (inverse) whole_inv_kernel<L, R><<<(unsigned)batch, threads, smem, st>>>(a, f);
+  else         whole_fwd_kernel<L, R><<<(unsigned)batch, threads, smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+}  // namespace
+
+// Levels the whole-signal kernel takes for a signal of length n with `steps` levels to do: all of them when the
+// deepest block keeps >= 128 samples, otherwise the levels whose block is longer than kDwtTailLen (the rest goes to the
+// warp-per-signal tail).  Every level costs the CTA two barriers -- fine for big levels, a loss for the deep end of a
+// full-depth transform (measured, n = 4096: all 12 levels here 2.13 ms, 3 levels here + 9 in the tail ~1.5 ms).
+// 0: this kernel does not apply.
+int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L) {
+  if (ctx->tune.dwt_whole < 0 || n <= kDwtTailLen || n > 4096 || (n & (n - 1)) || steps < 1) return 0;
+  if (L < 2 || L > 20 || (L & 1)) return 0;
+  if (ctx->tune.dwt_whole > 0 || (n >> steps) >= 128) return steps;
+  int top = 0;
+  while ((n >> top) > kDwtTailLen) top++;
+  return top < steps ? top : steps;
+}
+
+// `steps` levels of the FWT (pyramid) of batch signals of length n in (512, 4096] (see whole_dwt_levels).  Inverse with
+// d_prefix != nullptr: the deepest approximation (n >> steps samples per signal, stride prefix_sig) is read from
+// d_prefix instead of the head of d_in.
+int whole_dwt(jwc_ctx* ctx, cudaStream_t st, const double* d_in, double* d_out, int64_t batch, int64_t n, int steps,
+              const FilterPair& f, int L, int64_t ld, bool inverse, const double* d_prefix, int64_t prefix_sig) {
+  if (n <= kDwtTailLen || n > 4096 || (n & (n - 1)) || steps < 1 || ((int64_t)1 << steps) > n) return JWC_ERR_UNSUPPORTED;
+  if (L < 2 || L > 20 || (L & 1) || batch > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  WholeArgs a{};
+  a.src = d_in; a.dst = d_out; a.src_sig = ld; a.dst_sig = ld; a.n = (int)n; a.steps = steps;
+  a.prefix = inverse ? d_prefix : nullptr; a.prefix_sig = prefix_sig; a.prefix_len = (int)(n >> steps);
+  a.vec = (((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_prefix)) & 15) == 0 &&
+           (ld & 1) == 0 && (prefix_sig & 1) == 0 && (a.prefix_len & 1) == 0) ? 1 : 0;
+  switch (L) {
+#define JWC_WCASE(LL) case LL: return launch_whole<LL>(ctx, st, a, f, batch, inverse);
+    JWC_WCASE(2) JWC_WCASE(4) JWC_WCASE(6) JWC_WCASE(8) JWC_WCASE(10) JWC_WCASE(12) JWC_WCASE(14) JWC_WCASE(16)
+    JWC_WCASE(18) JWC_WCASE(20)
+#undef JWC_WCASE
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace jwc

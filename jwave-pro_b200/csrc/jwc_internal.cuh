@@ -50,6 +50,7 @@ struct Tuning {
   int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
   int modwt_small = 0;      // whole-signal forward MODWT kernel for n <= 2048: 0 = auto, -1 = off, 1 = whenever it fits
+  int dwt_whole = 0;        // whole-signal in-place FWT kernel for 512 < n <= 4096: 0 = auto, -1 = off
   int dwt_tail = 0;         // warp-per-signal pyramid tail for short signals: 0 = auto, -1 = off
   int h2d_buffers = 0;      // host pipeline staging depth (1..4), 0 = auto
   int force_generic = 0;
@@ -131,6 +132,11 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);
 int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+// whole-signal in-place FWT for 512 < n <= 4096 (jwc_dwt_whole.cu)
+int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L);
+int whole_dwt(jwc_ctx* ctx, cudaStream_t st, const double* d_in, double* d_out, int64_t batch, int64_t n, int steps,
+              const FilterPair& f, int L, int64_t ld, bool inverse, const double* d_prefix = nullptr,
+              int64_t prefix_sig = 0);
 // whole-signal-in-shared-memory forward MODWT for short signals / analysis windows (jwc_modwt_small.cu)
 int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
                         int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);

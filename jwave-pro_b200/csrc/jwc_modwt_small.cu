@@ -9,6 +9,7 @@
 // Arithmetic: MODWTTransform.java:290-304 + circularConvolve :677-690,
 //   W_j[t] = sum_m h[m] V_(j-1)[(t - m 2^(j-1)) mod n],  V_j likewise with g (m ascending, FMA).
 #include "jwc_internal.cuh"
+#include "jwc_tma.cuh"
 
 namespace jwc {
 
@@ -44,8 +45,9 @@ __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_
   double* nxt = cur + n;
   if (live) {
     const double* x = a.x + sig * a.x_sig;
-    for (int t = r; t < n; t += tps) cur[t] = x[t];
+    for (int t = r; t < n; t += tps) ptx::cp_async8(cur + t, x + t);   // all pieces in flight together
   }
+  ptx::cp_async_commit_wait_all();
   __syncthreads();
   double* co = a.coeffs + (live ? sig : 0) * (int64_t)(a.J + 1) * n;
   for (int j = 1; j <= a.J; j++) {

@@ -648,3 +648,30 @@ def test_windows_then_compressor_on_device(jw, gpu_ctx, oracle):
     y = dc.cpu().numpy()
     sure = np.abs(np.abs(ref) - mag) > 1e-9
     assert np.array_equal(y[sure] != 0.0, (np.abs(ref) >= mag)[sure])
+
+
+@pytest.mark.parametrize("cls,n,lvl,batch,force", [
+    ("Haar1", 1024, 2, 7, 0), ("Daubechies4", 2048, 3, 5, 0), ("Daubechies8", 4096, 4, 3, 0),
+    ("Symlet10", 4096, 5, 2, 0), ("Daubechies4", 4096, 12, 3, 1), ("Daubechies6", 1024, 10, 4, 1),
+])
+def test_fwt_whole_signal_kernel(jw, oracle, cls, n, lvl, batch, force):
+    """Signals of 1024..4096 samples: the whole signal in shared memory, levels in place (jwc_dwt_whole.cu); by default
+    for shallow transforms, forced here for full depth as well."""
+    ctx = jw.Context([0])
+    ctx.set_tuning("dwt_whole", force)
+    w = jw.wavelets.create(cls)
+    t = jw.CudaFastWaveletTransform(w, context=ctx)
+    X = splitmix_uniform(n + lvl, (batch, n))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.batch("fwt_fwd", X, lvl, s, wv, nthreads=8)
+    l0 = ctx.launch_count()
+    got = t.forwardBatch(X, lvl)
+    assert ctx.launch_count() - l0 == 1          # one launch: the whole-signal kernel took it
+    assert _maxerr(got, ref, X) <= TOL
+    rref = oracle.batch("fwt_rev", ref, lvl, w.getScalingReConstruction(), w.getWaveletReConstruction(), nthreads=8)
+    l0 = ctx.launch_count()
+    back = t.reverseBatch(ref, lvl)
+    assert ctx.launch_count() - l0 == 1
+    assert _maxerr(back, rref, X) <= TOL
+    assert _maxerr(t.reverseBatch(got, lvl), X, X) <= PR_TOL
+    ctx.close()
