@@ -362,7 +362,7 @@ def main():
         else:
             f_call = lambda k: et.forwardBatch(X, levels, out=Cs[k % 2])  # noqa: E731
             i_call = lambda k: et.reverseBatch(Cs[k % 2], levels, out=R)  # noqa: E731
-        psteps = 2 * esteps
+        psteps = max(20, 4 * esteps)   # long enough that the one-call pipeline fill is < 5 % of the timed region
 
         def pipeline(ex, steps):
             ff = ex.submit(f_call, 0)

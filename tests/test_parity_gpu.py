@@ -470,6 +470,8 @@ def test_modwt_single_series_split_over_devices(jw, oracle, cls, n, J):
     ("Symlet10", 256, 96 // 3, 5, 2, 2),    # L = 20: two fused levels at a time
     ("Daubechies5", 128, 64, 7, 6, 2),      # smallest height the fused launches take
     ("Daubechies10", 2048, 64, 2, 6, 1),
+    ("Daubechies4", 64, 1, 6, 0, 3),        # a single column
+    ("Haar1", 2, 2, 1, 1, 1),
 ])
 def test_2d_matches_oracle(jw, gpu_ctx, oracle, kind, cls, rows, cols, lvl_m, lvl_n, batch):
     w = jw.wavelets.create(cls)
