@@ -57,6 +57,9 @@ def main():
 
         f_ms = timed(lambda: t.forward2DDevice(x.data_ptr(), c.data_ptr(), batch, rows, cols, lm, ln, stream=st.cuda_stream))
         i_ms = timed(lambda: t.reverse2DDevice(c.data_ptr(), r.data_ptr(), batch, rows, cols, lm, ln, stream=st.cuda_stream))
+        # the first timed loop of a new shape also pays one-time costs (module load of new kernel instantiations, pool
+        # growth while the host runs ahead): time the forward again and keep the steady-state figure
+        f_ms = min(f_ms, timed(lambda: t.forward2DDevice(x.data_ptr(), c.data_ptr(), batch, rows, cols, lm, ln, stream=st.cuda_stream)))
         row_ms = timed(lambda: t.forwardDevice(x.data_ptr(), c.data_ptr(), batch * rows, cols, ln, stream=st.cuda_stream))
         t.forward2DDevice(x.data_ptr(), c.data_ptr(), batch, rows, cols, lm, ln, stream=st.cuda_stream)
         t.reverse2DDevice(c.data_ptr(), r.data_ptr(), batch, rows, cols, lm, ln, stream=st.cuda_stream)
