@@ -38,16 +38,32 @@ WORKLOADS = {
     "c3haar": ("fwt", "Haar1", 20, 1024, 1 << 20),
     "c3db8": ("fwt", "Daubechies8", 20, 1024, 1 << 20),
     "c4": ("wpt", "Symlet8", 6, 512, 65536),
+    # SURVEY section 8f rows (not BASELINE configs): 2-D FWT of 32 matrices 4096 x 4096 at full depth (levels = lvlM = lvlN,
+    # n = rows = cols), and the reference's sliding-window shape (512-sample windows, step 64, J = 8) over a 2^24 series
+    "fwt2d": ("fwt2d", "Daubechies4", 12, 32, 4096),
+    "windows": ("windows", "Daubechies4", 8, ((1 << 24) - 512) // 64 + 1, 512),
 }
+WINDOW_HOP = 64
 
 
 def workload_desc(name, kind, cls, levels, batch, n):
+    if kind == "fwt2d":
+        return "%s: 2-D FWT %s lvlM=lvlN=%d forward+reverse, %d matrices of %d x %d fp64 per GPU" % (
+            name, cls, levels, batch, n, n)
+    if kind == "windows":
+        return ("%s: sliding-window MODWT %s J=%d, %d windows of %d samples (step %d) of one series per GPU, forward "
+                "(windows read in place) + inverse" % (name, cls, levels, batch, n, WINDOW_HOP))
     return "%s: batched %s %s J=%d forward+inverse, %d signals x %d fp64 samples per GPU" % (
         name, kind.upper(), cls, levels, batch, n)
 
 
-def algorithmic_bytes_per_sample(kind, levels):
-    # MODWT fwd or inv 8*(J+2) B/sample; FWT / WPT 16 B/sample
+def algorithmic_bytes_per_sample(kind, levels, n=0):
+    # MODWT fwd or inv 8*(J+2) B/sample; FWT / WPT 16 B/sample; 2-D = row pass + column pass;
+    # windows: every series sample is read once (8*hop per window), J+1 rows written per window
+    if kind == "fwt2d":
+        return 32
+    if kind == "windows":
+        return 8.0 * (levels + 1) + 8.0 * WINDOW_HOP / n
     return 8 * (levels + 2) if kind == "modwt" else 16
 
 
@@ -126,10 +142,15 @@ def cpu_reference_time(kind, cls, levels, n, nsig, threads, repeats=1):
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        if kind == "modwt":
+        if kind in ("modwt", "windows"):   # windows: the reference copies each window out and transforms it
             g, h = oracle.modwt_filters(s, wv)
             c = oracle.batch("modwt_fwd_fft", X, levels, g, h, nthreads=threads)
             oracle.batch("modwt_inv_fft", c, levels, g, h, nthreads=threads)
+        elif kind == "fwt2d":
+            m = int(round(n ** 0.5))
+            c = oracle.batch2d("fwt", X.reshape(nsig, m, m), levels, levels, s, wv, nthreads=threads)
+            oracle.batch2d("fwt", c, levels, levels, w.getScalingReConstruction(), w.getWaveletReConstruction(),
+                           reverse=True, nthreads=threads)
         else:
             c = oracle.batch(kind + "_fwd", X, levels, s, wv, nthreads=threads)
             oracle.batch(kind + "_rev", c, levels, w.getScalingReConstruction(), w.getWaveletReConstruction(),
@@ -144,20 +165,21 @@ def run_reference(args, kind, cls, levels, batch, n, rank, world):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    unit = n * n if kind == "fwt2d" else n   # samples per unit of work (signal, window or matrix)
     # bounded sample per step: a few signals per core, so K+W steps finish in minutes
-    probe = cpu_reference_time(kind, cls, levels, n, cores, cores)
+    probe = cpu_reference_time(kind, cls, levels, unit, cores, cores)
     # seconds of host work per step, sized so that the whole --steps K --warmup W run ends within ~2.5 minutes
     target = min(6.0, max(0.5, 150.0 / max(1, args.steps + args.warmup)))
     nsig = int(max(cores, min(batch, cores * max(1, round(target / max(probe, 1e-3))))))
     times = []
     for i in range(args.warmup + args.steps):
-        dt = cpu_reference_time(kind, cls, levels, n, nsig, cores)
+        dt = cpu_reference_time(kind, cls, levels, unit, nsig, cores)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    value = 2.0 * nsig * n / (ms * 1e-3) / 1e9
+    value = 2.0 * nsig * unit / (ms * 1e-3) / 1e9
     sample = "%d signals x %d samples per step (of %d), forward+inverse, %d threads, one signal per thread" % (
-        nsig, n, batch, cores)
+        nsig, unit, batch, cores)
     line = {
         "impl": "reference", "metric": "MODWT/FWT/WPT Gsamples/s (forward+inverse sample-transforms per second)",
         "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -222,28 +244,45 @@ def main():
         k, v = kv.split("=")
         ctx.set_tuning(k, int(v))
     w = jw.wavelets.create(cls)
-    if kind == "modwt":
+    unit = n * n if kind == "fwt2d" else n   # samples per unit of work (signal, window or matrix)
+    if kind in ("modwt", "windows"):
         tr = jw.CudaMODWTTransform(w, context=ctx)
-    elif kind == "fwt":
+    elif kind in ("fwt", "fwt2d"):
         tr = jw.CudaFastWaveletTransform(w, context=ctx)
     else:
         tr = jw.CudaWaveletPacketTransform(w, context=ctx)
 
     # ---- synthetic inputs, resident in HBM (uniform(-1,1), seeded per rank) ---------------------------------
-    out_rows = levels + 1 if kind == "modwt" else 1
+    out_rows = levels + 1 if kind in ("modwt", "windows") else 1
+    series_len = (batch - 1) * WINDOW_HOP + n   # windows workload: one series per GPU, `batch` windows
     bufs = []
     for slot, d in enumerate(devices):
         with torch.cuda.device(d):
             gen = torch.Generator(device="cuda:%d" % d)
             gen.manual_seed(0x5EED0002 + rank * 16 + slot)
-            x = torch.rand((batch, n), dtype=torch.float64, device="cuda:%d" % d, generator=gen) * 2.0 - 1.0
-            c = torch.empty((batch, out_rows * n), dtype=torch.float64, device="cuda:%d" % d)
-            xr = torch.empty_like(x)
+            xshape = (series_len,) if kind == "windows" else (batch, unit)
+            x = torch.rand(xshape, dtype=torch.float64, device="cuda:%d" % d, generator=gen) * 2.0 - 1.0
+            c = torch.empty((batch, out_rows * unit), dtype=torch.float64, device="cuda:%d" % d)
+            xr = torch.empty((batch, unit), dtype=torch.float64, device="cuda:%d" % d)
             bufs.append((x, c, xr, torch.cuda.Stream(device=d)))   # explicit stream: kernels AND events go here
+    if kind == "windows":
+        import ctypes
+        _lib = jw._native.load()
+        _g, _h = (np.ascontiguousarray(v) for v in tr._filters())
+        _dp = ctypes.POINTER(ctypes.c_double)
 
     def fwd(slot):
         x, c, xr, st = bufs[slot]
-        if kind == "modwt":
+        if kind == "windows":
+            rc = _lib.jwc_modwt_forward_windows_dev(ctx.handle, slot, ctypes.c_void_p(st.cuda_stream),
+                                                    ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(c.data_ptr()),
+                                                    series_len, n, WINDOW_HOP, levels, _g.ctypes.data_as(_dp),
+                                                    _h.ctypes.data_as(_dp), len(_g), args.flags)
+            assert rc == 0, _lib.jwc_last_error()
+        elif kind == "fwt2d":
+            tr.forward2DDevice(x.data_ptr(), c.data_ptr(), batch, n, n, levels, levels, stream=st.cuda_stream,
+                               flags=args.flags, slot=slot)
+        elif kind == "modwt":
             tr.forwardMODWTDevice(x.data_ptr(), c.data_ptr(), batch, n, levels, stream=st.cuda_stream, flags=args.flags,
                                   slot=slot)
         else:
@@ -252,7 +291,10 @@ def main():
 
     def inv(slot):
         x, c, xr, st = bufs[slot]
-        if kind == "modwt":
+        if kind == "fwt2d":
+            tr.reverse2DDevice(c.data_ptr(), xr.data_ptr(), batch, n, n, levels, levels, stream=st.cuda_stream,
+                               flags=args.flags, slot=slot)
+        elif kind in ("modwt", "windows"):
             tr.inverseMODWTDevice(c.data_ptr(), xr.data_ptr(), batch, n, levels, stream=st.cuda_stream,
                                   flags=args.flags, slot=slot)
         else:
@@ -266,14 +308,17 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    clock = ClockSampler(devices[0]) if rank == 0 else None
+    clock = ClockSampler(devices[0]) if (rank == 0 and not os.environ.get("JWC_NO_CLOCK_SAMPLER")) else None
     for _ in range(args.warmup):
         for s in range(len(devices)):
             fwd(s)
             inv(s)
     sync_all()
     # correctness of the timed path itself: round trip must hold
-    pr = max(float((b[2] - b[0]).abs().max()) for b in bufs) if args.warmup > 0 else 0.0
+    if kind == "windows":   # every reconstructed window against its span of the series
+        pr = max(float((b[2] - b[0].unfold(0, n, WINDOW_HOP)).abs().max()) for b in bufs) if args.warmup > 0 else 0.0
+    else:
+        pr = max(float((b[2] - b[0]).abs().max()) for b in bufs) if args.warmup > 0 else 0.0
 
     # ---- timed region ---------------------------------------------------------------------------------------------
     ev = []
@@ -304,44 +349,71 @@ def main():
         from jwave_pro_b200.sharding import reduce_max
         total_ms, fwd_ms, inv_ms = reduce_max([total_ms, fwd_ms, inv_ms], device="cuda")
     ms_per_step = total_ms / args.steps
-    samples_per_step = 2.0 * batch * n * n_gpus
+    samples_per_step = 2.0 * batch * unit * n_gpus
     value = samples_per_step / (ms_per_step * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (forward) ------------------------------------------------------------------
     peak, peak_src = measured_peak()
-    bps = algorithmic_bytes_per_sample(kind, levels)
-    fwd_gbs = bps * batch * n / (fwd_ms * 1e-3) / 1e9
-    inv_gbs = bps * batch * n / (inv_ms * 1e-3) / 1e9
+    bps = algorithmic_bytes_per_sample(kind, levels, n)
+    bps_inv = 8.0 * (levels + 2) if kind == "windows" else bps   # the inverse reads J+1 rows, writes one, per window
+    fwd_gbs = bps * batch * unit / (fwd_ms * 1e-3) / 1e9
+    inv_gbs = bps_inv * batch * unit / (inv_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:   # measured DRAM bytes of this kernel from the committed ncu capture, scaled to this launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if args.workload in tj:
-            traffic = tj[args.workload]["forward_bytes_per_sample"] * batch * n
+            traffic = tj[args.workload]["forward_bytes_per_sample"] * batch * unit
             traffic_src = "profiles/r1_traffic.json (ncu --set full capture at a smaller batch, scaled per sample)"
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": "%s forward" % kind, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bps * batch * n, "avg_ms": fwd_ms,
+                "algorithmic_bytes_per_launch": bps * batch * unit, "avg_ms": fwd_ms,
                 "inverse": {"achieved": inv_gbs, "frac": inv_gbs / peak, "avg_ms": inv_ms}}
 
     # ---- e2e: the same metric through the host-buffer C ABI (pinned host memory, copies inside the timed region) ----
     e2e = None
     if not args.no_e2e:
-        eb = min(batch, 256) * len(devices)
-        hx = torch.empty((eb, n), dtype=torch.float64).pin_memory()
-        hx.copy_(torch.cat([b[0][:eb // len(devices)].cpu() for b in bufs]))
-        hc = torch.empty((eb, out_rows * n), dtype=torch.float64).pin_memory()
-        hr = torch.empty((eb, n), dtype=torch.float64).pin_memory()
+        nd = len(devices)
         ectx = jw.Context(devices)
-        if kind == "modwt":
+        if kind == "windows":
+            # one series on the host; a bounded number of windows so that pinned staging stays ~1 GB
+            eb = min(batch, 32768)
+            elen = (eb - 1) * WINDOW_HOP + n
+            hx = torch.empty(elen, dtype=torch.float64).pin_memory()
+            hx.copy_(bufs[0][0][:elen].cpu())
+            hc = torch.empty((eb, out_rows * unit), dtype=torch.float64).pin_memory()
+            hr = torch.empty((eb, unit), dtype=torch.float64).pin_memory()
             et = jw.CudaMODWTTransform(w, context=ectx)
             X, C, R = hx.numpy(), hc.numpy().reshape(eb, out_rows, n), hr.numpy()
-            step = lambda: (et.forwardMODWTBatch(X, levels, out=C), et.inverseMODWTBatch(C, out=R))  # noqa: E731
+            Xref = np.lib.stride_tricks.sliding_window_view(X, n)[::WINDOW_HOP][:eb]
+            e_fwd = lambda Cb: et.forwardMODWTWindows(X, n, WINDOW_HOP, levels, out=Cb)  # noqa: E731
+            e_inv = lambda Cb: et.inverseMODWTBatch(Cb, out=R)  # noqa: E731
+            in_bytes = elen * 8
         else:
-            et = (jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform)(w, context=ectx)
-            X, C, R = hx.numpy(), hc.numpy(), hr.numpy()
-            step = lambda: (et.forwardBatch(X, levels, out=C), et.reverseBatch(C, levels, out=R))  # noqa: E731
+            eb = min(batch, 8 if kind == "fwt2d" else 256) * nd
+            hx = torch.empty((eb, unit), dtype=torch.float64).pin_memory()
+            hx.copy_(torch.cat([b[0][:eb // nd].cpu() for b in bufs]))
+            hc = torch.empty((eb, out_rows * unit), dtype=torch.float64).pin_memory()
+            hr = torch.empty((eb, unit), dtype=torch.float64).pin_memory()
+            in_bytes = eb * unit * 8
+            if kind == "modwt":
+                et = jw.CudaMODWTTransform(w, context=ectx)
+                X, C, R = hx.numpy(), hc.numpy().reshape(eb, out_rows, n), hr.numpy()
+                e_fwd = lambda Cb: et.forwardMODWTBatch(X, levels, out=Cb)  # noqa: E731
+                e_inv = lambda Cb: et.inverseMODWTBatch(Cb, out=R)  # noqa: E731
+            elif kind == "fwt2d":
+                et = jw.CudaFastWaveletTransform(w, context=ectx)
+                X, C, R = (t_.numpy().reshape(eb, n, n) for t_ in (hx, hc, hr))
+                e_fwd = lambda Cb: et.forward2DBatch(X, levels, levels, out=Cb)  # noqa: E731
+                e_inv = lambda Cb: et.reverse2DBatch(Cb, levels, levels, out=R)  # noqa: E731
+            else:
+                et = (jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform)(w, context=ectx)
+                X, C, R = hx.numpy(), hc.numpy(), hr.numpy()
+                e_fwd = lambda Cb: et.forwardBatch(X, levels, out=Cb)  # noqa: E731
+                e_inv = lambda Cb: et.reverseBatch(Cb, levels, out=R)  # noqa: E731
+            Xref = X
+        step = lambda: (e_fwd(C), e_inv(C))  # noqa: E731
         step()
         esteps = max(2, min(args.steps, 5))
         if distributed:
@@ -350,18 +422,14 @@ def main():
         for _ in range(esteps):
             step()
         serial_ms = (time.perf_counter() - t0) * 1e3 / esteps
-        assert float(np.max(np.abs(R - X))) <= 1e-10
+        assert float(np.max(np.abs(R - Xref))) <= 1e-10
         # streaming form of the same work: two host threads on one context, the forward call of batch k+1 runs while
         # the inverse call of batch k does, so the forward's D2H and the inverse's H2D share the link full-duplex
         from concurrent.futures import ThreadPoolExecutor
         hc2 = torch.empty_like(hc).pin_memory()
         Cs = [C, hc2.numpy().reshape(C.shape)]
-        if kind == "modwt":
-            f_call = lambda k: et.forwardMODWTBatch(X, levels, out=Cs[k % 2])  # noqa: E731
-            i_call = lambda k: et.inverseMODWTBatch(Cs[k % 2], out=R)  # noqa: E731
-        else:
-            f_call = lambda k: et.forwardBatch(X, levels, out=Cs[k % 2])  # noqa: E731
-            i_call = lambda k: et.reverseBatch(Cs[k % 2], levels, out=R)  # noqa: E731
+        f_call = lambda k: e_fwd(Cs[k % 2])  # noqa: E731
+        i_call = lambda k: e_inv(Cs[k % 2])  # noqa: E731
         psteps = max(20, 4 * esteps)   # long enough that the one-call pipeline fill is < 5 % of the timed region
 
         def pipeline(ex, steps):
@@ -380,16 +448,19 @@ def main():
             t0 = time.perf_counter()
             pipeline(ex, psteps)
             e_ms = (time.perf_counter() - t0) * 1e3 / psteps
-        assert float(np.max(np.abs(R - X))) <= 1e-10
+        assert float(np.max(np.abs(R - Xref))) <= 1e-10
         if distributed:
             from jwave_pro_b200.sharding import reduce_max
             e_ms, serial_ms = reduce_max([e_ms, serial_ms], device="cuda")
-        io = (1 + out_rows) * eb * n * 8 * (world if distributed else 1)
-        gs = lambda ms: 2.0 * eb * n * (world if distributed else 1) / (ms * 1e-3) / 1e9  # noqa: E731
-        e2e = {"value": gs(e_ms), "unit": "Gsamples/s", "h2d_bytes_per_step": io, "d2h_bytes_per_step": io,
+        wmul = world if distributed else 1
+        c_bytes = eb * out_rows * unit * 8
+        h2d = (in_bytes + c_bytes) * wmul        # forward input + inverse coefficients
+        d2h = (c_bytes + eb * unit * 8) * wmul   # forward coefficients + inverse result
+        gs = lambda ms: 2.0 * eb * unit * wmul / (ms * 1e-3) / 1e9  # noqa: E731
+        e2e = {"value": gs(e_ms), "unit": "Gsamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e_ms, "serial_value": gs(serial_ms), "serial_ms_per_step": serial_ms,
                "batch_per_gpu": eb // len(devices),
-               "note": "jwc_*_forward + jwc_*_inverse on pinned host buffers, %d signals per GPU per step (bounded so "
+               "note": "jwc_*_forward + jwc_*_inverse on pinned host buffers, %d units per GPU per step (bounded so "
                        "pinned staging stays small); PCIe-bound. value: forward of batch k+1 and inverse of batch k "
                        "issued from two host threads (both link directions busy), %d steps incl. pipeline fill; "
                        "serial_value: the two calls one after the other" % (eb // len(devices), psteps)}
@@ -399,13 +470,14 @@ def main():
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        probe = cpu_reference_time(kind, cls, levels, n, cores, cores)
+        probe = cpu_reference_time(kind, cls, levels, unit, cores, cores)
         nsig = int(max(cores, min(batch, cores * max(1, round(12.0 / max(probe, 1e-3))))))
-        dt = cpu_reference_time(kind, cls, levels, n, nsig, cores)
-        cpu = {"value": 2.0 * nsig * n / dt / 1e9, "unit": "Gsamples/s", "cores": cores, "kind": "port",
+        dt = cpu_reference_time(kind, cls, levels, unit, nsig, cores)
+        cpu = {"value": 2.0 * nsig * unit / dt / 1e9, "unit": "Gsamples/s", "cores": cores, "kind": "port",
                "sample": "%d of %d signals x %d samples, forward+inverse, %d threads (one signal per thread); C "
-                         "restatement of the reference's %s" % (nsig, batch, n, cores,
-                                                                "FFT-convolution MODWT" if kind == "modwt" else kind.upper())}
+                         "restatement of the reference's %s" % (
+                             nsig, batch, unit, cores,
+                             "FFT-convolution MODWT" if kind in ("modwt", "windows") else kind.upper())}
 
     if rank == 0:
         line = {
@@ -415,7 +487,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_desc(args.workload, kind, cls, levels, batch, n),
                        "l2": "inputs larger than L2 (%.1f GiB read per direction vs 126 MB L2)" % (
-                           (out_rows if kind == "modwt" else 1) * batch * n * 8 / 2 ** 30),
+                           (out_rows if kind in ("modwt", "windows") else 1) * batch * unit * 8 / 2 ** 30),
                        "sharding": "by signal, no collective", "tune": args.tune, "flags": args.flags,
                        "round_trip_max_err": pr},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),

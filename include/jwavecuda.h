@@ -82,6 +82,10 @@ JWC_API void jwc_free_device(jwc_ctx* ctx, int slot, void* p);
 JWC_API int jwc_copy_to_device(jwc_ctx* ctx, int slot, void* dst_dev, const void* src_host, size_t bytes);
 JWC_API int jwc_copy_to_host(jwc_ctx* ctx, int slot, void* dst_host, const void* src_dev, size_t bytes);
 JWC_API int jwc_synchronize(jwc_ctx* ctx);
+/* Device workspace (intermediate levels, host-pipeline staging) is cached per (device, stream) inside the context so
+ * that a transform call makes no allocator call in steady state; this returns it to the driver (synchronises the
+ * context's devices).  jwc_destroy does the same. */
+JWC_API int jwc_release_scratch(jwc_ctx* ctx);
 
 /* ---- MODWT ------------------------------------------------------------------------------------------
  * g, h: the level-1 MODWT filters g~ = (scalingDeCom/||.||)/sqrt2, h~ = (waveletDeCom/||.||)/sqrt2

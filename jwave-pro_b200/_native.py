@@ -27,7 +27,8 @@ _TRANSFORMS_AED = ["fwt_aed_forward", "fwt_aed_inverse", "wpt_aed_forward", "wpt
 _TRANSFORMS_2D = ["fwt2d_forward", "fwt2d_inverse", "wpt2d_forward", "wpt2d_inverse"]
 SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal", "jwc_last_error", "jwc_version",
             "jwc_launch_count", "jwc_set_tuning", "jwc_get_tuning", "jwc_alloc_pinned", "jwc_free_pinned",
-            "jwc_alloc_device", "jwc_free_device", "jwc_copy_to_device", "jwc_copy_to_host", "jwc_synchronize"]
+            "jwc_alloc_device", "jwc_free_device", "jwc_copy_to_device", "jwc_copy_to_host", "jwc_synchronize",
+            "jwc_release_scratch"]
            + ["jwc_" + t for t in _TRANSFORMS] + ["jwc_" + t + "_dev" for t in _TRANSFORMS]
            + ["jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"]
            + ["jwc_modwt_forward_windows", "jwc_modwt_forward_windows_dev", "jwc_compress_magnitude",
@@ -85,6 +86,8 @@ def load():
         lib.jwc_copy_to_host.restype = _int
         lib.jwc_synchronize.argtypes = [_vp]
         lib.jwc_synchronize.restype = _int
+        lib.jwc_release_scratch.argtypes = [_vp]
+        lib.jwc_release_scratch.restype = _int
         for t in _TRANSFORMS:
             fn = getattr(lib, "jwc_" + t)
             fn.argtypes = [_vp, _vp, _vp, _i64, _i64, _int, _dp, _dp, _int, _u32]
@@ -159,6 +162,11 @@ class Context:
 
     def synchronize(self):
         rc = self._lib.jwc_synchronize(self._h)
+        if rc != 0:
+            raise RuntimeError(last_error())
+
+    def release_scratch(self):
+        rc = self._lib.jwc_release_scratch(self._h)
         if rc != 0:
             raise RuntimeError(last_error())
 

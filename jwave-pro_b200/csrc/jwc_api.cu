@@ -132,7 +132,7 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
     if (row_steps == 0)
       return fwd ? dwt2d_columns_forward(ctx, dev, st, d_in, d_out, batch, rows, cols, d2.lvl_m, fp, L, tree, exact)
                  : dwt2d_columns_inverse(ctx, dev, st, d_in, d_out, batch, rows, cols, d2.lvl_m, fp, L, tree, exact);
-    Scratch ws(st);
+    Scratch ws(ctx, dev, st);
     double* mid = ws.get((size_t)(batch * rows * cols));
     if (!mid) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
     if (fwd) {
@@ -152,7 +152,10 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
         rc = small_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, d2.hop);
         if (rc == JWC_ERR_UNSUPPORTED) rc = fast_modwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, d2.hop);
         break;
-      case Op::ModwtInv: rc = fast_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L); break;
+      case Op::ModwtInv:
+        rc = small_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L);
+        if (rc == JWC_ERR_UNSUPPORTED) rc = fast_modwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L);
+        break;
       case Op::FwtFwd: rc = fast_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
       case Op::FwtInv: rc = fast_dwt_inverse(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, false); break;
       case Op::WptFwd: rc = fast_dwt_forward(ctx, dev, st, d_in, d_out, batch, n, levels, fp, L, true); break;
@@ -262,12 +265,12 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
     rc = JWC_ERR_CUDA;
   };
   cudaError_t e;
+  Scratch staging(ctx, dev, sc);   // kept in the lane's arena between calls; released when this call has drained
   for (int i = 0; i < nbuf && rc == JWC_OK; i++) {
-    if ((e = cudaMallocAsync((void**)&d_in[i], (size_t)in_span(chunk) * sizeof(double), sc)) != cudaSuccess ||
-        (e = cudaMallocAsync((void**)&d_out[i], (size_t)(chunk * out_per) * sizeof(double), sc)) != cudaSuccess) {
-      (void)cudaGetLastError();
-      set_error("device staging allocation of %lld MiB failed: %s",
-                (long long)((chunk * (in_per + out_per) * 8) >> 20), cudaGetErrorString(e));
+    d_in[i] = staging.get((size_t)in_span(chunk));
+    d_out[i] = staging.get((size_t)(chunk * out_per));
+    if (!d_in[i] || !d_out[i]) {
+      set_error("device staging allocation of %lld MiB failed", (long long)((chunk * (in_per + out_per) * 8) >> 20));
       rc = JWC_ERR_NOMEM;
     }
     if (rc == JWC_OK && ((e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming)) != cudaSuccess ||
@@ -314,13 +317,12 @@ int run_host_slot(jwc_ctx* ctx, int slot, Op op, const double* in, double* out, 
     else if (e3 != cudaSuccess) fail(e3, "cudaStreamSynchronize(copy_out)");
   }
   for (int i = 0; i < kMaxBuf; i++) {
-    if (d_in[i]) cudaFreeAsync(d_in[i], sc);
-    if (d_out[i]) cudaFreeAsync(d_out[i], sc);
     if (ev_in[i]) cudaEventDestroy(ev_in[i]);
     if (ev_k[i]) cudaEventDestroy(ev_k[i]);
     if (ev_out[i]) cudaEventDestroy(ev_out[i]);
   }
   if (ev_alloc) cudaEventDestroy(ev_alloc);
+  staging.release();               // before the lane goes back: its next user finds the staging blocks free
   lane_release(ctx, slot, lane);
   return rc;
 }
@@ -532,8 +534,34 @@ JWC_API jwc_ctx* jwc_create(const int* devices, int ndev) {
   return ctx;
 }
 
+// Give the cached workspace back to the driver (all devices are synchronised first).  Safe at any quiet moment; the
+// next call simply allocates again.
+JWC_API int jwc_release_scratch(jwc_ctx* ctx) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (auto& s : ctx->slots) {
+    cudaSetDevice(s.ordinal);
+    cudaDeviceSynchronize();
+  }
+  int rc = JWC_OK;
+  for (auto& kv : ctx->arenas) {
+    cudaSetDevice(kv.first.first);
+    for (auto it = kv.second.begin(); it != kv.second.end();) {
+      if (it->in_use) { ++it; rc = JWC_ERR_INVALID; continue; }   // a call is enqueueing right now: keep its blocks
+      cudaFree(it->p);
+      it = kv.second.erase(it);
+    }
+  }
+  cudaSetDevice(prev);
+  if (rc != JWC_OK) set_error("jwc_release_scratch: calls in flight kept their workspace");
+  return rc;
+}
+
 JWC_API void jwc_destroy(jwc_ctx* ctx) {
   if (!ctx) return;
+  jwc_release_scratch(ctx);
   int prev = 0;
   cudaGetDevice(&prev);
   for (auto& s : ctx->slots) {

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) threshold_kernel(const double* __res
 int compress_magnitude(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
                        int64_t count, double threshold, double* d_mag) {
   if (count <= 0) return JWC_OK;
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   int nparts = (int)((count + 65535) / 65536);
   if (nparts > kMaxParts) nparts = kMaxParts;
   if (nparts < 1) nparts = 1;

@@ -539,7 +539,7 @@ int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
   (void)dev;
   const int steps = count_steps(rows, levels);
   const int64_t mat = rows * cols;
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   if (tree) {
     // every block of h rows -> [lo | hi] of itself; whole-array ping-pong, last step lands in d_out
     double* tmp = nullptr;
@@ -618,7 +618,7 @@ int dwt2d_columns_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
                           bool exact) {
   const int steps = count_steps(rows, levels);
   const int64_t mat = rows * cols;
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   if (tree) {
     double* tmp = nullptr;
     if (steps >= 2) {

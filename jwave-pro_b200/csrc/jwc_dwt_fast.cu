@@ -624,7 +624,7 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, false, ld);
   if (!plan.ok) return JWC_ERR_UNSUPPORTED;
   debug_dwt_plan("forward", plan, n, levels, L, tree);
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   const int npass = (int)plan.passes.size();
   double* tail_a = nullptr;
   if (lt > 0) {
@@ -689,7 +689,7 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     if (top == steps) return whole_dwt(ctx, st, d_in, d_out, batch, n, steps, f, L, ld, true);
     if (top > 0) {
       // deep end first (warp per signal) into scratch, then the big levels with that approximation as their head
-      Scratch ws(st);
+      Scratch ws(ctx, dev, st);
       const int64_t h0 = n >> top;
       double* a_top = ws.get((size_t)batch * h0);
       if (!a_top) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
@@ -704,7 +704,7 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   const DwtPlan plan = make_plan(ctx, dev, d_in, d_out, n, plan_steps, L, tree, true, ld);
   if (!plan.ok) return JWC_ERR_UNSUPPORTED;
   debug_dwt_plan("inverse", plan, n, levels, L, tree);
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   const int npass = (int)plan.passes.size();
   double* tail_a = nullptr;
   if (lt > 0) {

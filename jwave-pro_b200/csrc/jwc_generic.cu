@@ -185,7 +185,7 @@ void fill_offsets(ModwtLevelArgs& a, int level, int L, int64_t n) {
 int generic_modwt_forward_from(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_v, int64_t v_sig,
                                int first_level, double* d_coeffs, int64_t batch, int64_t n, int levels,
                                const FilterPair& f, int L, bool exact) {
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   double* vbuf[2] = {nullptr, nullptr};
   const int todo = levels - first_level + 1;
   if (todo >= 2) {
@@ -234,7 +234,7 @@ int generic_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
 
 int generic_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                           int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool exact) {
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   double* vbuf[2] = {nullptr, nullptr};
   if (levels >= 2) {
     vbuf[0] = ws.get((size_t)batch * n);
@@ -285,7 +285,7 @@ int generic_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
   int steps = 0;  // number of analysis steps actually performed (reference loop: while h >= 2 && l < level)
   for (int64_t h = n; h >= 2 && steps < levels; h >>= 1) steps++;
   if (steps == 0) return copy_rows(ctx, dev, st, d_in, d_out, ld, ld, n, batch);
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   if (tree) {
     double* tmp = nullptr;
     if (steps >= 2) {
@@ -354,7 +354,7 @@ int generic_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
   int steps = 0;
   for (int64_t h = h0; h <= n && h >= 2; h <<= 1) steps++;
   if (steps == 0) return copy_rows(ctx, dev, st, d_in, d_out, ld, ld, n, batch);
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   if (tree) {
     double* tmp = nullptr;
     if (steps >= 2) {

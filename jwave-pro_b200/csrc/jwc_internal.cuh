@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#include <list>
+#include <map>
 #include <vector>
 
 #include "../../include/jwavecuda.h"
@@ -74,35 +76,73 @@ struct DeviceSlot {
 
 }  // namespace jwc
 
+namespace jwc {
+// A piece of device workspace kept by the context for one (device, stream) pair.
+struct ScratchBlock {
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool in_use = false;   // held by a call that is still enqueueing work
+};
+}  // namespace jwc
+
 struct jwc_ctx {
   std::vector<jwc::DeviceSlot> slots;
   std::atomic<uint64_t> launches{0};
   std::atomic<int> host_calls{0};   // host-buffer calls in flight (copy pacing, see run_host_slot)
   jwc::Tuning tune;
   std::mutex mu;
+  // workspace arenas, guarded by mu (std::list: blocks keep their address while others are added)
+  std::map<std::pair<int, cudaStream_t>, std::list<jwc::ScratchBlock>> arenas;
 };
 
 namespace jwc {
 
-// Stream-ordered scratch: cudaMallocAsync/cudaFreeAsync on the call's stream, so concurrent calls on one
-// context never share workspace (re-entrancy requirement of SURVEY.md section 8b "threading").
+// Workspace of one call.  Blocks come from the context's arena of the call's (device, stream) and go back to it when
+// the call has finished ENQUEUEING: everything that uses a block is ordered on that one stream, so the next call on
+// the stream may reuse it at once, and a call that is enqueueing concurrently from another host thread never gets a
+// block that is still held (re-entrancy requirement of SURVEY.md section 8b "threading").  In steady state a call
+// makes no allocator call at all -- per-call cudaMallocAsync / cudaFreeAsync pairs measured 2-5x slower transforms
+// whenever something polled the driver (nvidia-smi -lms 20 next to a 2-D FWT: 3.6 ms -> 7.7-17 ms).  Blocks live until
+// jwc_release_scratch / jwc_destroy.
 struct Scratch {
+  jwc_ctx* ctx;
+  int ordinal;
   cudaStream_t stream;
-  std::vector<void*> ptrs;
-  explicit Scratch(cudaStream_t s) : stream(s) {}
+  std::vector<ScratchBlock*> held;
+  Scratch(jwc_ctx* c, const DeviceSlot& dev, cudaStream_t s) : ctx(c), ordinal(dev.ordinal), stream(s) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
   double* get(size_t n_doubles) {
-    void* p = nullptr;
     if (n_doubles == 0) n_doubles = 1;
-    if (cudaMallocAsync(&p, n_doubles * sizeof(double), stream) != cudaSuccess) {
+    const size_t bytes = (n_doubles * sizeof(double) + 255) & ~(size_t)255;
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      ScratchBlock* best = nullptr;
+      for (auto& b : ctx->arenas[std::make_pair(ordinal, stream)])
+        if (!b.in_use && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+      if (best) {
+        best->in_use = true;
+        held.push_back(best);
+        return static_cast<double*>(best->p);
+      }
+    }
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, bytes, stream) != cudaSuccess) {
       (void)cudaGetLastError();
       return nullptr;
     }
-    ptrs.push_back(p);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto& arena = ctx->arenas[std::make_pair(ordinal, stream)];
+    arena.push_back(ScratchBlock{p, bytes, true});
+    held.push_back(&arena.back());
     return static_cast<double*>(p);
   }
-  ~Scratch() {
-    for (void* p : ptrs) cudaFreeAsync(p, stream);
+  void release() {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (ScratchBlock* b : held) b->in_use = false;
+    held.clear();
   }
+  ~Scratch() { release(); }
 };
 
 // ---- generic (any shape, one level per launch) kernels: jwc_generic.cu ---------------------------------
@@ -132,6 +172,8 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);
 int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
+int small_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
 // whole-signal in-place FWT for 512 < n <= 4096 (jwc_dwt_whole.cu)
 int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L);
 int whole_dwt(jwc_ctx* ctx, cudaStream_t st, const double* d_in, double* d_out, int64_t batch, int64_t n, int steps,

@@ -343,7 +343,7 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   if (plan.passes.empty()) return JWC_ERR_UNSUPPORTED;
   debug_plan("modwt forward", plan, n, levels, L);
 
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   const int64_t cs = (int64_t)(levels + 1) * n;
   const int npass = (int)plan.passes.size();
   const bool need_scratch = !(plan.all_fused && npass == 1);
@@ -634,7 +634,7 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   if (plan.passes.empty() || !plan.all_fused) return JWC_ERR_UNSUPPORTED;
   debug_plan("modwt inverse", plan, n, levels, L);
 
-  Scratch ws(st);
+  Scratch ws(ctx, dev, st);
   const int64_t cs = (int64_t)(levels + 1) * n;
   const int npass = (int)plan.passes.size();
   double* vbuf[2] = {nullptr, nullptr};

@@ -117,6 +117,84 @@ __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_
   }
 }
 
+// Inverse: V_(j-1)[t] = sum_m g[m] V_j[(t + m s) mod n] + sum_m h[m] W_j[(t + m s) mod n]  (MODWTTransform.java:355-372,
+// :703-716), j = J .. 1.  V ping-pongs in shared memory, W_j is fetched into a third buffer level by level (cp.async).
+template <int LT>
+__global__ void __launch_bounds__(kThreads) modwt_small_inv_kernel(const __grid_constant__ SmallArgs a,
+                                                                   const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  const int tps = kThreads / a.per_cta;
+  const int s_local = threadIdx.x / tps, r = threadIdx.x % tps;
+  const int64_t sig = (int64_t)blockIdx.x * a.per_cta + s_local;
+  const bool live = sig < a.batch;
+  const int n = a.n;
+  double* cur = sm + (size_t)s_local * 3 * n;
+  double* nxt = cur + n;
+  double* wb = nxt + n;
+  const double* co = a.x + (live ? sig : 0) * (int64_t)(a.J + 1) * n;   // a.x = coefficient array here
+  double* out = a.coeffs + (live ? sig : 0) * a.x_sig;                    // a.coeffs = reconstructed signals, stride x_sig
+  if (live)
+    for (int t = r; t < n; t += tps) ptx::cp_async8(cur + t, co + (int64_t)a.J * n + t);
+  for (int j = a.J; j >= 1; j--) {
+    if (live)
+      for (int t = r; t < n; t += tps) ptx::cp_async8(wb + t, co + (int64_t)(j - 1) * n + t);
+    ptx::cp_async_commit_wait_all();
+    __syncthreads();
+    const int step = (int)((((int64_t)1) << (j - 1)) % n);
+    const bool last = (j == 1);
+    if (live) {
+      bool done = false;
+      if constexpr (LT > 0) {
+        if (step > 0 && n % (step * kChain) == 0) {
+          const int items = n / kChain;
+          for (int it = r; it < items; it += tps) {
+            const int a0 = it % step, grp = it / step;
+            const int t0 = a0 + grp * kChain * step;
+            int idx = t0;
+            double acc[kChain];
+#pragma unroll
+            for (int q = 0; q < kChain; q++) acc[q] = 0.0;
+#pragma unroll
+            for (int u = 0; u <= kChain + LT - 2; u++) {
+              const double v = cur[idx], w = wb[idx];
+#pragma unroll
+              for (int q = 0; q < kChain; q++) {
+                const int m = u - q;                 // output t0 + q s takes input t0 + u s with tap m
+                if (m >= 0 && m < LT) acc[q] = fma(w, f.f1[m], fma(v, f.f0[m], acc[q]));
+              }
+              idx += step;
+              if (idx >= n) idx -= n;
+            }
+#pragma unroll
+            for (int q = 0; q < kChain; q++) {
+              const int t = t0 + q * step;
+              if (last) out[t] = acc[q];
+              else nxt[t] = acc[q];
+            }
+          }
+          done = true;
+        }
+      }
+      if (!done) {
+        for (int t = r; t < n; t += tps) {
+          double sa = 0.0, sd = 0.0;
+          int idx = t;
+          for (int m = 0; m < a.L; m++) {
+            sa = fma(cur[idx], f.f0[m], sa);
+            sd = fma(wb[idx], f.f1[m], sd);
+            idx += step;
+            if (idx >= n) idx -= n;
+          }
+          if (last) out[t] = sa + sd;
+          else nxt[t] = sa + sd;
+        }
+      }
+    }
+    __syncthreads();
+    double* tmp = cur; cur = nxt; nxt = tmp;
+  }
+}
+
 }  // namespace
 
 // Returns JWC_ERR_UNSUPPORTED when the shape is not one this kernel is meant for.
@@ -141,6 +219,35 @@ int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
     JWC_SCASE(18) JWC_SCASE(20)
 #undef JWC_SCASE
     default: modwt_small_fwd_kernel<0><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+  }
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+}  // namespace jwc
+
+namespace jwc {
+
+int small_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L) {
+  (void)dev;
+  const int mode = ctx->tune.modwt_small;
+  if (mode < 0 || n > 2048 || n < 1 || levels > 30 || L < 1) return JWC_ERR_UNSUPPORTED;
+  const int64_t halo = (int64_t)(L - 1) * ((((int64_t)1) << levels) - 1);
+  if (mode == 0 && 3 * halo <= n) return JWC_ERR_UNSUPPORTED;
+  SmallArgs a{};
+  a.x = d_coeffs; a.coeffs = d_x; a.x_sig = n; a.batch = batch; a.n = (int)n; a.J = levels; a.L = L;
+  a.per_cta = n <= 512 ? 4 : (n <= 1024 ? 2 : 1);
+  const int64_t ctas = (batch + a.per_cta - 1) / a.per_cta;
+  if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)a.per_cta * 3 * (size_t)n * sizeof(double);   // <= 48 KB
+  switch (L) {
+#define JWC_SCASE(LL) case LL: modwt_small_inv_kernel<LL><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+    JWC_SCASE(2) JWC_SCASE(4) JWC_SCASE(6) JWC_SCASE(8) JWC_SCASE(10) JWC_SCASE(12) JWC_SCASE(14) JWC_SCASE(16)
+    JWC_SCASE(18) JWC_SCASE(20)
+#undef JWC_SCASE
+    default: modwt_small_inv_kernel<0><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
   }
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());
