@@ -29,7 +29,7 @@ struct SmallArgs {
 constexpr int kChain = 4;   // outputs per work item of the register-blocked path
 
 // LT = compile-time filter length (taps become constant-bank operands, the chain loop unrolls), 0 = run-time length.
-// Register-blocked path (LT > 0, n divisible by kChain * stride): a thread produces the kChain outputs
+// Register-blocked path (LT > 0, n divisible by the stride): a thread produces the kChain outputs
 // t0, t0 + s, ..., t0 + (kChain-1) s, which share their inputs -- kChain + L - 1 shared-memory loads instead of
 // kChain * L.  Other shapes (any n, any L) take the one-output-at-a-time loop.
 template <int LT>
@@ -59,12 +59,15 @@ __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_
       double* v_row = co + (int64_t)a.J * n;
       bool done = false;
       if constexpr (LT > 0) {
-        if (step > 0 && n % (step * kChain) == 0) {
-          const int items = n / kChain;
+        if (step > 0 && n % step == 0) {
+          // residue class a0 (mod step) holds n / step outputs a0 + b step; chains of kChain consecutive b, the last
+          // one of a class may be partial (its surplus outputs are computed from wrapped inputs and dropped)
+          const int per_class = n / step, chains = (per_class + kChain - 1) / kChain;
+          const int items = step * chains;
           int back = ((LT - 1) * step) % n;          // inputs start (L-1) strides before the first output
           for (int it = r; it < items; it += tps) {
-            const int a0 = it % step, grp = it / step;
-            const int t0 = a0 + grp * kChain * step;
+            const int a0 = it % step, b0 = (it / step) * kChain;
+            const int t0 = a0 + b0 * step;
             int idx = t0 - back;
             if (idx < 0) idx += n;
             double aw[kChain], av[kChain];
@@ -86,10 +89,12 @@ __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_
             }
 #pragma unroll
             for (int q = 0; q < kChain; q++) {
-              const int t = t0 + q * step;
-              w_row[t] = aw[q];
-              if (last) v_row[t] = av[q];
-              else nxt[t] = av[q];
+              if (b0 + q < per_class) {
+                const int t = t0 + q * step;
+                w_row[t] = aw[q];
+                if (last) v_row[t] = av[q];
+                else nxt[t] = av[q];
+              }
             }
           }
           done = true;
@@ -118,7 +123,8 @@ __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_
 }
 
 // Inverse: V_(j-1)[t] = sum_m g[m] V_j[(t + m s) mod n] + sum_m h[m] W_j[(t + m s) mod n]  (MODWTTransform.java:355-372,
-// :703-716), j = J .. 1.  V ping-pongs in shared memory, W_j is fetched into a third buffer level by level (cp.async).
+// :703-716), j = J .. 1.  V ping-pongs in shared memory, W_j streams into one of two more buffers (cp.async) while the
+// level before it computes.
 template <int LT>
 __global__ void __launch_bounds__(kThreads) modwt_small_inv_kernel(const __grid_constant__ SmallArgs a,
                                                                    const __grid_constant__ FilterPair f) {
@@ -128,28 +134,37 @@ __global__ void __launch_bounds__(kThreads) modwt_small_inv_kernel(const __grid_
   const int64_t sig = (int64_t)blockIdx.x * a.per_cta + s_local;
   const bool live = sig < a.batch;
   const int n = a.n;
-  double* cur = sm + (size_t)s_local * 3 * n;
+  double* cur = sm + (size_t)s_local * 4 * n;
   double* nxt = cur + n;
-  double* wb = nxt + n;
+  double* wbuf[2] = {nxt + n, nxt + 2 * n};
   const double* co = a.x + (live ? sig : 0) * (int64_t)(a.J + 1) * n;   // a.x = coefficient array here
   double* out = a.coeffs + (live ? sig : 0) * a.x_sig;                    // a.coeffs = reconstructed signals, stride x_sig
   if (live)
-    for (int t = r; t < n; t += tps) ptx::cp_async8(cur + t, co + (int64_t)a.J * n + t);
-  for (int j = a.J; j >= 1; j--) {
-    if (live)
-      for (int t = r; t < n; t += tps) ptx::cp_async8(wb + t, co + (int64_t)(j - 1) * n + t);
-    ptx::cp_async_commit_wait_all();
+    for (int t = r; t < n; t += tps) {
+      ptx::cp_async8(cur + t, co + (int64_t)a.J * n + t);
+      ptx::cp_async8(wbuf[0] + t, co + (int64_t)(a.J - 1) * n + t);
+    }
+  ptx::cp_async_commit();
+  int wi = 0;
+  for (int j = a.J; j >= 1; j--, wi ^= 1) {
+    // W of the NEXT level streams in while this level computes
+    if (live && j > 1)
+      for (int t = r; t < n; t += tps) ptx::cp_async8(wbuf[wi ^ 1] + t, co + (int64_t)(j - 2) * n + t);
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<1>();
     __syncthreads();
+    const double* wb = wbuf[wi];
     const int step = (int)((((int64_t)1) << (j - 1)) % n);
     const bool last = (j == 1);
     if (live) {
       bool done = false;
       if constexpr (LT > 0) {
-        if (step > 0 && n % (step * kChain) == 0) {
-          const int items = n / kChain;
+        if (step > 0 && n % step == 0) {
+          const int per_class = n / step, chains = (per_class + kChain - 1) / kChain;
+          const int items = step * chains;
           for (int it = r; it < items; it += tps) {
-            const int a0 = it % step, grp = it / step;
-            const int t0 = a0 + grp * kChain * step;
+            const int a0 = it % step, b0 = (it / step) * kChain;
+            const int t0 = a0 + b0 * step;
             int idx = t0;
             double acc[kChain];
 #pragma unroll
@@ -167,9 +182,11 @@ __global__ void __launch_bounds__(kThreads) modwt_small_inv_kernel(const __grid_
             }
 #pragma unroll
             for (int q = 0; q < kChain; q++) {
-              const int t = t0 + q * step;
-              if (last) out[t] = acc[q];
-              else nxt[t] = acc[q];
+              if (b0 + q < per_class) {
+                const int t = t0 + q * step;
+                if (last) out[t] = acc[q];
+                else nxt[t] = acc[q];
+              }
             }
           }
           done = true;
@@ -241,13 +258,20 @@ int small_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
   a.per_cta = n <= 512 ? 4 : (n <= 1024 ? 2 : 1);
   const int64_t ctas = (batch + a.per_cta - 1) / a.per_cta;
   if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)a.per_cta * 3 * (size_t)n * sizeof(double);   // <= 48 KB
+  const size_t smem = (size_t)a.per_cta * 4 * (size_t)n * sizeof(double);   // 64 KB: above the 48 KB default
   switch (L) {
-#define JWC_SCASE(LL) case LL: modwt_small_inv_kernel<LL><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+#define JWC_SCASE(LL)                                                                                               \
+  case LL:                                                                                                          \
+    JWC_CUDA_CHECK(cudaFuncSetAttribute(modwt_small_inv_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); \
+    modwt_small_inv_kernel<LL><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);                                         \
+    break;
     JWC_SCASE(2) JWC_SCASE(4) JWC_SCASE(6) JWC_SCASE(8) JWC_SCASE(10) JWC_SCASE(12) JWC_SCASE(14) JWC_SCASE(16)
     JWC_SCASE(18) JWC_SCASE(20)
 #undef JWC_SCASE
-    default: modwt_small_inv_kernel<0><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+    default:
+      JWC_CUDA_CHECK(cudaFuncSetAttribute(modwt_small_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      modwt_small_inv_kernel<0><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);
+      break;
   }
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());
