@@ -612,6 +612,10 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);
   if (steps == 0) return JWC_ERR_UNSUPPORTED;   // plain copy: the generic path handles it
+  if (tree && whole_dwt_levels(ctx, n, steps, L, true) == steps) {   // short packets transforms: all blocks in place
+    const int rc = whole_dwt(ctx, st, d_in, d_out, batch, n, steps, f, L, ld, false, nullptr, 0, true);
+    if (rc != JWC_ERR_UNSUPPORTED) return rc;
+  }
   if (!tree) {   // 512 < n <= 4096: the whole signal in shared memory, levels in place (jwc_dwt_whole.cu)
     // (forward: only when it takes every level -- for a deep transform the first tile pass + the warp tail measured
     // faster than this kernel + the tail, 1.73 vs 1.83 ms on 131 072 rows of 4096; the inverse is the other way round)
@@ -684,6 +688,10 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
   if (n >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
   const int steps = steps_forward(n, levels);   // the reverse loops undo exactly the forward's steps
   if (steps == 0) return JWC_ERR_UNSUPPORTED;
+  if (tree && whole_dwt_levels(ctx, n, steps, L, true) == steps) {
+    const int rc = whole_dwt(ctx, st, d_in, d_out, batch, n, steps, f, L, ld, true, nullptr, 0, true);
+    if (rc != JWC_ERR_UNSUPPORTED) return rc;
+  }
   if (!tree) {
     const int top = whole_dwt_levels(ctx, n, steps, L);
     if (top == steps) return whole_dwt(ctx, st, d_in, d_out, batch, n, steps, f, L, ld, true);

@@ -29,6 +29,7 @@ struct WholeArgs {
   int prefix_len;
   int n, steps;
   int vec;   // 1: rows are 16-byte aligned (double2 copies in and out)
+  int tree;  // 1: wavelet packets -- every block of h samples is transformed at each level, not only the first
 };
 
 // asynchronous copies: every thread's pieces are in flight together (a plain load/store loop pays one global-memory
@@ -59,18 +60,23 @@ __device__ __forceinline__ void store_row(double* y, const double* sm, int n, in
   }
 }
 
-// One analysis level in place on sm[0..h).
+// One analysis level in place: every block of h samples (the first `blocks` of them) becomes [lo | hi] of itself.
+// A work item = R consecutive outputs of one block; item -> (block, run) so that a level's items are dense in the
+// thread index whatever the block length.
 template <int L, int R>
-__device__ __forceinline__ void fwd_level(double* sm, int h, const FilterPair& f) {
+__device__ __forceinline__ void fwd_level(double* sm, int h, int blocks, const FilterPair& f) {
   const int half = h >> 1, mask = h - 1;
-  const int i0 = threadIdx.x * R;
+  const int rpb = (half + R - 1) / R;                 // runs per block
+  const int item = threadIdx.x;
+  const bool active = item < blocks * rpb;
+  const int p = item / rpb, i0 = (item - p * rpb) * R;
+  double* blk = sm + p * h;
   double lo[R], hi[R];
-  const bool active = i0 < half;
   if (active) {
     constexpr int W = R + L / 2 - 1;
     double2 win[W];
 #pragma unroll
-    for (int t = 0; t < W; t++) win[t] = *reinterpret_cast<const double2*>(sm + ((2 * i0 + 2 * t) & mask));
+    for (int t = 0; t < W; t++) win[t] = *reinterpret_cast<const double2*>(blk + ((2 * i0 + 2 * t) & mask));
 #pragma unroll
     for (int q = 0; q < R; q++) lo[q] = hi[q] = 0.0;
 #pragma unroll
@@ -82,33 +88,36 @@ __device__ __forceinline__ void fwd_level(double* sm, int h, const FilterPair& f
         hi[q] = fma(v, f.f1[m], hi[q]);
       }
   }
-  __syncthreads();   // every read of this level is done: write [lo | hi] over the prefix
+  __syncthreads();   // every read of this level is done: write [lo | hi] over the block
   if (active) {
 #pragma unroll
     for (int q = 0; q < R; q++)
       if (i0 + q < half) {
-        sm[i0 + q] = lo[q];
-        sm[half + i0 + q] = hi[q];
+        blk[i0 + q] = lo[q];
+        blk[half + i0 + q] = hi[q];
       }
   }
   __syncthreads();
 }
 
 template <int L, int R>
-__device__ __forceinline__ void inv_level(double* sm, int h, const FilterPair& f) {
+__device__ __forceinline__ void inv_level(double* sm, int h, int blocks, const FilterPair& f) {
   constexpr int M = L / 2;
   const int half = h >> 1, mask = half - 1;
-  const int q0 = threadIdx.x * R;
+  const int rpb = (half + R - 1) / R;
+  const int item = threadIdx.x;
+  const bool active = item < blocks * rpb;
+  const int p = item / rpb, q0 = (item - p * rpb) * R;
+  double* blk = sm + p * h;
   double e[R], o[R];
-  const bool active = q0 < half;
   if (active) {
     constexpr int W = R + M - 1;
     double wl[W], wh[W];
 #pragma unroll
     for (int t = 0; t < W; t++) {
       const int i = (q0 - (M - 1) + t) & mask;   // two's-complement mask = mod half (also when L/2 > half)
-      wl[t] = sm[i];
-      wh[t] = sm[half + i];
+      wl[t] = blk[i];
+      wh[t] = blk[half + i];
     }
 #pragma unroll
     for (int u = 0; u < R; u++) e[u] = o[u] = 0.0;
@@ -126,8 +135,8 @@ __device__ __forceinline__ void inv_level(double* sm, int h, const FilterPair& f
 #pragma unroll
     for (int u = 0; u < R; u++)
       if (q0 + u < half) {
-        sm[2 * (q0 + u)] = e[u];
-        sm[2 * (q0 + u) + 1] = o[u];
+        blk[2 * (q0 + u)] = e[u];
+        blk[2 * (q0 + u) + 1] = o[u];
       }
   }
   __syncthreads();
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(448) whole_fwd_kernel(const __grid_constant__ 
   load_row(sm, a.src + (int64_t)blockIdx.x * a.src_sig, n, a.vec);
   __syncthreads();
   int h = n;
-  for (int lev = 0; lev < a.steps; lev++, h >>= 1) fwd_level<L, R>(sm, h, f);
+  for (int lev = 0; lev < a.steps; lev++, h >>= 1) fwd_level<L, R>(sm, h, a.tree ? n / h : 1, f);
   store_row(a.dst + (int64_t)blockIdx.x * a.dst_sig, sm, n, a.vec);
 }
 
@@ -157,14 +166,19 @@ __global__ void __launch_bounds__(448) whole_inv_kernel(const __grid_constant__ 
     load_row(sm, a.src + (int64_t)blockIdx.x * a.src_sig, n, a.vec);
   __syncthreads();
   int h = n >> (a.steps - 1);
-  for (int lev = 0; lev < a.steps; lev++, h <<= 1) inv_level<L, R>(sm, h, f);
+  for (int lev = 0; lev < a.steps; lev++, h <<= 1) inv_level<L, R>(sm, h, a.tree ? n / h : 1, f);
   store_row(a.dst + (int64_t)blockIdx.x * a.dst_sig, sm, n, a.vec);
 }
 
 template <int L>
 int launch_whole(jwc_ctx* ctx, cudaStream_t st, const WholeArgs& a, const FilterPair& f, int64_t batch, bool inverse) {
   constexpr int R = (L <= 10) ? 7 : 5;
-  int threads = ((a.n / 2 + R - 1) / R + 31) / 32 * 32;   // one thread per run of the largest level
+  int items = 0;   // one thread per work item of the busiest level
+  for (int lev = 0, h = a.n; lev < a.steps; lev++, h >>= 1) {
+    const int it = (a.tree ? a.n / h : 1) * ((h / 2 + R - 1) / R);
+    if (it > items) items = it;
+  }
+  const int threads = (items + 31) / 32 * 32;
   if (threads > 448) return JWC_ERR_UNSUPPORTED;
   const size_t smem = (size_t)a.n * sizeof(double);
   if (inverse) whole_inv_kernel<L, R><<<(unsigned)batch, threads, smem, st>>>(a, f);
@@ -181,7 +195,11 @@ int launch_whole(jwc_ctx* ctx, cudaStream_t st, const WholeArgs& a, const Filter
 // warp-per-signal tail).  Every level costs the CTA two barriers -- fine for big levels, a loss for the deep end of a
 // full-depth transform (measured, n = 4096: all 12 levels here 2.13 ms, 3 levels here + 9 in the tail ~1.5 ms).
 // 0: this kernel does not apply.
-int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L) {
+int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L, bool tree) {
+  if (tree) {   // packets: every level is as big as the first, so all levels or nothing (launch_whole checks the fit)
+    if (ctx->tune.dwt_whole < 0 || n < 64 || n > 4096 || (n & (n - 1)) || steps < 1 || L < 2 || L > 20 || (L & 1)) return 0;
+    return steps;
+  }
   if (ctx->tune.dwt_whole < 0 || n <= kDwtTailLen || n > 4096 || (n & (n - 1)) || steps < 1) return 0;
   if (L < 2 || L > 20 || (L & 1)) return 0;
   if (ctx->tune.dwt_whole > 0 || (n >> steps) >= 128) return steps;
@@ -194,12 +212,12 @@ int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L) {
 // d_prefix != nullptr: the deepest approximation (n >> steps samples per signal, stride prefix_sig) is read from
 // d_prefix instead of the head of d_in.
 int whole_dwt(jwc_ctx* ctx, cudaStream_t st, const double* d_in, double* d_out, int64_t batch, int64_t n, int steps,
-              const FilterPair& f, int L, int64_t ld, bool inverse, const double* d_prefix, int64_t prefix_sig) {
-  if (n <= kDwtTailLen || n > 4096 || (n & (n - 1)) || steps < 1 || ((int64_t)1 << steps) > n) return JWC_ERR_UNSUPPORTED;
+              const FilterPair& f, int L, int64_t ld, bool inverse, const double* d_prefix, int64_t prefix_sig, bool tree) {
+  if (n < 64 || n > 4096 || (n & (n - 1)) || steps < 1 || ((int64_t)1 << steps) > n) return JWC_ERR_UNSUPPORTED;
   if (L < 2 || L > 20 || (L & 1) || batch > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
   WholeArgs a{};
-  a.src = d_in; a.dst = d_out; a.src_sig = ld; a.dst_sig = ld; a.n = (int)n; a.steps = steps;
-  a.prefix = inverse ? d_prefix : nullptr; a.prefix_sig = prefix_sig; a.prefix_len = (int)(n >> steps);
+  a.src = d_in; a.dst = d_out; a.src_sig = ld; a.dst_sig = ld; a.n = (int)n; a.steps = steps; a.tree = tree ? 1 : 0;
+  a.prefix = (inverse && !tree) ? d_prefix : nullptr; a.prefix_sig = prefix_sig; a.prefix_len = (int)(n >> steps);
   a.vec = (((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_prefix)) & 15) == 0 &&
            (ld & 1) == 0 && (prefix_sig & 1) == 0 && (a.prefix_len & 1) == 0) ? 1 : 0;
   switch (L) {

@@ -175,10 +175,10 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
 int small_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_coeffs, double* d_x,
                         int64_t batch, int64_t n, int levels, const FilterPair& f, int L);
 // whole-signal in-place FWT for 512 < n <= 4096 (jwc_dwt_whole.cu)
-int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L);
+int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L, bool tree = false);
 int whole_dwt(jwc_ctx* ctx, cudaStream_t st, const double* d_in, double* d_out, int64_t batch, int64_t n, int steps,
               const FilterPair& f, int L, int64_t ld, bool inverse, const double* d_prefix = nullptr,
-              int64_t prefix_sig = 0);
+              int64_t prefix_sig = 0, bool tree = false);
 // whole-signal-in-shared-memory forward MODWT for short signals / analysis windows (jwc_modwt_small.cu)
 int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
                         int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);

@@ -677,3 +677,27 @@ def test_fwt_whole_signal_kernel(jw, oracle, cls, n, lvl, batch, force):
     assert _maxerr(back, rref, X) <= TOL
     assert _maxerr(t.reverseBatch(got, lvl), X, X) <= PR_TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("cls,n,lvl,batch,one_launch", [
+    ("Symlet8", 4096, 6, 5, True), ("Haar1", 1024, 3, 9, True), ("Daubechies2", 64, 6, 33, True),
+    ("Daubechies10", 2048, 5, 3, True), ("Daubechies4", 2048, 11, 2, False), ("Coiflet1", 256, 8, 4, True),
+])
+def test_wpt_whole_signal_kernel(jw, oracle, cls, n, lvl, batch, one_launch):
+    """Short packet transforms: every block of every level in place in shared memory (jwc_dwt_whole.cu, tree mode);
+    depths whose busiest level has more work items than a CTA has threads fall back to the tile kernels."""
+    ctx = jw.Context([0])
+    w = jw.wavelets.create(cls)
+    t = jw.CudaWaveletPacketTransform(w, context=ctx)
+    X = splitmix_uniform(7 * n + lvl, (batch, n))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.batch("wpt_fwd", X, lvl, s, wv, nthreads=8)
+    l0 = ctx.launch_count()
+    got = t.forwardBatch(X, lvl)
+    assert (ctx.launch_count() - l0 == 1) == one_launch
+    assert _maxerr(got, ref, X) <= TOL
+    rref = oracle.batch("wpt_rev", ref, lvl, w.getScalingReConstruction(), w.getWaveletReConstruction(), nthreads=8)
+    back = t.reverseBatch(ref, lvl)
+    assert _maxerr(back, rref, X) <= TOL
+    assert _maxerr(t.reverseBatch(got, lvl), X, X) <= PR_TOL
+    ctx.close()

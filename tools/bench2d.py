@@ -17,7 +17,8 @@ import jwave_pro_b200 as jw  # noqa: E402
 
 CASES = [("fwt", "Haar1", 32, 4096, 4096, None, None), ("fwt", "Daubechies4", 32, 4096, 4096, None, None),
          ("fwt", "Daubechies8", 32, 4096, 4096, None, None), ("fwt", "Daubechies4", 128, 2048, 2048, 3, 3),
-         ("wpt", "Symlet8", 32, 4096, 4096, 3, 3), ("fwt", "Daubechies20", 32, 4096, 4096, None, None)]
+         ("wpt", "Symlet8", 32, 4096, 4096, 3, 3), ("fwt", "Daubechies20", 32, 4096, 4096, None, None),
+         ("wpt", "Daubechies4", 32, 4096, 4096, 3, 3), ("wpt", "Haar1", 32, 4096, 4096, 6, 6)]
 
 
 def main():
