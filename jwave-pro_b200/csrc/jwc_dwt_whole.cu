@@ -198,6 +198,9 @@ int launch_whole(jwc_ctx* ctx, cudaStream_t st, const WholeArgs& a, const Filter
 int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L, bool tree) {
   if (tree) {   // packets: every level is as big as the first, so all levels or nothing (launch_whole checks the fit)
     if (ctx->tune.dwt_whole < 0 || n < 64 || n > 4096 || (n & (n - 1)) || steps < 1 || L < 2 || L > 20 || (L & 1)) return 0;
+    // long filters are fp64-bound either way and the tile kernels' tap handling is better there (measured, sym8, 3
+    // levels on 131 072 rows of 4096: 3.07 ms here vs 2.69 ms) -- unless forced
+    if (L > 10 && ctx->tune.dwt_whole == 0) return 0;
     return steps;
   }
   if (ctx->tune.dwt_whole < 0 || n <= kDwtTailLen || n > 4096 || (n & (n - 1)) || steps < 1) return 0;

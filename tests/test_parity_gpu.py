@@ -682,11 +682,13 @@ def test_fwt_whole_signal_kernel(jw, oracle, cls, n, lvl, batch, force):
 @pytest.mark.parametrize("cls,n,lvl,batch,one_launch", [
     ("Symlet8", 4096, 6, 5, True), ("Haar1", 1024, 3, 9, True), ("Daubechies2", 64, 6, 33, True),
     ("Daubechies10", 2048, 5, 3, True), ("Daubechies4", 2048, 11, 2, False), ("Coiflet1", 256, 8, 4, True),
+    ("Daubechies5", 4096, 4, 3, True),
 ])
 def test_wpt_whole_signal_kernel(jw, oracle, cls, n, lvl, batch, one_launch):
     """Short packet transforms: every block of every level in place in shared memory (jwc_dwt_whole.cu, tree mode);
     depths whose busiest level has more work items than a CTA has threads fall back to the tile kernels."""
     ctx = jw.Context([0])
+    ctx.set_tuning("dwt_whole", 1)     # also for the long filters, which default to the tile kernels
     w = jw.wavelets.create(cls)
     t = jw.CudaWaveletPacketTransform(w, context=ctx)
     X = splitmix_uniform(7 * n + lvl, (batch, n))
