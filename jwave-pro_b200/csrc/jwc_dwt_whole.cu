@@ -198,9 +198,10 @@ int launch_whole(jwc_ctx* ctx, cudaStream_t st, const WholeArgs& a, const Filter
 int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L, bool tree) {
   if (tree) {   // packets: every level is as big as the first, so all levels or nothing (launch_whole checks the fit)
     if (ctx->tune.dwt_whole < 0 || n < 64 || n > 4096 || (n & (n - 1)) || steps < 1 || L < 2 || L > 20 || (L & 1)) return 0;
-    // long filters are fp64-bound either way and the tile kernels' tap handling is better there (measured, sym8, 3
-    // levels on 131 072 rows of 4096: 3.07 ms here vs 2.69 ms) -- unless forced
-    if (L > 10 && ctx->tune.dwt_whole == 0) return 0;
+    // measured on 131 072 rows of 4096 (this kernel vs the tile kernels): Haar 6 levels 2.82 vs 4.44 ms, but db4 3 levels
+    // 2.26 vs 1.93 ms and sym8 3 levels 3.07 vs 2.69 ms -- a single fused tile pass beats it, several passes do not.
+    // Default: short filters, deep transforms; anything else only when forced (dwt_whole = 1).
+    if (ctx->tune.dwt_whole == 0 && !(L <= 4 && steps >= 4)) return 0;
     return steps;
   }
   if (ctx->tune.dwt_whole < 0 || n <= kDwtTailLen || n > 4096 || (n & (n - 1)) || steps < 1) return 0;
