@@ -26,7 +26,9 @@ struct SmallArgs {
   int per_cta;       // signals per CTA
 };
 
-constexpr int kChain = 4;   // outputs per work item of the register-blocked path
+constexpr int kChain = 5;   // outputs per work item of the register-blocked path; ODD: chains start 5 strides apart, so a
+                            // warp's shared loads fall into distinct banks (4 gave 4-way conflicts, ncu: 94 M conflicts for
+                            // 16 M wavefronts); 5 rather than 7 keeps the short classes of the coarse levels >= 80 % full
 
 // LT = compile-time filter length (taps become constant-bank operands, the chain loop unrolls), 0 = run-time length.
 // Register-blocked path (LT > 0, n divisible by the stride): a thread produces the kChain outputs
