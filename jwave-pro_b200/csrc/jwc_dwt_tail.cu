@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kWarps * 32) tail_fwd_kernel(const __grid_cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t sig = (int64_t)blockIdx.x * kWarps + warp;
   if (sig >= a.batch) return;   // warps are independent: no block-wide barrier below
-  double* cur = sm + (size_t)warp * (a.h0 + a.h0 / 2);
+  double* cur = sm + (size_t)warp * ((a.h0 + a.h0 / 2 + 1) & ~1);   // even slice size: 16-byte loads stay aligned
   double* nxt = cur + a.h0;
   const double* x = a.src + sig * a.src_sig;
   for (int t = lane; t < a.h0; t += 32) ptx::cp_async8(cur + t, x + t);   // all pieces in flight together
@@ -53,10 +53,10 @@ __global__ void __launch_bounds__(kWarps * 32) tail_fwd_kernel(const __grid_cons
       double lo = 0.0, hi = 0.0;
       if constexpr (LT > 0) {
 #pragma unroll
-        for (int j = 0; j < LT; j++) {
-          const double v = cur[(2 * i + j) & mask];
-          lo = fma(v, f.f0[j], lo);
-          hi = fma(v, f.f1[j], hi);
+        for (int p = 0; p < LT / 2; p++) {   // x[2i+2p], x[2i+2p+1] as one 16-byte load (lanes 16 bytes apart)
+          const double2 v = *reinterpret_cast<const double2*>(cur + ((2 * i + 2 * p) & mask));
+          lo = fma(v.y, f.f0[2 * p + 1], fma(v.x, f.f0[2 * p], lo));
+          hi = fma(v.y, f.f1[2 * p + 1], fma(v.x, f.f1[2 * p], hi));
         }
       } else {
         for (int j = 0; j < a.L; j++) {
@@ -134,7 +134,7 @@ int launch_tail(jwc_ctx* ctx, cudaStream_t st, const TailArgs& a, const FilterPa
   const int64_t ctas = (a.batch + kWarps - 1) / kWarps;
   if (ctas <= 0) return JWC_OK;
   if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)kWarps * (inverse ? 2 * a.h0 : a.h0 + a.h0 / 2) * sizeof(double);
+  const size_t smem = (size_t)kWarps * (inverse ? 2 * a.h0 : ((a.h0 + a.h0 / 2 + 1) & ~1)) * sizeof(double);
   switch ((a.L & 1) ? 0 : a.L) {
 #define JWC_TCASE(LL)                                                                          \
   case LL:                                                                                     \
