@@ -759,8 +759,12 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
     a.nblocks = (unsigned)nblocks;
     a.pf_dist = (p.mode == DWT_BULK) ? dwt_prefetch_distance(ctx, dev, p.smem, p.threads) : 0;
-    int rc = tree ? dispatch_dwt_pass<true, true>(ctx, st, a, f, L, p.threads, p.smem, nblocks)
-                  : dispatch_dwt_pass<false, true>(ctx, st, a, f, L, p.threads, p.smem, nblocks);
+    int rc = JWC_ERR_UNSUPPORTED;
+    if (!tree)   // long signals: the tiled in-place kernel (jwc_dwt_whole.cu) takes passes of up to 3 levels
+      rc = tile_dwt_inverse_pass(ctx, st, a.ain, a.ain_sig, a.in, a.in_sig, a.out, a.out_sig, n, p.l0, p.k, batch, f, L);
+    if (rc == JWC_ERR_UNSUPPORTED)
+      rc = tree ? dispatch_dwt_pass<true, true>(ctx, st, a, f, L, p.threads, p.smem, nblocks)
+                : dispatch_dwt_pass<false, true>(ctx, st, a, f, L, p.threads, p.smem, nblocks);
     if (rc != JWC_OK) return rc;
     asrc = a.out; asrc_sig = a.out_sig;
   }

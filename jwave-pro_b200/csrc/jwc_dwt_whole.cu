@@ -170,6 +170,85 @@ __global__ void __launch_bounds__(448) whole_inv_kernel(const __grid_constant__ 
   store_row(a.dst + (int64_t)blockIdx.x * a.dst_sig, sm, n, a.vec);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same in-place synthesis for LONG signals, tile by tile (pyramid inverse passes of k <= 3 levels).
+//
+// A tile of T = 4096 output samples needs A_(l0+k)[g0/2^k ..), D_(l0+k)[g0/2^k ..), ..., D_(l0+1)[g0/2 ..): laid out
+// as [A | D_k | ... | D_1] in shared memory that IS the in-place pyramid of a T-sample signal, so the whole-signal
+// level code runs on it unchanged.  Its periodic wrap is wrong only for the first c0 = 2 (L/2-1) (2^k - 1) outputs
+// (c_(s-1) = 2 (c_s + L/2 - 1)); the tile therefore starts `pad` >= c0 samples early and throws that prefix away
+// (2.5 % recomputation for L = 16, k = 3).  The loader wraps the segment reads mod the level lengths, which makes the
+// first tile of a signal read the signal's tail -- the transform's own periodicity.
+// ---------------------------------------------------------------------------------------------------------------------
+struct TileArgs {
+  const double* ain;    // A at depth l0 + k, h >> k samples per signal
+  const double* din;    // the coefficient array (pyramid layout of the whole signal)
+  double* out;          // A at depth l0, h samples per signal
+  int64_t ain_sig, din_sig, out_sig;
+  int64_t N;            // length of the whole signal (D_j lives at [N >> j, N >> (j-1)) of din)
+  int64_t h;            // N >> l0
+  int l0, k;
+  int T, pad, valid;    // tile length, discarded prefix, outputs kept per tile (T - pad)
+  int tiles;
+};
+
+template <int L, int R>
+__global__ void __launch_bounds__(448) tile_inv_kernel(const __grid_constant__ TileArgs a,
+                                                       const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  const int64_t b = blockIdx.x / a.tiles;
+  const int t = blockIdx.x - (int)(b * a.tiles);
+  const int64_t o0 = (int64_t)t * a.valid;       // first output this tile keeps
+  const int64_t g0 = o0 - a.pad;                 // first output it computes (multiple of 2^k; negative for tile 0)
+  const int T = a.T;
+  // gather the k + 1 segments; every level length is a power of two, so wrapping is a mask
+  {
+    const double* ain = a.ain + b * a.ain_sig;
+    const double* din = a.din + b * a.din_sig;
+    const int seg = T >> a.k;
+    const int64_t len = a.h >> a.k, start = g0 >> a.k;   // arithmetic shift: floor, also for negative g0
+    for (int i = threadIdx.x; i < seg; i += blockDim.x) {
+      const int64_t src = (start + i) & (len - 1);
+      ptx::cp_async8(sm + i, ain + src);
+      ptx::cp_async8(sm + seg + i, din + (a.N >> (a.l0 + a.k)) + src);
+    }
+    for (int s = a.k - 1; s >= 1; s--) {
+      const int segs = T >> s;                            // D_(l0+s): T >> s samples at [T >> s, T >> (s-1))
+      const int64_t lens = a.h >> s, starts = g0 >> s;
+      const double* d = din + (a.N >> (a.l0 + s));
+      for (int i = 2 * threadIdx.x; i < segs; i += 2 * blockDim.x)
+        ptx::cp_async16(sm + segs + i, d + ((starts + i) & (lens - 1)));   // starts even, lens even: pairs stay together
+    }
+    ptx::cp_async_commit_wait_all();
+  }
+  __syncthreads();
+  int h = T >> (a.k - 1);
+  for (int lev = 0; lev < a.k; lev++, h <<= 1) inv_level<L, R>(sm, h, 1, f);
+  double* out = a.out + b * a.out_sig + o0;
+  int64_t keep = a.h - o0;
+  if (keep > a.valid) keep = a.valid;
+  for (int i = 2 * threadIdx.x; i < keep; i += 2 * blockDim.x)
+    *reinterpret_cast<double2*>(out + i) = *reinterpret_cast<const double2*>(sm + a.pad + i);
+}
+
+template <int L>
+int launch_tile_inv(jwc_ctx* ctx, cudaStream_t st, TileArgs a, const FilterPair& f, int64_t batch) {
+  constexpr int R = (L <= 10) ? 7 : 5;
+  a.T = 4096;
+  const int c0 = 2 * (L / 2 - 1) * ((1 << a.k) - 1);
+  a.pad = (c0 + 7) & ~7;                    // multiple of 2^k (k <= 3) and of two doubles
+  a.valid = a.T - a.pad;
+  a.tiles = (int)((a.h + a.valid - 1) / a.valid);
+  const int64_t ctas = (int64_t)a.tiles * batch;
+  if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  const int threads = ((a.T / 2 + R - 1) / R + 31) / 32 * 32;
+  const size_t smem = (size_t)a.T * sizeof(double);
+  tile_inv_kernel<L, R><<<(unsigned)ctas, threads, smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
 template <int L>
 int launch_whole(jwc_ctx* ctx, cudaStream_t st, const WholeArgs& a, const FilterPair& f, int64_t batch, bool inverse) {
   constexpr int R = (L <= 10) ? 7 : 5;
@@ -226,6 +305,32 @@ int whole_dwt(jwc_ctx* ctx, cudaStream_t st, const double* d_in, double* d_out, 
            (ld & 1) == 0 && (prefix_sig & 1) == 0 && (a.prefix_len & 1) == 0) ? 1 : 0;
   switch (L) {
 #define JWC_WCASE(LL) case LL: return launch_whole<LL>(ctx, st, a, f, batch, inverse);
+    JWC_WCASE(2) JWC_WCASE(4) JWC_WCASE(6) JWC_WCASE(8) JWC_WCASE(10) JWC_WCASE(12) JWC_WCASE(14) JWC_WCASE(16)
+    JWC_WCASE(18) JWC_WCASE(20)
+#undef JWC_WCASE
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
+// One pyramid-inverse pass of k <= 3 levels on long signals (h = N >> l0 >= 16384) with the tiled in-place kernel.
+// Needs 16-byte aligned rows everywhere (the caller checks the strides it chose); JWC_ERR_UNSUPPORTED otherwise.
+int tile_dwt_inverse_pass(jwc_ctx* ctx, cudaStream_t st, const double* ain, int64_t ain_sig, const double* din,
+                          int64_t din_sig, double* out, int64_t out_sig, int64_t N, int l0, int k, int64_t batch,
+                          const FilterPair& f, int L) {
+  // Opt-in only (dwt_tile_inv = 1): measured on C3 (1024 x 2^20, 20 levels) it LOSES to the TMA tile kernels of
+  // jwc_dwt_fast.cu -- Haar inverse 3.24 vs 3.11 ms, db8 5.66 vs 4.87 ms (element-wise cp.async gathers of four
+  // segments and six block barriers per tile, against bulk copies with L2 prefetch).  Kept as the cross-check it is.
+  if (ctx->tune.dwt_tile_inv <= 0 || L < 2 || L > 20 || (L & 1) || k < 1 || k > 3) return JWC_ERR_UNSUPPORTED;
+  const int64_t h = N >> l0;
+  if (h < 16384 || (h & (h - 1))) return JWC_ERR_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(ain) | reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(out)) & 15) ||
+      ((ain_sig | din_sig | out_sig) & 1))
+    return JWC_ERR_UNSUPPORTED;
+  TileArgs a{};
+  a.ain = ain; a.din = din; a.out = out; a.ain_sig = ain_sig; a.din_sig = din_sig; a.out_sig = out_sig;
+  a.N = N; a.h = h; a.l0 = l0; a.k = k;
+  switch (L) {
+#define JWC_WCASE(LL) case LL: return launch_tile_inv<LL>(ctx, st, a, f, batch);
     JWC_WCASE(2) JWC_WCASE(4) JWC_WCASE(6) JWC_WCASE(8) JWC_WCASE(10) JWC_WCASE(12) JWC_WCASE(14) JWC_WCASE(16)
     JWC_WCASE(18) JWC_WCASE(20)
 #undef JWC_WCASE

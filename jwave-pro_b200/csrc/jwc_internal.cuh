@@ -52,6 +52,7 @@ struct Tuning {
   int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
   int modwt_small = 0;      // whole-signal forward MODWT kernel for n <= 2048: 0 = auto, -1 = off, 1 = whenever it fits
+  int dwt_tile_inv = 0;     // tiled in-place kernel for the pyramid-inverse passes of long signals: 1 = on (default off: slower)
   int dwt_whole = 0;        // whole-signal in-place FWT kernel for 512 < n <= 4096: 0 = auto, -1 = off
   int dwt_tail = 0;         // warp-per-signal pyramid tail for short signals: 0 = auto, -1 = off
   int h2d_buffers = 0;      // host pipeline staging depth (1..4), 0 = auto
@@ -179,6 +180,9 @@ int whole_dwt_levels(const jwc_ctx* ctx, int64_t n, int steps, int L, bool tree 
 int whole_dwt(jwc_ctx* ctx, cudaStream_t st, const double* d_in, double* d_out, int64_t batch, int64_t n, int steps,
               const FilterPair& f, int L, int64_t ld, bool inverse, const double* d_prefix = nullptr,
               int64_t prefix_sig = 0, bool tree = false);
+int tile_dwt_inverse_pass(jwc_ctx* ctx, cudaStream_t st, const double* ain, int64_t ain_sig, const double* din,
+                          int64_t din_sig, double* out, int64_t out_sig, int64_t N, int l0, int k, int64_t batch,
+                          const FilterPair& f, int L);
 // whole-signal-in-shared-memory forward MODWT for short signals / analysis windows (jwc_modwt_small.cu)
 int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
                         int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);

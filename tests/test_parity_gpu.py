@@ -703,3 +703,21 @@ def test_wpt_whole_signal_kernel(jw, oracle, cls, n, lvl, batch, one_launch):
     assert _maxerr(back, rref, X) <= TOL
     assert _maxerr(t.reverseBatch(got, lvl), X, X) <= PR_TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("cls,n,lvl", [("Haar1", 1 << 16, 16), ("Daubechies8", 1 << 15, 9), ("Symlet5", 1 << 17, 4)])
+def test_fwt_inverse_tiled_in_place_variant(jw, oracle, cls, n, lvl):
+    """The opt-in tiled in-place inverse pass (dwt_tile_inv = 1; slower than the default TMA tile kernels, kept as an
+    independent implementation): same results."""
+    ctx = jw.Context([0])
+    ctx.set_tuning("dwt_tile_inv", 1)
+    w = jw.wavelets.create(cls)
+    t = jw.CudaFastWaveletTransform(w, context=ctx)
+    X = splitmix_uniform(n + lvl, (3, n))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.batch("fwt_fwd", X, lvl, s, wv, nthreads=8)
+    rref = oracle.batch("fwt_rev", ref, lvl, w.getScalingReConstruction(), w.getWaveletReConstruction(), nthreads=8)
+    assert _maxerr(t.reverseBatch(ref, lvl), rref, X) <= TOL
+    assert np.array_equal(t.reverseBatch(ref, lvl), jw.CudaFastWaveletTransform(w).reverseBatch(ref, lvl)) or \
+        _maxerr(t.reverseBatch(ref, lvl), jw.CudaFastWaveletTransform(w).reverseBatch(ref, lvl), X) <= TOL
+    ctx.close()
