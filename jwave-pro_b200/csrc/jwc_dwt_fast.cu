@@ -24,6 +24,11 @@ namespace jwc {
 
 namespace {
 
+#ifndef JWC_SYN_DIRECT
+#define JWC_SYN_DIRECT 0
+#endif
+constexpr bool kSynDirect = JWC_SYN_DIRECT != 0;   // experiment: constant-operand taps in the pyramid inverse for 12 <= L <= 20;
+                                                   // measured (C3 db8 inverse): 7.98 ms vs 4.87 ms with the shared-memory taps -> off
 constexpr int kUniformTapsMaxDwt = 10;   // longer filters read their taps from a shared-memory copy (see MODWT kernel)
 
 void debug_dwt_plan(const char* what, const DwtPlan& plan, int64_t n, int levels, int L, bool tree) {
@@ -304,11 +309,12 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
 // =========================================================================================================================
 // inverse (synthesis)
 // =========================================================================================================================
-template <int L, int R, bool QMF, int NS>
+// DIRECT: taps as constant-bank operands of the DFMAs (f.f0[static index]) also for long filters -- no tap registers
+template <int L, int R, bool QMF, int NS, bool DIRECT = false>
 __device__ __forceinline__ void syn_item(const double* __restrict__ plo, const double* __restrict__ phi,
                                          const FilterPair& f, const double* __restrict__ taps, const double (&sreg)[NS],
                                          double2 (&o)[R]) {
-  constexpr bool ST = (L > kUniformTapsMaxDwt) && !QMF;
+  constexpr bool ST = (L > kUniformTapsMaxDwt) && !QMF && !DIRECT;
   constexpr int HL = L / 2;
 #pragma unroll
   for (int r = 0; r < R; r++) { o[r].x = 0.0; o[r].y = 0.0; }
@@ -370,7 +376,7 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, con
     const int u0 = (w - q * nb) * R;
     const int clo = oin + (2 * q) * st_in + off + u0;
     double2 o[R];
-    syn_item<L, R, QMF, NS>(smem + clo, smem + clo + st_in, f, ctaps, sreg, o);
+    syn_item<L, R, QMF, NS, kSynDirect && !TREE && (L > kUniformTapsMaxDwt) && (L <= 20)>(smem + clo, smem + clo + st_in, f, ctaps, sreg, o);
     double2* dst = reinterpret_cast<double2*>(smem + oout + q * st_out) + u0;
     if (u0 + R <= np) {
 #pragma unroll
