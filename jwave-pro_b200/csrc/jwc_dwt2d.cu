@@ -416,7 +416,7 @@ int launch_fused(jwc_ctx* ctx, cudaStream_t st, ColFuseArgs a, const FilterPair&
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-      JWC_CUDA_CHECK(cudaFuncSetAttribute(col_ana_fused_kernel<L, K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      JWC_CUDA_CHECK(allow_max_dynamic_smem(col_ana_fused_kernel<L, K, T>));
       configured_dev = dev;
     }
     col_ana_fused_kernel<L, K, T><<<grid, block, smem, st>>>(a, f);
@@ -426,7 +426,7 @@ int launch_fused(jwc_ctx* ctx, cudaStream_t st, ColFuseArgs a, const FilterPair&
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-      JWC_CUDA_CHECK(cudaFuncSetAttribute(col_syn_fused_kernel<L, K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      JWC_CUDA_CHECK(allow_max_dynamic_smem(col_syn_fused_kernel<L, K, T>));
       configured_dev = dev;
     }
     col_syn_fused_kernel<L, K, T><<<grid, block, smem, st>>>(a, f);

@@ -538,11 +538,11 @@ int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const F
                     int64_t nblocks) {
   if (INV) {
     auto kern = dwt_inv_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
-    JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   } else {
     auto kern = dwt_fwd_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
-    JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   }
   count_launch(ctx);

@@ -213,6 +213,37 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
 int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
                      int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, int64_t ld = 0);
 
+// The dynamic-shared-memory cap of a kernel is per-function state shared by every host thread: setting it to "what this
+// launch needs" races with a concurrent launch of the same instantiation that needs more (found by the concurrent
+// device-call test: cudaErrorInvalidValue at launch).  So every kernel gets the SAME cap once per device: the opt-in
+// maximum minus its static shared memory; the carve-out actually used still follows each launch's own request.
+inline cudaError_t allow_max_dynamic_smem_impl(const void* kern) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, bool> done;   // (kernel, device ordinal)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count(std::make_pair(kern, dev))) return cudaSuccess;
+  }
+  int optin = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(mu);
+    done[std::make_pair(kern, dev)] = true;
+  }
+  return e;
+}
+template <typename Kern>
+inline cudaError_t allow_max_dynamic_smem(Kern kern) {
+  return allow_max_dynamic_smem_impl(reinterpret_cast<const void*>(kern));
+}
+
 inline void count_launch(jwc_ctx* ctx, uint64_t k = 1) { ctx->launches.fetch_add(k, std::memory_order_relaxed); }
 
 template <bool EXACT>

@@ -303,7 +303,7 @@ template <int L>
 int launch_fwd_pass(jwc_ctx* ctx, cudaStream_t st, const FwdPassArgs& a, const FilterPair& f, int threads, size_t smem,
                     int64_t nblocks) {
   auto kern = modwt_fwd_pass_kernel<L, kModwtR>;
-  JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
   kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());
@@ -596,7 +596,7 @@ template <int L>
 int launch_inv_pass(jwc_ctx* ctx, cudaStream_t st, const InvPassArgs& a, const FilterPair& f, int threads, size_t smem,
                     int64_t nblocks) {
   auto kern = modwt_inv_pass_kernel<L, kModwtR>;
-  JWC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
   kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());

@@ -264,14 +264,14 @@ int small_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
   switch (L) {
 #define JWC_SCASE(LL)                                                                                               \
   case LL:                                                                                                          \
-    JWC_CUDA_CHECK(cudaFuncSetAttribute(modwt_small_inv_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); \
+    JWC_CUDA_CHECK(allow_max_dynamic_smem(modwt_small_inv_kernel<LL>)); \
     modwt_small_inv_kernel<LL><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);                                         \
     break;
     JWC_SCASE(2) JWC_SCASE(4) JWC_SCASE(6) JWC_SCASE(8) JWC_SCASE(10) JWC_SCASE(12) JWC_SCASE(14) JWC_SCASE(16)
     JWC_SCASE(18) JWC_SCASE(20)
 #undef JWC_SCASE
     default:
-      JWC_CUDA_CHECK(cudaFuncSetAttribute(modwt_small_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      JWC_CUDA_CHECK(allow_max_dynamic_smem(modwt_small_inv_kernel<0>));
       modwt_small_inv_kernel<0><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);
       break;
   }

@@ -721,3 +721,57 @@ def test_fwt_inverse_tiled_in_place_variant(jw, oracle, cls, n, lvl):
     assert np.array_equal(t.reverseBatch(ref, lvl), jw.CudaFastWaveletTransform(w).reverseBatch(ref, lvl)) or \
         _maxerr(t.reverseBatch(ref, lvl), jw.CudaFastWaveletTransform(w).reverseBatch(ref, lvl), X) <= TOL
     ctx.close()
+
+
+def test_workspace_arenas_under_concurrent_device_calls(jw, oracle):
+    """Multi-pass transforms take their workspace from the context's per-stream arenas.  Six host threads enqueue 2-D
+    FWTs and deep 1-D FWTs on ONE context at once -- three on the context's shared stream, three on private streams --
+    and every result must be right; then the arenas are released and the context still works."""
+    import torch
+    ctx = jw.Context([0])
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaFastWaveletTransform(w, context=ctx)
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    X2 = splitmix_uniform(3, (4, 256, 512))
+    ref2 = oracle.batch2d("fwt", X2, 8, 9, s, wv, nthreads=8)
+    X1 = splitmix_uniform(4, (6, 1 << 16))
+    ref1 = oracle.batch("fwt_fwd", X1, 16, s, wv, nthreads=8)
+    dX2, dX1 = torch.from_numpy(X2).cuda(), torch.from_numpy(X1).cuda()
+    torch.cuda.synchronize()
+    errs = []
+
+    def work(tid):
+        try:
+            st = torch.cuda.Stream() if tid % 2 else None
+            stream = st.cuda_stream if st is not None else None
+            for it in range(8):
+                o2, o1 = torch.empty_like(dX2), torch.empty_like(dX1)
+                kw = {} if stream is None else {"stream": stream}
+                if stream is None:   # the context's own stream: pass NULL through the raw ABI
+                    lib = jw._native.load()
+                    dp = ctypes.POINTER(ctypes.c_double)
+                    f0, f1 = np.ascontiguousarray(s), np.ascontiguousarray(wv)
+                    rc = lib.jwc_fwt2d_forward_dev(ctx.handle, 0, None, ctypes.c_void_p(dX2.data_ptr()),
+                                                   ctypes.c_void_p(o2.data_ptr()), 4, 256, 512, 8, 9,
+                                                   f0.ctypes.data_as(dp), f1.ctypes.data_as(dp), len(f0), 0)
+                    rc |= lib.jwc_fwt_forward_dev(ctx.handle, 0, None, ctypes.c_void_p(dX1.data_ptr()),
+                                                  ctypes.c_void_p(o1.data_ptr()), 6, 1 << 16, 16,
+                                                  f0.ctypes.data_as(dp), f1.ctypes.data_as(dp), len(f0), 0)
+                    assert rc == 0, lib.jwc_last_error()
+                    ctx.synchronize()
+                else:
+                    t.forward2DDevice(dX2.data_ptr(), o2.data_ptr(), 4, 256, 512, 8, 9, **kw)
+                    t.forwardDevice(dX1.data_ptr(), o1.data_ptr(), 6, 1 << 16, 16, **kw)
+                    st.synchronize()
+                if _maxerr(o2.cpu().numpy(), ref2, X2) > TOL or _maxerr(o1.cpu().numpy(), ref1, X1) > TOL:
+                    errs.append((tid, it))
+        except Exception as e:   # noqa: BLE001
+            errs.append((tid, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [x_.start() for x_ in th]
+    [x_.join() for x_ in th]
+    assert not errs, errs[:3]
+    ctx.release_scratch()
+    assert _maxerr(t.forward2DBatch(X2, 8, 9), ref2, X2) <= TOL
+    ctx.close()
