@@ -775,3 +775,39 @@ def test_workspace_arenas_under_concurrent_device_calls(jw, oracle):
     ctx.release_scratch()
     assert _maxerr(t.forward2DBatch(X2, 8, 9), ref2, X2) <= TOL
     ctx.close()
+
+
+def test_mixed_shapes_from_many_threads(jw, gpu_ctx, oracle):
+    """Eight host threads on the default context, each with its own transform, wavelet and shape (different kernel
+    instantiations, shared-memory sizes and pass plans), through the host-buffer API."""
+    jobs = [("modwt", "Daubechies4", 4096, 6), ("modwt", "Daubechies20", 8192, 5), ("fwt", "Haar1", 1 << 15, 15),
+            ("fwt", "Daubechies8", 1 << 14, 14), ("wpt", "Symlet8", 4096, 6), ("wpt", "Daubechies2", 1 << 13, 5),
+            ("fwt", "Symlet10", 2048, 3), ("modwt", "Haar1", 512, 8)]
+    refs, errs = [], []
+    for kind, cls, n, lvl in jobs:
+        w = jw.wavelets.create(cls)
+        X = splitmix_uniform(n + lvl, (5, n))
+        if kind == "modwt":
+            ref, _ = _modwt_oracle(oracle, w, X, lvl)
+        else:
+            ref = oracle.batch(kind + "_fwd", X, lvl, w.getScalingDeComposition(), w.getWaveletDeComposition(), nthreads=4)
+        refs.append((w, X, ref))
+
+    def work(i):
+        kind, cls, n, lvl = jobs[i]
+        w, X, ref = refs[i]
+        try:
+            t = {"modwt": jw.CudaMODWTTransform, "fwt": jw.CudaFastWaveletTransform,
+                 "wpt": jw.CudaWaveletPacketTransform}[kind](w)
+            for it in range(12):
+                got = t.forwardMODWTBatch(X, lvl) if kind == "modwt" else t.forwardBatch(X, lvl)
+                back = t.inverseMODWTBatch(got) if kind == "modwt" else t.reverseBatch(got, lvl)
+                if _maxerr(got, ref, X) > TOL or _maxerr(back, X, X) > PR_TOL:
+                    errs.append((i, it))
+        except Exception as e:   # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    [x_.start() for x_ in th]
+    [x_.join() for x_ in th]
+    assert not errs, errs[:3]
