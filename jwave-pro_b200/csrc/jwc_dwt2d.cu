@@ -566,7 +566,9 @@ int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
   // Schedule first (fused launches of 2-3 levels where the shape allows, single levels otherwise), then allocate.
   std::vector<int> sched;
   for (int l = 0; l < steps;) {
-    int k = exact ? 0 : fused_levels_fwd(L, rows >> l, cols, steps - l);
+    // the fused launch stages its rows with 16-byte cp.async: the first launch reads the caller's buffer
+    const bool aligned = l > 0 || (reinterpret_cast<uintptr_t>(d_src) & 15) == 0;
+    int k = (exact || !aligned) ? 0 : fused_levels_fwd(L, rows >> l, cols, steps - l);
     if (k < 2) k = 1;
     sched.push_back(k);
     l += k;

@@ -811,3 +811,52 @@ def test_mixed_shapes_from_many_threads(jw, gpu_ctx, oracle):
     [x_.start() for x_ in th]
     [x_.join() for x_ in th]
     assert not errs, errs[:3]
+
+
+def test_device_pointers_that_are_only_8_byte_aligned(jw, gpu_ctx, oracle):
+    """Views into larger device arrays start on any 8-byte boundary: every vectorised / bulk / cp.async16 path must
+    notice and fall back to its element-wise loaders."""
+    import torch
+    w = jw.wavelets.Daubechies4()
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    f = jw.CudaFastWaveletTransform(w)
+    m = jw.CudaMODWTTransform(w)
+
+    def odd_view(arr):      # same values, data pointer = 16k + 8
+        big = torch.empty(arr.size + 1, dtype=torch.float64, device="cuda")
+        big[1:] = torch.from_numpy(arr.reshape(-1)).cuda()
+        assert big[1:].data_ptr() % 16 == 8
+        return big, big[1:]
+
+    def odd_out(count):
+        big = torch.empty(count + 1, dtype=torch.float64, device="cuda")
+        return big, big[1:]
+
+    # 2-D (fused column launches), short-signal FWT (whole-signal kernel), long FWT (bulk-copy tiles), MODWT tiles, windows
+    X2 = splitmix_uniform(1, (2, 256, 64))
+    _, dx = odd_view(X2); _, do = odd_out(X2.size)
+    f.forward2DDevice(dx.data_ptr(), do.data_ptr(), 2, 256, 64, 8, 6)
+    torch.cuda.synchronize()
+    assert _maxerr(do.cpu().numpy().reshape(X2.shape), oracle.batch2d("fwt", X2, 8, 6, s, wv), X2) <= TOL
+    for n, lvl in ((2048, 3), (1 << 16, 16), (300 * 0 + 512, 9)):
+        X = splitmix_uniform(n, (3, n))
+        _, dx = odd_view(X); _, do = odd_out(X.size)
+        f.forwardDevice(dx.data_ptr(), do.data_ptr(), 3, n, lvl)
+        torch.cuda.synchronize()
+        ref = oracle.batch("fwt_fwd", X, lvl, s, wv)
+        assert _maxerr(do.cpu().numpy().reshape(X.shape), ref, X) <= TOL
+        _, dc = odd_view(ref); _, dr = odd_out(X.size)
+        f.reverseDevice(dc.data_ptr(), dr.data_ptr(), 3, n, lvl)
+        torch.cuda.synchronize()
+        assert _maxerr(dr.cpu().numpy().reshape(X.shape), X, X) <= PR_TOL
+    for n, J in ((8192, 6), (512, 8)):
+        X = splitmix_uniform(n + 1, (3, n))
+        ref, _ = _modwt_oracle(oracle, w, X, J)
+        _, dx = odd_view(X); _, do = odd_out(ref.size)
+        m.forwardMODWTDevice(dx.data_ptr(), do.data_ptr(), 3, n, J)
+        torch.cuda.synchronize()
+        assert _maxerr(do.cpu().numpy().reshape(ref.shape), ref, X) <= TOL
+        _, dr = odd_out(X.size)
+        m.inverseMODWTDevice(do.data_ptr(), dr.data_ptr(), 3, n, J)
+        torch.cuda.synchronize()
+        assert _maxerr(dr.cpu().numpy().reshape(X.shape), X, X) <= PR_TOL
