@@ -131,3 +131,26 @@ def test_ancient_egyptian_multipliers(jw, oracle):
         assert sum(1 << p for p in dec(n)) == n and dec(n) == oracle.aed_blocks(n)
     with pytest.raises(jw.JWaveFailure):
         dec(0)
+
+
+def test_2d_and_window_argument_checks_need_no_gpu(jw):
+    """Validation happens on the host before any native call, with the reference's exception types and message
+    substrings (BasicTransform.java:336-399 delegates to the 1-D checks of FastWaveletTransform.java:74-83)."""
+    f = jw.CudaFastWaveletTransform(jw.wavelets.Daubechies4())
+    with pytest.raises(jw.JWaveFailure, match=r"2\^p"):
+        f.forward(np.zeros((6, 8)))                 # rows not a power of two
+    with pytest.raises(jw.JWaveFailure, match=r"2\^p"):
+        f.forward2DBatch(np.zeros((2, 8, 12)))      # cols not a power of two
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        f.forward(np.zeros((8, 8)), 4, 3)
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        f.reverse(np.zeros((8, 8)), 3, -1)
+    m = jw.CudaMODWTTransform(jw.wavelets.Haar1())
+    with pytest.raises(jw.IllegalArgumentException):
+        m.forwardMODWTWindows(np.zeros(100), 128, 16, 3)      # window longer than the series
+    with pytest.raises(jw.IllegalArgumentException):
+        m.forwardMODWTWindows(np.zeros(100), 32, 0, 3)        # hop < 1
+    with pytest.raises(jw.IllegalArgumentException, match="exceeds theoretical limit"):
+        m.forwardMODWTWindows(np.zeros(100), 32, 8, 6)        # J > log2(window)
+    with pytest.raises(jw.JWaveFailure):
+        jw.AncientEgyptianDecomposition(m)                     # only the pyramid transforms can be wrapped
