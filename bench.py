@@ -239,6 +239,16 @@ def main():
         torch.cuda.set_device(devices[0])
     n_gpus = world if distributed else len(devices)
 
+    numa = None
+    if distributed and not os.environ.get("JWC_NO_CPU_AFFINITY"):
+        # one process per GPU: run (and first-touch the pinned staging buffers) on the CPUs next to this rank's GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = "cpu affinity of rank = NVML ideal CPUs of its GPU (%d cpus)" % len(os.sched_getaffinity(0))
+        except Exception as e:  # noqa: BLE001
+            numa = "cpu affinity not set (%s)" % type(e).__name__
     ctx = jw.Context(devices)
     for kv in filter(None, args.tune.split(",")):
         k, v = kv.split("=")
@@ -488,7 +498,7 @@ def main():
             "config": {"workload": workload_desc(args.workload, kind, cls, levels, batch, n),
                        "l2": "inputs larger than L2 (%.1f GiB read per direction vs 126 MB L2)" % (
                            (out_rows if kind in ("modwt", "windows") else 1) * batch * unit * 8 / 2 ** 30),
-                       "sharding": "by signal, no collective", "tune": args.tune, "flags": args.flags,
+                       "sharding": "by signal, no collective", "numa": numa, "tune": args.tune, "flags": args.flags,
                        "round_trip_max_err": pr},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         }
