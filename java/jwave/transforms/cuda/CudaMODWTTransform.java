@@ -107,4 +107,19 @@ public class CudaMODWTTransform extends MODWTTransform {
     double[][] f = filters();
     JwcNative.run(JwcNative.MODWT_INVERSE, CudaContext.get(), coeffs, x, batch, n, maxLevel, f[0], f[1], 0);
   }
+
+  /**
+   * Sliding-window analysis of one long series (the loop of MODWTSlidingWindowTest.java:20-70 without the per-window
+   * arraycopy): window w = series[w*hop .. w*hop + window), coeffs [nWindows][maxLevel+1][window], with
+   * nWindows = (seriesLength - window) / hop + 1.  The windows are read in place on the device.
+   */
+  public void forwardMODWTWindows(MemorySegment series, MemorySegment coeffs, long seriesLength, int window, long hop,
+      int maxLevel) {
+    checkLevel(maxLevel);
+    checkLimit(maxLevel, window);
+    if (window < 1 || hop < 1 || seriesLength < window)
+      throw new IllegalArgumentException("need 1 <= window <= series length and hop >= 1");
+    double[][] f = filters();
+    JwcNative.runWindows(CudaContext.get(), series, coeffs, seriesLength, window, hop, maxLevel, f[0], f[1], 0);
+  }
 }

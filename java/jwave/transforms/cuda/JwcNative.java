@@ -34,6 +34,7 @@ public final class JwcNative {
   private static final String[] NAMES_2D = {
       "jwc_fwt2d_forward", "jwc_fwt2d_inverse", "jwc_wpt2d_forward", "jwc_wpt2d_inverse" };
   public static final int FWT2D_FORWARD = 0, FWT2D_INVERSE = 1, WPT2D_FORWARD = 2, WPT2D_INVERSE = 3;
+  private static final MethodHandle WINDOWS;
   private static final MethodHandle[] TRANSFORMS_AED = new MethodHandle[4];
   private static final String[] NAMES_AED = {
       "jwc_fwt_aed_forward", "jwc_fwt_aed_inverse", "jwc_wpt_aed_forward", "jwc_wpt_aed_inverse" };
@@ -69,6 +70,10 @@ public final class JwcNative {
     FunctionDescriptor ta = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS,
         ADDRESS, JAVA_INT, JAVA_INT);
     for (int i = 0; i < NAMES_AED.length; i++) TRANSFORMS_AED[i] = handle(NAMES_AED[i], ta);
+    // int jwc_modwt_forward_windows(jwc_ctx*, const double* series, double* coeffs, int64 series_len, int64 window,
+    //                               int64 hop, int levels, const double* g, const double* h, int L, unsigned flags)
+    WINDOWS = handle("jwc_modwt_forward_windows", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG,
+        JAVA_LONG, JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
   }
 
   private static MethodHandle handle(String name, FunctionDescriptor fd) {
@@ -201,6 +206,21 @@ public final class JwcNative {
       MemorySegment so = a.allocateArray(JAVA_DOUBLE, in.length);
       runAed(which, ctx, si, so, 1, in.length, f0, f1, flags);
       return so.toArray(JAVA_DOUBLE);
+    }
+  }
+
+  /** Forward MODWT of every window series[w*hop .. w*hop + window) of one series; coeffs [nwin][levels+1][window]. */
+  public static void runWindows(MemorySegment ctx, MemorySegment series, MemorySegment coeffs, long seriesLength,
+      long window, long hop, int levels, double[] g, double[] h, int flags) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment s0 = a.allocateArray(JAVA_DOUBLE, g);
+      MemorySegment s1 = a.allocateArray(JAVA_DOUBLE, h);
+      int rc = (int) WINDOWS.invokeExact(ctx, series, coeffs, seriesLength, window, hop, levels, s0, s1, g.length, flags);
+      if (rc != 0) throw new IllegalStateException("jwc_modwt_forward_windows failed (" + rc + "): " + lastError());
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
     }
   }
 }
