@@ -549,6 +549,8 @@ def test_modwt_coefficients_format_from_device_layout(jw, gpu_ctx, oracle):
     ("Coiflet2", 1, 4),
     ("Daubechies2", 1 << 12, 2),      # a power of two: one block, identical to the plain transform
     ("Daubechies3", 200000, 2),       # blocks above and below the short-signal tail threshold
+    ("Daubechies4", 4097, 3),         # 4096 | 1 with an odd row stride: whole-signal / tail kernels without 16-byte alignment
+    ("Haar1", 2048 + 1024 + 2, 4),
 ])
 def test_ancient_egyptian_decomposition(jw, gpu_ctx, oracle, kind, cls, n, batch):
     w = jw.wavelets.create(cls)
