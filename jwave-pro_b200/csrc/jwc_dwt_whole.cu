@@ -143,7 +143,7 @@ __device__ __forceinline__ void inv_level(double* sm, int h, int blocks, const F
 }
 
 template <int L, int R>
-__global__ void __launch_bounds__(448) whole_fwd_kernel(const __grid_constant__ WholeArgs a,
+__global__ void __launch_bounds__(R == 7 ? 320 : 416, R == 7 ? 4 : 3) whole_fwd_kernel(const __grid_constant__ WholeArgs a,
                                                         const __grid_constant__ FilterPair f) {
   extern __shared__ double sm[];
   const int n = a.n;
@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(448) whole_fwd_kernel(const __grid_constant__ 
   store_row(a.dst + (int64_t)blockIdx.x * a.dst_sig, sm, n, a.vec);
 }
 
+// R = 7 launches at most 320 threads, R = 5 at most 416: four resp. three CTAs of 32 KB per SM
 template <int L, int R>
-__global__ void __launch_bounds__(448) whole_inv_kernel(const __grid_constant__ WholeArgs a,
+__global__ void __launch_bounds__(R == 7 ? 320 : 416, R == 7 ? 4 : 3) whole_inv_kernel(const __grid_constant__ WholeArgs a,
                                                         const __grid_constant__ FilterPair f) {
   extern __shared__ double sm[];
   const int n = a.n;
@@ -258,7 +259,7 @@ int launch_whole(jwc_ctx* ctx, cudaStream_t st, const WholeArgs& a, const Filter
     if (it > items) items = it;
   }
   const int threads = (items + 31) / 32 * 32;
-  if (threads > 448) return JWC_ERR_UNSUPPORTED;
+  if (threads > (R == 7 ? 320 : 416)) return JWC_ERR_UNSUPPORTED;
   const size_t smem = (size_t)a.n * sizeof(double);
   if (inverse) whole_inv_kernel<L, R><<<(unsigned)batch, threads, smem, st>>>(a, f);
   else         whole_fwd_kernel<L, R><<<(unsigned)batch, threads, smem, st>>>(a, f);
