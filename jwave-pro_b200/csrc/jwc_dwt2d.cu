@@ -469,6 +469,134 @@ int run_fused(jwc_ctx* ctx, cudaStream_t st, const ColFuseArgs& a, const FilterP
   return JWC_ERR_UNSUPPORTED;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Wavelet-packet columns, two levels per launch (forward).  A tile of T rows of one block (height h, periodic within
+// the block) gives T/2 + (L-2) rows of BOTH level-1 children (low and high keep their halo: both are split again),
+// then T/4 rows of each of the four grandchildren, which go to their quarters of the block in the output matrix:
+// [LL | LH | HL | HH].  Traffic of the two levels: one read + one write of the matrix instead of two of each.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ColTreeArgs {
+  const double* src;
+  double* dst;
+  int64_t mat;          // matrix stride (src and dst have the same shape)
+  int64_t ld, cols;
+  int64_t h;            // block height at the first of the two levels
+  int64_t tiles, strips, blocks;
+  int lg_strips, lg_tiles, lg_blocks;
+};
+
+template <int L, int T>
+__global__ void __launch_bounds__(kStrip* kGroups) col_ana_tree2_kernel(const __grid_constant__ ColTreeArgs a,
+                                                                        const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  constexpr int H1 = L - 2, H2 = 3 * (L - 2);
+  constexpr int NA = T + H2, N1 = T / 2 + H1;
+  double* A = sm;
+  double* B0 = sm + (NA + kPad) * kStrip;          // level-1 low child
+  double* B1 = B0 + (N1 + kPad) * kStrip;          // level-1 high child
+  unsigned id = blockIdx.x;
+  const unsigned strip = id & ((1u << a.lg_strips) - 1);
+  id >>= a.lg_strips;
+  const int64_t r0 = (int64_t)(id & ((1u << a.lg_tiles) - 1)) * T;
+  id >>= a.lg_tiles;
+  const int64_t p = id & ((1u << a.lg_blocks) - 1), b = id >> a.lg_blocks;
+  const int64_t c0 = (int64_t)strip * kStrip;
+  const int ncol = (int)((a.cols - c0 < kStrip) ? a.cols - c0 : kStrip);
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kStrip + tx;
+  {
+    const double* src = a.src + b * a.mat + p * a.h * a.ld + c0;
+    for (int idx = tid; idx < NA * (kStrip / 2); idx += kStrip * kGroups) {
+      const int row = idx / (kStrip / 2), seg = idx % (kStrip / 2);
+      if (2 * seg < ncol) ptx::cp_async16(&A[row * kStrip + 2 * seg], src + ((r0 + row) & (a.h - 1)) * a.ld + 2 * seg);
+    }
+    ptx::cp_async_commit_wait_all();
+  }
+  __syncthreads();
+  // level 1: both children keep N1 rows
+  for (int i0 = ty * kRun; i0 < N1; i0 += kGroups * kRun) {
+    constexpr int W = L + 2 * kRun - 2;
+    double win[W];
+#pragma unroll
+    for (int t = 0; t < W; t++) win[t] = A[(2 * i0 + t) * kStrip + tx];
+    double sl[kRun], sh[kRun];
+#pragma unroll
+    for (int q = 0; q < kRun; q++) sl[q] = sh[q] = 0.0;
+#pragma unroll
+    for (int m = 0; m < L; m++)
+#pragma unroll
+      for (int q = 0; q < kRun; q++) {
+        sl[q] = fma(win[2 * q + m], f.f0[m], sl[q]);
+        sh[q] = fma(win[2 * q + m], f.f1[m], sh[q]);
+      }
+#pragma unroll
+    for (int q = 0; q < kRun; q++)
+      if (i0 + q < N1) {
+        B0[(i0 + q) * kStrip + tx] = sl[q];
+        B1[(i0 + q) * kStrip + tx] = sh[q];
+      }
+  }
+  __syncthreads();
+  // level 2: T/4 rows of each grandchild, straight to its quarter of the block
+  const int64_t quarter = a.h >> 2;
+  double* out = a.dst + b * a.mat + (p * a.h + (r0 >> 2)) * a.ld + c0 + tx;
+  constexpr int NQ = T / 4;                        // multiple of kRun
+  for (int w = ty; w < 2 * (NQ / kRun); w += kGroups) {
+    const int parent = w / (NQ / kRun), i0 = (w - parent * (NQ / kRun)) * kRun;
+    const double* in = parent ? B1 : B0;
+    constexpr int W = L + 2 * kRun - 2;
+    double win[W];
+#pragma unroll
+    for (int t = 0; t < W; t++) win[t] = in[(2 * i0 + t) * kStrip + tx];
+    double sl[kRun], sh[kRun];
+#pragma unroll
+    for (int q = 0; q < kRun; q++) sl[q] = sh[q] = 0.0;
+#pragma unroll
+    for (int m = 0; m < L; m++)
+#pragma unroll
+      for (int q = 0; q < kRun; q++) {
+        sl[q] = fma(win[2 * q + m], f.f0[m], sl[q]);
+        sh[q] = fma(win[2 * q + m], f.f1[m], sh[q]);
+      }
+    if (tx < ncol) {
+      double* lo = out + (int64_t)(2 * parent) * quarter * a.ld;
+      double* hi = out + (int64_t)(2 * parent + 1) * quarter * a.ld;
+#pragma unroll
+      for (int q = 0; q < kRun; q++) {
+        lo[(int64_t)(i0 + q) * a.ld] = sl[q];
+        hi[(int64_t)(i0 + q) * a.ld] = sh[q];
+      }
+    }
+  }
+}
+
+template <int L>
+int launch_tree2(jwc_ctx* ctx, cudaStream_t st, ColTreeArgs a, const FilterPair& f, int64_t batch) {
+  constexpr int T = 128;
+  a.strips = (a.cols + kStrip - 1) / kStrip;
+  a.tiles = a.h / T;
+  a.lg_strips = ilog2_exact(a.strips);
+  a.lg_tiles = ilog2_exact(a.tiles);
+  a.lg_blocks = ilog2_exact(a.blocks);
+  if (a.lg_strips < 0 || a.lg_tiles < 0 || a.lg_blocks < 0) return JWC_ERR_UNSUPPORTED;
+  const int64_t ctas = a.strips * a.tiles * a.blocks * batch;
+  if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)((T + 3 * (L - 2) + kPad) + 2 * (T / 2 + (L - 2) + kPad)) * kStrip * sizeof(double);
+  JWC_CUDA_CHECK(allow_max_dynamic_smem(col_ana_tree2_kernel<L, T>));
+  col_ana_tree2_kernel<L, T><<<(unsigned)ctas, dim3(kStrip, kGroups), smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+int run_tree2(jwc_ctx* ctx, cudaStream_t st, const ColTreeArgs& a, const FilterPair& f, int64_t batch, int L) {
+  switch (L) {
+#define X(LL) case LL: return launch_tree2<LL>(ctx, st, a, f, batch);
+    JWC_FUSE_L(X)
+#undef X
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
 template <int L>
 void launch_ana(const ColArgs& a, const FilterPair& f, dim3 grid, dim3 block, cudaStream_t st, bool exact) {
   if (exact) col_ana_kernel<L, true><<<grid, block, 0, st>>>(a, f);
@@ -541,24 +669,41 @@ int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
   const int64_t mat = rows * cols;
   Scratch ws(ctx, dev, st);
   if (tree) {
-    // every block of h rows -> [lo | hi] of itself; whole-array ping-pong, last step lands in d_out
+    // every block of h rows -> [lo | hi] of itself; whole-array ping-pong, last launch lands in d_out.  Two levels per
+    // launch (col_ana_tree2_kernel) where a 128-row tile fits the block, single levels otherwise.
+    std::vector<int> sched;
+    for (int l = 0; l < steps;) {
+      const bool aligned = l > 0 || (reinterpret_cast<uintptr_t>(d_src) & 15) == 0;
+      const int k = (!exact && aligned && ctx->tune.wpt2d_fuse >= 0 && steps - l >= 2 && (rows >> l) >= 128 && !(cols & 1) &&
+                     L >= 2 && L <= 20 && !(L & 1)) ? 2 : 1;
+      sched.push_back(k);
+      l += k;
+    }
     double* tmp = nullptr;
-    if (steps >= 2) {
+    if (sched.size() >= 2) {
       tmp = ws.get((size_t)batch * mat);
       if (!tmp) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
     }
     const double* src = d_src;
     int64_t h = rows;
-    for (int l = 0; l < steps; l++, h >>= 1) {
-      double* dst = (((steps - 1 - l) & 1) == 0) ? d_out : tmp;
-      ColArgs a{};
-      a.src_lo = src; a.src_lo_mat = mat; a.src_lo_blk = h * cols;
-      a.dst_lo = dst; a.dst_lo_mat = mat; a.dst_lo_blk = h * cols;
-      a.dst_hi = dst + (h >> 1) * cols; a.dst_hi_mat = mat; a.dst_hi_blk = h * cols;
-      a.ld = cols; a.cols = cols; a.h = h; a.blocks = rows / h; a.L = L;
-      const int rc = col_step(ctx, st, a, f, batch, false, exact);
+    for (size_t i = 0; i < sched.size(); i++) {
+      double* dst = (((sched.size() - 1 - i) & 1) == 0) ? d_out : tmp;
+      int rc;
+      if (sched[i] == 2) {
+        ColTreeArgs a{};
+        a.src = src; a.dst = dst; a.mat = mat; a.ld = cols; a.cols = cols; a.h = h; a.blocks = rows / h;
+        rc = run_tree2(ctx, st, a, f, batch, L);
+      } else {
+        ColArgs a{};
+        a.src_lo = src; a.src_lo_mat = mat; a.src_lo_blk = h * cols;
+        a.dst_lo = dst; a.dst_lo_mat = mat; a.dst_lo_blk = h * cols;
+        a.dst_hi = dst + (h >> 1) * cols; a.dst_hi_mat = mat; a.dst_hi_blk = h * cols;
+        a.ld = cols; a.cols = cols; a.h = h; a.blocks = rows / h; a.L = L;
+        rc = col_step(ctx, st, a, f, batch, false, exact);
+      }
       if (rc != JWC_OK) return rc;
       src = dst;
+      h >>= sched[i];
     }
     return JWC_OK;
   }
