@@ -649,6 +649,128 @@ int col_step(jwc_ctx* ctx, cudaStream_t st, ColArgs a, const FilterPair& f, int6
   return JWC_OK;
 }
 
+// Inverse of the above: two synthesis levels per launch.  The four grandchildren are read from HBM where they lie
+// (inside the sliding-window loads), the two rebuilt level-1 children live in shared memory with their left halo.
+template <int L, int T>
+__global__ void __launch_bounds__(kStrip* kGroups) col_syn_tree2_kernel(const __grid_constant__ ColTreeArgs a,
+                                                                        const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  constexpr int M = L / 2;
+  constexpr int G1 = inv_halo(L, 1, 2), G2 = inv_halo(L, 2, 2);
+  constexpr int N1 = T / 2 + G1;                       // rows of each level-1 child (even)
+  constexpr int W = kRun + M - 1;
+  double* X0 = sm;
+  double* X1 = sm + (N1 + kPad) * kStrip;
+  unsigned id = blockIdx.x;
+  const unsigned strip = id & ((1u << a.lg_strips) - 1);
+  id >>= a.lg_strips;
+  const int64_t r0 = (int64_t)(id & ((1u << a.lg_tiles) - 1)) * T;
+  id >>= a.lg_tiles;
+  const int64_t p = id & ((1u << a.lg_blocks) - 1), b = id >> a.lg_blocks;
+  const int64_t c0 = (int64_t)strip * kStrip;
+  const int ncol = (int)((a.cols - c0 < kStrip) ? a.cols - c0 : kStrip);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t cx = c0 + (tx < ncol ? tx : 0);
+  const int64_t quarter = a.h >> 2;
+  const double* blk = a.src + b * a.mat + p * a.h * a.ld + cx;
+  // step 2: child c (0 = low, 1 = high) from the grandchildren in quarters 2c and 2c+1
+  {
+    constexpr int off = G2 - G1 / 2 - (M - 1);
+    constexpr int runs = (N1 / 2 + kRun - 1) / kRun;
+    for (int w = ty; w < 2 * runs; w += kGroups) {
+      const int c = w / runs, u0 = (w - c * runs) * kRun;
+      const double* g_lo = blk + (int64_t)(2 * c) * quarter * a.ld;
+      const double* g_hi = blk + (int64_t)(2 * c + 1) * quarter * a.ld;
+      double* xo = c ? X1 : X0;
+      double wl[W], wh[W];
+      int64_t gr = ((r0 >> 2) - G2 + off + u0) & (quarter - 1);
+#pragma unroll
+      for (int t = 0; t < W; t++) {
+        wl[t] = g_lo[gr * a.ld];
+        wh[t] = g_hi[gr * a.ld];
+        if (++gr == quarter) gr = 0;
+      }
+      double e[kRun], o[kRun];
+#pragma unroll
+      for (int u = 0; u < kRun; u++) e[u] = o[u] = 0.0;
+#pragma unroll
+      for (int m = M - 1; m >= 0; m--)
+#pragma unroll
+        for (int u = 0; u < kRun; u++) {
+          const double cl = wl[u - m + M - 1], ch = wh[u - m + M - 1];
+          e[u] = fma(ch, f.f1[2 * m], fma(cl, f.f0[2 * m], e[u]));
+          o[u] = fma(ch, f.f1[2 * m + 1], fma(cl, f.f0[2 * m + 1], o[u]));
+        }
+#pragma unroll
+      for (int u = 0; u < kRun; u++)
+        if (u0 + u < N1 / 2) {
+          xo[(2 * (u0 + u)) * kStrip + tx] = e[u];
+          xo[(2 * (u0 + u) + 1) * kStrip + tx] = o[u];
+        }
+    }
+  }
+  __syncthreads();
+  // step 1: the T output rows from the two children
+  {
+    constexpr int off = G1 - (M - 1);
+    double* out = a.dst + b * a.mat + (p * a.h + r0) * a.ld + c0 + tx;
+    for (int u0 = ty * kRun; u0 < T / 2; u0 += kGroups * kRun) {
+      double wl[W], wh[W];
+#pragma unroll
+      for (int t = 0; t < W; t++) {
+        wl[t] = X0[(off + u0 + t) * kStrip + tx];
+        wh[t] = X1[(off + u0 + t) * kStrip + tx];
+      }
+      double e[kRun], o[kRun];
+#pragma unroll
+      for (int u = 0; u < kRun; u++) e[u] = o[u] = 0.0;
+#pragma unroll
+      for (int m = M - 1; m >= 0; m--)
+#pragma unroll
+        for (int u = 0; u < kRun; u++) {
+          const double cl = wl[u - m + M - 1], ch = wh[u - m + M - 1];
+          e[u] = fma(ch, f.f1[2 * m], fma(cl, f.f0[2 * m], e[u]));
+          o[u] = fma(ch, f.f1[2 * m + 1], fma(cl, f.f0[2 * m + 1], o[u]));
+        }
+      if (tx < ncol) {
+#pragma unroll
+        for (int u = 0; u < kRun; u++) {
+          out[(int64_t)(2 * (u0 + u)) * a.ld] = e[u];
+          out[(int64_t)(2 * (u0 + u) + 1) * a.ld] = o[u];
+        }
+      }
+    }
+  }
+}
+
+template <int L>
+int launch_tree2_inv(jwc_ctx* ctx, cudaStream_t st, ColTreeArgs a, const FilterPair& f, int64_t batch) {
+  constexpr int T = 128;
+  a.strips = (a.cols + kStrip - 1) / kStrip;
+  a.tiles = a.h / T;
+  a.lg_strips = ilog2_exact(a.strips);
+  a.lg_tiles = ilog2_exact(a.tiles);
+  a.lg_blocks = ilog2_exact(a.blocks);
+  if (a.lg_strips < 0 || a.lg_tiles < 0 || a.lg_blocks < 0) return JWC_ERR_UNSUPPORTED;
+  const int64_t ctas = a.strips * a.tiles * a.blocks * batch;
+  if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(2 * (T / 2 + inv_halo(L, 1, 2) + kPad)) * kStrip * sizeof(double);
+  JWC_CUDA_CHECK(allow_max_dynamic_smem(col_syn_tree2_kernel<L, T>));
+  col_syn_tree2_kernel<L, T><<<(unsigned)ctas, dim3(kStrip, kGroups), smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+int run_tree2_inv(jwc_ctx* ctx, cudaStream_t st, const ColTreeArgs& a, const FilterPair& f, int64_t batch, int L) {
+  switch (L) {
+#define X(LL) case LL: return launch_tree2_inv<LL>(ctx, st, a, f, batch);
+    JWC_FUSE_L(X)
+#undef X
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
 int count_steps(int64_t rows, int levels) {
   int steps = 0;   // the reference's loop: while h >= 2 && l < level
   for (int64_t h = rows; h >= 2 && steps < levels; h >>= 1) steps++;
@@ -767,23 +889,46 @@ int dwt2d_columns_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
   const int64_t mat = rows * cols;
   Scratch ws(ctx, dev, st);
   if (tree) {
+    // deepest level first; two levels per launch (col_syn_tree2_kernel) where the rebuilt block holds a 128-row tile and
+    // its quarters hold the left halo
+    std::vector<int> sched;
+    {
+      int64_t h = rows >> (steps - 1);   // block height produced by the first (deepest) step
+      for (int done = 0; done < steps;) {
+        const bool aligned = true;       // no 16-byte loads in the inverse kernel
+        const int64_t h2 = h << 1;       // block height after two steps
+        const int k = (!exact && aligned && ctx->tune.wpt2d_fuse >= 0 && steps - done >= 2 && h2 >= 128 &&
+                       (h2 >> 2) >= inv_halo(L, 2, 2) && (h2 >> 2) >= L / 2 && L >= 2 && L <= 20 && !(L & 1)) ? 2 : 1;
+        sched.push_back(k);
+        done += k;
+        h <<= k;
+      }
+    }
     double* tmp = nullptr;
-    if (steps >= 2) {
+    if (sched.size() >= 2) {
       tmp = ws.get((size_t)batch * mat);
       if (!tmp) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
     }
     const double* src = d_in;
     int64_t h = rows >> (steps - 1);
-    for (int l = 0; l < steps; l++, h <<= 1) {
-      double* dst = (((steps - 1 - l) & 1) == 0) ? d_dst : tmp;
-      ColArgs a{};
-      a.src_lo = src; a.src_lo_mat = mat; a.src_lo_blk = h * cols;
-      a.src_hi = src + (h >> 1) * cols; a.src_hi_mat = mat; a.src_hi_blk = h * cols;
-      a.dst_lo = dst; a.dst_lo_mat = mat; a.dst_lo_blk = h * cols;
-      a.ld = cols; a.cols = cols; a.h = h; a.blocks = rows / h; a.L = L;
-      const int rc = col_step(ctx, st, a, f, batch, true, exact);
+    for (size_t i = 0; i < sched.size(); i++) {
+      double* dst = (((sched.size() - 1 - i) & 1) == 0) ? d_dst : tmp;
+      int rc;
+      if (sched[i] == 2) {
+        ColTreeArgs a{};
+        a.src = src; a.dst = dst; a.mat = mat; a.ld = cols; a.cols = cols; a.h = h << 1; a.blocks = rows / (h << 1);
+        rc = run_tree2_inv(ctx, st, a, f, batch, L);
+      } else {
+        ColArgs a{};
+        a.src_lo = src; a.src_lo_mat = mat; a.src_lo_blk = h * cols;
+        a.src_hi = src + (h >> 1) * cols; a.src_hi_mat = mat; a.src_hi_blk = h * cols;
+        a.dst_lo = dst; a.dst_lo_mat = mat; a.dst_lo_blk = h * cols;
+        a.ld = cols; a.cols = cols; a.h = h; a.blocks = rows / h; a.L = L;
+        rc = col_step(ctx, st, a, f, batch, true, exact);
+      }
       if (rc != JWC_OK) return rc;
       src = dst;
+      h <<= sched[i];
     }
     return JWC_OK;
   }
