@@ -224,6 +224,14 @@ JWC_API int jwc_wpt_aed_forward_dev(jwc_ctx* ctx, int slot, void* stream, const 
 JWC_API int jwc_wpt_aed_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
                                     int64_t batch, int64_t n, const double* lo, const double* hi, int L, unsigned flags);
 
+/* ---- diagnostics: roofline denominators measured with the library's own kernels on device `slot` ---------------
+ * jwc_diag_dfma_tflops: sustained fp64 FMA rate (TFLOP/s, 16 independent chains per thread, uniform operands -- the
+ * operand form of the filter inner loops); jwc_diag_copy_gbs: plain device-to-device copy of `bytes` bytes (read +
+ * write GB/s).  bench.py reports the fp64-bound configurations (Daubechies20 MODWT, Symlet8 WPT) against the first
+ * (SURVEY.md section 8d).  Both synchronise the slot's stream. */
+JWC_API int jwc_diag_dfma_tflops(jwc_ctx* ctx, int slot, double* tflops);
+JWC_API int jwc_diag_copy_gbs(jwc_ctx* ctx, int slot, size_t bytes, double* gbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,7 @@ SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal"
            + ["jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"]
            + ["jwc_modwt_forward_windows", "jwc_modwt_forward_windows_dev", "jwc_compress_magnitude",
               "jwc_compress_magnitude_dev"]
+           + ["jwc_diag_dfma_tflops", "jwc_diag_copy_gbs"]
            + ["jwc_" + t for t in _TRANSFORMS_2D] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_2D]
            + ["jwc_" + t for t in _TRANSFORMS_AED] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_AED])
 
@@ -118,6 +119,10 @@ def load():
             fn = getattr(lib, "jwc_" + t + "_dev")
             fn.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _dp, _dp, _int, _u32]
             fn.restype = _int
+        lib.jwc_diag_dfma_tflops.argtypes = [_vp, _int, _dp]
+        lib.jwc_diag_dfma_tflops.restype = _int
+        lib.jwc_diag_copy_gbs.argtypes = [_vp, _int, ctypes.c_size_t, _dp]
+        lib.jwc_diag_copy_gbs.restype = _int
         for nm in ("jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"):
             fn = getattr(lib, nm)
             fn.argtypes = [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _int, _dp, _dp, _int, _u32]
@@ -159,6 +164,22 @@ class Context:
         rc = self._lib.jwc_set_tuning(self._h, key.encode(), int(value))
         if rc != 0:
             raise ValueError(last_error())
+
+    def dfma_tflops(self, slot=0):
+        """fp64 FMA rate of device `slot` measured now (TFLOP/s): the second roofline of the fp64-bound configs."""
+        v = ctypes.c_double(0.0)
+        rc = self._lib.jwc_diag_dfma_tflops(self._h, slot, ctypes.byref(v))
+        if rc != 0:
+            raise RuntimeError(last_error())
+        return v.value
+
+    def copy_gbs(self, nbytes=1 << 30, slot=0):
+        """plain device copy rate of device `slot` measured now (read + write GB/s)."""
+        v = ctypes.c_double(0.0)
+        rc = self._lib.jwc_diag_copy_gbs(self._h, slot, nbytes, ctypes.byref(v))
+        if rc != 0:
+            raise RuntimeError(last_error())
+        return v.value
 
     def synchronize(self):
         rc = self._lib.jwc_synchronize(self._h)

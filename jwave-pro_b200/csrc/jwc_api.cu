@@ -43,6 +43,12 @@ struct Dim2 {
   int64_t hop = 0;    // > 0: forward MODWT of overlapping windows of ONE series; window b starts at b * hop
 };
 
+}  // namespace
+cudaError_t pool_alloc(const DeviceSlot& dev, void** p, size_t bytes, cudaStream_t st) {
+  return dev.pool ? cudaMallocFromPoolAsync(p, bytes ? bytes : 1, dev.pool, st) : cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+namespace {
+
 bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 int ilog2(int64_t n) {
   int p = 0;
@@ -410,8 +416,8 @@ int modwt_split(jwc_ctx* ctx, bool inverse, const double* const* d_in, double* c
     const int64_t len = n * (p + 1) / P - n * p / P, next = len + H;
     const int in_rows = inverse ? rows : 1, out_rows = inverse ? 1 : rows;
     cudaError_t e;
-    if ((e = cudaMallocAsync((void**)&ext_in[p], (size_t)(in_rows * next) * sizeof(double), dev.stream)) != cudaSuccess ||
-        (e = cudaMallocAsync((void**)&ext_out[p], (size_t)(out_rows * next) * sizeof(double), dev.stream)) != cudaSuccess) {
+    if ((e = pool_alloc(dev, (void**)&ext_in[p], (size_t)(in_rows * next) * sizeof(double), dev.stream)) != cudaSuccess ||
+        (e = pool_alloc(dev, (void**)&ext_out[p], (size_t)(out_rows * next) * sizeof(double), dev.stream)) != cudaSuccess) {
       (void)cudaGetLastError();
       set_error("split staging allocation failed on slot %d: %s", p, cudaGetErrorString(e));
       rc = JWC_ERR_NOMEM;
@@ -429,8 +435,12 @@ int modwt_split(jwc_ctx* ctx, bool inverse, const double* const* d_in, double* c
       // every coefficient row: [own chunk | halo from the right neighbour's head]
       const int q = (p + 1) % P;
       const int64_t qlen = n * (q + 1) / P - n * q / P;
-      e = cudaMemcpy2DAsync(ext_in[p], (size_t)next * sizeof(double), d_in[p], (size_t)len * sizeof(double),
-                            (size_t)len * sizeof(double), (size_t)rows, cudaMemcpyDeviceToDevice, dev.stream);
+      // one plain copy per row (at most 31): cudaMemcpy2D rejects pitches beyond cudaDeviceProp::memPitch (2 GiB),
+      // which is exactly the long-series case this entry point exists for
+      e = cudaSuccess;
+      for (int r = 0; r < rows && e == cudaSuccess; r++)
+        e = cudaMemcpyAsync(ext_in[p] + (int64_t)r * next, d_in[p] + (int64_t)r * len, (size_t)len * sizeof(double),
+                            cudaMemcpyDeviceToDevice, dev.stream);
       for (int r = 0; r < rows && e == cudaSuccess; r++)
         e = cudaMemcpyPeerAsync(ext_in[p] + (int64_t)r * next + len, dev.ordinal, d_in[q] + (int64_t)r * qlen,
                                 ctx->slots[q].ordinal, (size_t)H * sizeof(double), dev.stream);
@@ -446,10 +456,12 @@ int modwt_split(jwc_ctx* ctx, bool inverse, const double* const* d_in, double* c
                     L, flags);
     if (rc != JWC_OK) break;
     cudaError_t e;
-    if (!inverse)   // rows of the extended result, positions H .. H+len
-      e = cudaMemcpy2DAsync(d_out[p], (size_t)len * sizeof(double), ext_out[p] + H, (size_t)next * sizeof(double),
-                            (size_t)len * sizeof(double), (size_t)rows, cudaMemcpyDeviceToDevice, dev.stream);
-    else            // positions 0 .. len
+    if (!inverse) {   // rows of the extended result, positions H .. H+len (row by row: no 2-D pitch limit)
+      e = cudaSuccess;
+      for (int r = 0; r < rows && e == cudaSuccess; r++)
+        e = cudaMemcpyAsync(d_out[p] + (int64_t)r * len, ext_out[p] + (int64_t)r * next + H, (size_t)len * sizeof(double),
+                            cudaMemcpyDeviceToDevice, dev.stream);
+    } else            // positions 0 .. len
       e = cudaMemcpyAsync(d_out[p], ext_out[p], (size_t)len * sizeof(double), cudaMemcpyDeviceToDevice, dev.stream);
     if (e != cudaSuccess) { set_error("split result copy failed on slot %d: %s", p, cudaGetErrorString(e)); rc = JWC_ERR_CUDA; }
   }
@@ -522,11 +534,19 @@ JWC_API jwc_ctx* jwc_create(const int* devices, int ndev) {
       jwc_destroy(ctx);
       return nullptr;
     }
-    // keep freed scratch in the pool instead of returning it to the driver after every call
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, o) == cudaSuccess) {
+    // library scratch comes from a PRIVATE stream-ordered pool (the device's default pool, which other users of
+    // cudaMallocAsync in the process share, is left alone); freed blocks stay in it until jwc_release_scratch
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = o;
+    if (cudaMemPoolCreate(&s.pool, &props) == cudaSuccess) {
       uint64_t thr = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      cudaMemPoolSetAttribute(s.pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else {
+      (void)cudaGetLastError();
+      s.pool = nullptr;   // Scratch falls back to the default pool
     }
     ctx->slots.push_back(s);
   }
@@ -554,6 +574,8 @@ JWC_API int jwc_release_scratch(jwc_ctx* ctx) {
       it = kv.second.erase(it);
     }
   }
+  for (auto& s : ctx->slots)
+    if (s.pool) cudaMemPoolTrimTo(s.pool, 0);
   cudaSetDevice(prev);
   if (rc != JWC_OK) set_error("jwc_release_scratch: calls in flight kept their workspace");
   return rc;
@@ -568,6 +590,7 @@ JWC_API void jwc_destroy(jwc_ctx* ctx) {
     cudaSetDevice(s.ordinal);
     if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
     for (auto& l : s.idle_lanes) jwc::lane_destroy(l);
+    if (s.pool) cudaMemPoolDestroy(s.pool);
   }
   cudaSetDevice(prev);
   delete ctx;
@@ -735,8 +758,8 @@ JWC_API int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, 
   double *d_x = nullptr, *d_mag = nullptr;
   int rc = JWC_OK;
   cudaError_t e;
-  if ((e = cudaMallocAsync((void**)&d_x, (size_t)count * sizeof(double), st)) != cudaSuccess ||
-      (e = cudaMallocAsync((void**)&d_mag, sizeof(double), st)) != cudaSuccess) {
+  if ((e = jwc::pool_alloc(dev, (void**)&d_x, (size_t)count * sizeof(double), st)) != cudaSuccess ||
+      (e = jwc::pool_alloc(dev, (void**)&d_mag, sizeof(double), st)) != cudaSuccess) {
     (void)cudaGetLastError();
     set_error("device staging allocation failed: %s", cudaGetErrorString(e));
     rc = JWC_ERR_NOMEM;

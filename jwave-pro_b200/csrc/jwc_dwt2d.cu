@@ -795,7 +795,9 @@ int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
     // launch (col_ana_tree2_kernel) where a 128-row tile fits the block, single levels otherwise.
     std::vector<int> sched;
     for (int l = 0; l < steps;) {
-      const bool aligned = l > 0 || (reinterpret_cast<uintptr_t>(d_src) & 15) == 0;
+      // the fused launch stages its rows with 16-byte cp.async; the ping-pong makes every launch after the first read
+      // either scratch (aligned) or the caller's d_out, so both caller pointers must be 16-byte aligned
+      const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
       const int k = (!exact && aligned && ctx->tune.wpt2d_fuse >= 0 && steps - l >= 2 && (rows >> l) >= 128 && !(cols & 1) &&
                      L >= 2 && L <= 20 && !(L & 1)) ? 2 : 1;
       sched.push_back(k);

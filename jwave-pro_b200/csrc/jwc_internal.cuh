@@ -73,6 +73,7 @@ struct DeviceSlot {
   cudaStream_t stream = nullptr;      // compute stream of the slot (device-pointer calls that pass NULL)
   int sm_count = 0;
   int max_smem_optin = 0;
+  cudaMemPool_t pool = nullptr;       // private stream-ordered pool of the context on this device (library scratch)
   std::vector<Lane> idle_lanes;       // guarded by jwc_ctx::mu
 };
 
@@ -99,6 +100,28 @@ struct jwc_ctx {
 
 namespace jwc {
 
+// Bound on the number of (device, stream) arenas a context keeps: beyond it, arenas without a block in use are given
+// back to the driver (device-synchronising, so rare by construction).  Caller holds ctx->mu.
+constexpr size_t kMaxArenas = 48;
+inline void evict_idle_arenas(jwc_ctx* ctx) {
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int synced = -1;
+  for (auto it = ctx->arenas.begin(); it != ctx->arenas.end();) {
+    bool busy = false;
+    for (auto& b : it->second) busy = busy || b.in_use;
+    if (busy) { ++it; continue; }
+    if (synced != it->first.first) {   // map is ordered by device: one synchronisation per device
+      cudaSetDevice(it->first.first);
+      cudaDeviceSynchronize();
+      synced = it->first.first;
+    }
+    for (auto& b : it->second) cudaFree(b.p);
+    it = ctx->arenas.erase(it);
+  }
+  cudaSetDevice(prev);
+}
+
 // Workspace of one call.  Blocks come from the context's arena of the call's (device, stream) and go back to it when
 // the call has finished ENQUEUEING: everything that uses a block is ordered on that one stream, so the next call on
 // the stream may reuse it at once, and a call that is enqueueing concurrently from another host thread never gets a
@@ -110,8 +133,9 @@ struct Scratch {
   jwc_ctx* ctx;
   int ordinal;
   cudaStream_t stream;
+  cudaMemPool_t pool;
   std::vector<ScratchBlock*> held;
-  Scratch(jwc_ctx* c, const DeviceSlot& dev, cudaStream_t s) : ctx(c), ordinal(dev.ordinal), stream(s) {}
+  Scratch(jwc_ctx* c, const DeviceSlot& dev, cudaStream_t s) : ctx(c), ordinal(dev.ordinal), stream(s), pool(dev.pool) {}
   Scratch(const Scratch&) = delete;
   Scratch& operator=(const Scratch&) = delete;
   double* get(size_t n_doubles) {
@@ -129,11 +153,14 @@ struct Scratch {
       }
     }
     void* p = nullptr;
-    if (cudaMallocAsync(&p, bytes, stream) != cudaSuccess) {
+    const cudaError_t e = pool ? cudaMallocFromPoolAsync(&p, bytes, pool, stream) : cudaMallocAsync(&p, bytes, stream);
+    if (e != cudaSuccess) {
       (void)cudaGetLastError();
       return nullptr;
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
+    // callers that come with ever new (short-lived) streams would otherwise pile up cached blocks without bound
+    if (ctx->arenas.size() >= kMaxArenas && !ctx->arenas.count(std::make_pair(ordinal, stream))) evict_idle_arenas(ctx);
     auto& arena = ctx->arenas[std::make_pair(ordinal, stream)];
     arena.push_back(ScratchBlock{p, bytes, true});
     held.push_back(&arena.back());

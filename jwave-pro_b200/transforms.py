@@ -34,6 +34,21 @@ def _ptr(a):
     return a.ctypes.data_as(_dp)
 
 
+def _out_buffer(out, shape):
+    """Result buffer of a batched call: a fresh array, or the caller's `out` after checking that native code may write
+    `shape` float64 values into it (a float32, strided, read-only or undersized array would be silent heap corruption)."""
+    shape = tuple(int(v) for v in shape)
+    if out is None:
+        return np.empty(shape, dtype=np.float64)
+    if not isinstance(out, np.ndarray) or out.dtype != np.float64:
+        raise IllegalArgumentException("out must be a numpy float64 array")
+    if not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+        raise IllegalArgumentException("out must be C-contiguous and writeable")
+    if tuple(out.shape) != shape:
+        raise IllegalArgumentException("out has shape %s, expected %s" % (tuple(out.shape), shape))
+    return out
+
+
 class BasicTransform:
     """transforms/BasicTransform.java:42 -- only the 1-D surface the hot path touches."""
 
@@ -165,7 +180,7 @@ class _CudaPyramidBase(WaveletTransform):
         if level is None:
             level = self.calcExponent(N)
         self._check(N, level, "forward")
-        out = np.empty_like(X) if out is None else out
+        out = _out_buffer(out, X.shape)
         self._call(self._fn + "_forward", X, out, B, N, level, self._wavelet.getScalingDeComposition(),
                    self._wavelet.getWaveletDeComposition(), flags)
         return out
@@ -176,7 +191,7 @@ class _CudaPyramidBase(WaveletTransform):
         if level is None:
             level = self.calcExponent(N)
         self._check(N, level, "reverse")
-        out = np.empty_like(C) if out is None else out
+        out = _out_buffer(out, C.shape)
         self._call(self._fn + "_inverse", C, out, B, N, level, self._wavelet.getScalingReConstruction(),
                    self._wavelet.getWaveletReConstruction(), flags)
         return out
@@ -204,7 +219,7 @@ class _CudaPyramidBase(WaveletTransform):
         X = _as_f64(cubeTime)
         B, rows, cols = X.shape
         lvlM, lvlN = self._levels2d(rows, cols, lvlM, lvlN, "forward")
-        out = np.empty_like(X) if out is None else out
+        out = _out_buffer(out, X.shape)
         self._call2d(self._fn + "2d_forward", X, out, B, rows, cols, lvlM, lvlN,
                      self._wavelet.getScalingDeComposition(), self._wavelet.getWaveletDeComposition(), flags)
         return out
@@ -213,7 +228,7 @@ class _CudaPyramidBase(WaveletTransform):
         C = _as_f64(cubeHilb)
         B, rows, cols = C.shape
         lvlM, lvlN = self._levels2d(rows, cols, lvlM, lvlN, "reverse")
-        out = np.empty_like(C) if out is None else out
+        out = _out_buffer(out, C.shape)
         self._call2d(self._fn + "2d_inverse", C, out, B, rows, cols, lvlM, lvlN,
                      self._wavelet.getScalingReConstruction(), self._wavelet.getWaveletReConstruction(), flags)
         return out
@@ -311,7 +326,7 @@ class AncientEgyptianDecomposition(BasicTransform):
         t = self._basicTransform
         X = _as_f64(mat)
         B, N = X.shape
-        out = np.empty_like(X) if out is None else out
+        out = _out_buffer(out, X.shape)
         if N == 0 or B == 0:
             return out
         w = t._wavelet
@@ -462,6 +477,14 @@ class CudaMODWTTransform(WaveletTransform):
                                            % (maxLevel, theoretical, N))
         return True
 
+    def _check_inverse_levels(self, maxLevel):
+        # the reference's inverse reaches the same limit through getCachedGFilter -> upsample()
+        # (MODWTTransform.java:490-515, 618-620): level > MAX_DECOMPOSITION_LEVEL -> IllegalArgumentException
+        if maxLevel > self.MAX_DECOMPOSITION_LEVEL:
+            raise IllegalArgumentException("MODWTTransform#upsample - maximum supported decomposition level is %d, "
+                                           "requested: %d"
+                                           % (self.MAX_DECOMPOSITION_LEVEL, maxLevel))
+
     def forwardMODWT(self, data, maxLevel, flags=0):
         N = 0 if data is None else len(data)
         if not self._check_levels(maxLevel, N):
@@ -482,6 +505,7 @@ class CudaMODWTTransform(WaveletTransform):
         N = c.shape[1]
         if N == 0:
             return np.empty(0)
+        self._check_inverse_levels(maxLevel)
         g, h = self._filters()
         x = np.empty(N)
         self._call("jwc_modwt_inverse", c, x, 1, N, maxLevel, g, h, flags)
@@ -541,7 +565,7 @@ class CudaMODWTTransform(WaveletTransform):
             raise IllegalArgumentException("need a 1-D series with 1 <= window <= len(series) and hop >= 1")
         self._check_levels(maxLevel, window)
         nwin = (len(x) - window) // hop + 1
-        out = np.empty((nwin, maxLevel + 1, window)) if out is None else out
+        out = _out_buffer(out, (nwin, maxLevel + 1, window))
         g, h = self._filters()
         lib = _native.load()
         g, h = _as_f64(g), _as_f64(h)
@@ -568,15 +592,16 @@ class CudaMODWTTransform(WaveletTransform):
         B, N = X.shape
         self._check_levels(maxLevel, N)
         g, h = self._filters()
-        out = np.empty((B, maxLevel + 1, N)) if out is None else out
+        out = _out_buffer(out, (B, maxLevel + 1, N))
         self._call("jwc_modwt_forward", X, out, B, N, maxLevel, g, h, flags)
         return out
 
     def inverseMODWTBatch(self, coeffs, flags=0, out=None):
         C = _as_f64(coeffs)
         B, J1, N = C.shape
+        self._check_inverse_levels(J1 - 1)
         g, h = self._filters()
-        out = np.empty((B, N)) if out is None else out
+        out = _out_buffer(out, (B, N))
         self._call("jwc_modwt_inverse", C, out, B, N, J1 - 1, g, h, flags)
         return out
 
@@ -608,5 +633,6 @@ class CudaMODWTTransform(WaveletTransform):
         self._call_dev("jwc_modwt_forward", d_x, d_coeffs, batch, n, maxLevel, g, h, flags, stream, slot)
 
     def inverseMODWTDevice(self, d_coeffs, d_x, batch, n, maxLevel, stream=0, flags=0, slot=0):
+        self._check_inverse_levels(maxLevel)
         g, h = self._filters()
         self._call_dev("jwc_modwt_inverse", d_coeffs, d_x, batch, n, maxLevel, g, h, flags, stream, slot)
