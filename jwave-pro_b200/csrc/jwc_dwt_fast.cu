@@ -50,6 +50,8 @@ struct DwtPassArgs {
   int64_t h;           // node length at depth l0 (= N >> l0)
   int l0, k, T, tiles, nodes, cap, mode;
   int pf_dist;        // L2 prefetch distance in CTAs (0 = off)
+  int log_tiles;      // tiles and nodes are powers of two: the CTA index is taken apart with shifts (a 64-bit
+                      // division is a ~100-instruction subroutine, and a CTA only lives for a few thousand)
   unsigned nblocks;
   int hl[16];             // inverse: left halo of the depth-jj arrays (dwt_inv_halo), precomputed on the host
 };
@@ -58,8 +60,12 @@ struct DwtPassArgs {
 // length hn at `base` into dst.  One thread; the mbarrier must already expect the bytes.  start, hn, len are even.
 __device__ __forceinline__ void bulk_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
                                                uint64_t* bar) {
-  int64_t pos = start % hn;
-  if (pos < 0) pos += hn;
+  // no 64-bit modulo here: it would be a subroutine call inside the level loop of the inverse kernel, and everything
+  // live across that call (accumulator / tap registers of the other threads' code path) pays for it.  |start| is at
+  // most a halo (tens of samples), so the two loops run a handful of times for one thread.
+  int64_t pos = start;
+  while (pos < 0) pos += hn;
+  while (pos >= hn) pos -= hn;
   int done = 0;
   while (done < len) {
     int64_t run = hn - pos;
@@ -72,9 +78,12 @@ __device__ __forceinline__ void bulk_load_circ(double* dst, const double* base, 
 
 __device__ __forceinline__ void scalar_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
                                                  int tid, int nt) {
+  // node lengths are < 2^31 (checked by the callers): 32-bit remainder, no division subroutine
+  const int h32 = (int)hn;
+  int s32 = (int)(start % hn);
+  if (s32 < 0) s32 += h32;
   for (int e = tid; e < len; e += nt) {
-    int64_t pos = (start + e) % hn;
-    if (pos < 0) pos += hn;
+    const int pos = (int)(((unsigned)s32 + (unsigned)e) % (unsigned)h32);
     dst[e] = base[pos];
   }
 }
@@ -204,17 +213,16 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
   }
   const int oT = 2 * a.cap;                         // tap copy, then the mbarrier
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
-  if (L > kUniformTapsMaxDwt) {
+  if (L > 20) {   // shorter filters take their taps from the constant bank (uniform registers)
     for (int t = tid; t < JWC_MAX_TAPS; t += nt) {
       smem[oT + t] = f.f0[t];
       smem[oT + JWC_MAX_TAPS + t] = f.f1[t];
     }
   }
-  int64_t bid = blockIdx.x;
-  const int ti = (int)(bid % a.tiles);
-  bid /= a.tiles;
-  const int p = (int)(bid % a.nodes);
-  const int64_t b = bid / a.nodes;
+  const unsigned bid = blockIdx.x;
+  const int ti = (int)(bid & (unsigned)(a.tiles - 1));
+  const int p = (int)((bid >> a.log_tiles) & (unsigned)(a.nodes - 1));
+  const int64_t b = (int64_t)(bid >> (a.log_tiles + a.l0 * (a.nodes > 1 ? 1 : 0)));
   const int tlen = (int)((a.h < a.T) ? a.h : a.T);
   const int64_t a0 = (int64_t)ti * tlen;
   const double* node = a.in + b * a.in_sig + (int64_t)p * a.h;
@@ -229,11 +237,10 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
       ptx::mbar_expect_tx(bar, (uint32_t)(tlen + H) * 8u);
       bulk_load_circ(smem, node, a0, tlen + H, a.h, bar);
       if (a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {   // one wave ahead into L2
-        int64_t nb = (int64_t)blockIdx.x + a.pf_dist;
-        const int ti2 = (int)(nb % a.tiles);
-        nb /= a.tiles;
-        const int p2 = (int)(nb % a.nodes);
-        const int64_t b2 = nb / a.nodes;
+        const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
+        const int ti2 = (int)(nb & (unsigned)(a.tiles - 1));
+        const int p2 = (int)((nb >> a.log_tiles) & (unsigned)(a.nodes - 1));
+        const int64_t b2 = (int64_t)(nb >> (a.log_tiles + a.l0 * (a.nodes > 1 ? 1 : 0)));
         ptx::bulk_prefetch_l2(a.in + b2 * a.in_sig + (int64_t)p2 * a.h + (int64_t)ti2 * tlen, (uint32_t)tlen * 8u);
       }
       ptx::mbar_wait(bar, 0);
@@ -253,14 +260,26 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
     const int st_in = len_in + (len_in & 1) + 2 * kDwtR, st_out = len_out + (len_out & 1) + 2 * kDwtR;
     const int own = tlen >> jj;                       // outputs of each child that belong to this tile
     const int parents = TREE ? (1 << (jj - 1)) : 1;
-    // rows per item: RMAX unless that would leave more than 3/4 of the threads without an item (deep, small levels).
-    // Small R costs shared-memory bandwidth (the window overlap L/2-1 and the tap loads are paid per item).
-    if (4 * parents * ((len_out + RMAX - 1) / RMAX) >= nt || RMAX == 1)
-      ana_level<L, RMAX, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
-    else if (4 * parents * ((len_out + 2) / 3) >= nt)
-      ana_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
-    else
-      ana_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+    // rows per item: as many as the build offers unless that leaves more than 3/4 of the threads without an item
+    const int Rsel = dwt_pick_r(L, len_out, parents, nt);
+    switch (Rsel) {
+      case 7:
+        if constexpr (RMAX >= 7) {
+          ana_level<L, 7, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+          break;
+        }
+      case 5:
+        if constexpr (RMAX == 5) {
+          ana_level<L, 5, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+          break;
+        }
+      case 3:
+        ana_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+        break;
+      default:
+        ana_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, len_out, own, parents, tid, nt);
+    }
+
     // ---- ship what is final after this level ------------------------------------------------------------------------------
     const bool last = (jj == a.k);
     const bool vec_ok = bulk && (own & 1) == 0;
@@ -390,7 +409,7 @@ __device__ __forceinline__ void syn_level(double* smem, const FilterPair& f, con
 }
 
 template <int L, int RMAX, bool TREE, bool QMF>
-__global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L == 10) ? 2 : 3))) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
+__global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <= 20) ? 2 : 3))) dwt_inv_pass_kernel(const __grid_constant__ DwtPassArgs a,
                                                               const __grid_constant__ FilterPair f) {
   constexpr int NS = QMF ? L : 1;
   double sreg[NS];
@@ -407,17 +426,16 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L =
   if (tid < 16) s_hl[tid] = a.hl[tid];
   const int oT = 2 * a.cap;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oT + 2 * JWC_MAX_TAPS);
-  if (L > kUniformTapsMaxDwt) {
+  if (L > 20 || (L > kUniformTapsMaxDwt && !TREE && !QMF)) {   // the only instantiations that read the shared-memory copy
     for (int t = tid; t < JWC_MAX_TAPS; t += nt) {
       smem[oT + t] = f.f0[t];
       smem[oT + JWC_MAX_TAPS + t] = f.f1[t];
     }
   }
-  int64_t bid = blockIdx.x;
-  const int ti = (int)(bid % a.tiles);
-  bid /= a.tiles;
-  const int p = (int)(bid % a.nodes);
-  const int64_t b = bid / a.nodes;
+  const unsigned bid = blockIdx.x;
+  const int ti = (int)(bid & (unsigned)(a.tiles - 1));
+  const int p = (int)((bid >> a.log_tiles) & (unsigned)(a.nodes - 1));
+  const int64_t b = (int64_t)(bid >> (a.log_tiles + a.l0 * (a.nodes > 1 ? 1 : 0)));
   const int tlen = (int)((a.h < a.T) ? a.h : a.T);
   const int64_t a0 = (int64_t)ti * tlen;
   const bool bulk = (a.mode == DWT_BULK);
@@ -434,11 +452,10 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L =
   }
   __syncthreads();   // mbarriers, s_hl and the tap copy are visible
   if (bulk && a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {   // one wave ahead into L2
-    int64_t nb = (int64_t)blockIdx.x + a.pf_dist;
-    const int ti2 = (int)(nb % a.tiles);
-    nb /= a.tiles;
-    const int p2 = (int)(nb % a.nodes);
-    const int64_t b2 = nb / a.nodes;
+    const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
+    const int ti2 = (int)(nb & (unsigned)(a.tiles - 1));
+    const int p2 = (int)((nb >> a.log_tiles) & (unsigned)(a.nodes - 1));
+    const int64_t b2 = (int64_t)(nb >> (a.log_tiles + a.l0 * (a.nodes > 1 ? 1 : 0)));
     const int64_t a2 = (int64_t)ti2 * tlen;
     if (TREE) {
       const int own = tlen >> a.k;
@@ -510,12 +527,25 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L =
     const int np = (hl_out >> 1) + (tlen >> jj);          // output pairs per parent
     const int off = hl_in - (hl_out >> 1) - (L / 2 - 1);   // first child index read by pair 0
     const int parents = TREE ? (1 << (jj - 1)) : 1;
-    if (4 * parents * ((np + RMAX - 1) / RMAX) >= nt || RMAX == 1)
-      syn_level<L, RMAX, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
-    else if (4 * parents * ((np + 2) / 3) >= nt)
-      syn_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
-    else
-      syn_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+    const int Rsel = dwt_pick_r(L, np, parents, nt);
+    switch (Rsel) {
+      case 7:
+        if constexpr (RMAX >= 7) {
+          syn_level<L, 7, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+          break;
+        }
+      case 5:
+        if constexpr (RMAX == 5) {
+          syn_level<L, 5, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+          break;
+        }
+      case 3:
+        syn_level<L, 3, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+        break;
+      default:
+        syn_level<L, 1, TREE, QMF, NS>(smem, f, sreg, oT, oin, oout, st_in, st_out, np, off, parents, tid, nt);
+    }
+
     if (bulk && jj == 1) ptx::fence_proxy_async();
     __syncthreads();
   }
@@ -533,21 +563,27 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L == 8 || L =
   }
 }
 
-template <int L, bool TREE, bool INV, bool QMF>
-int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int threads, size_t smem,
-                    int64_t nblocks) {
+template <int L, int RMAX, bool TREE, bool INV, bool QMF>
+int launch_dwt_pass_r(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int threads, size_t smem,
+                      int64_t nblocks) {
   if (INV) {
-    auto kern = dwt_inv_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
+    auto kern = dwt_inv_pass_kernel<L, RMAX, TREE, QMF>;
     JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   } else {
-    auto kern = dwt_fwd_pass_kernel<L, (L > kUniformTapsMaxDwt ? 5 : kDwtR), TREE, QMF>;
+    auto kern = dwt_fwd_pass_kernel<L, RMAX, TREE, QMF>;
     JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
     kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
   }
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());
   return JWC_OK;
+}
+
+template <int L, bool TREE, bool INV, bool QMF>
+int launch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int threads, size_t smem,
+                    int64_t nblocks) {
+  return launch_dwt_pass_r<L, dwt_rmax(L), TREE, INV, QMF>(ctx, st, a, f, threads, smem, nblocks);
 }
 
 // exact quadrature-mirror relation of the reference's orthogonal wavelets (Wavelet.java:109-113)
@@ -562,20 +598,20 @@ bool is_qmf(const FilterPair& f, int L) {
 template <bool TREE, bool INV>
 int dispatch_dwt_pass(jwc_ctx* ctx, cudaStream_t st, const DwtPassArgs& a, const FilterPair& f, int L, int threads,
                       size_t smem, int64_t nblocks) {
-  // forward only: the synthesis kernels gain nothing from it (measured) and the pyramid instantiation spills
-  if constexpr (!INV) if (L >= 12 && L <= 20 && ctx->tune.dwt_qmf >= 0 && is_qmf(f, L)) {
+  // forward, and the pyramid inverse (its non-QMF instantiation reads the taps from shared memory with broadcast LDS
+  // and runs reg,reg,reg DFMAs; the QMF one keeps the L distinct tap values in uniform registers).  The packet-tree
+  // inverse already has uniform-register taps without it.
+  if constexpr (!INV || !TREE) if (L >= 12 && L <= 20 && ctx->tune.dwt_qmf >= 0 && is_qmf(f, L)) {
     switch (L) {
 #define JWC_QCASE(LL) case LL: return launch_dwt_pass<LL, TREE, INV, true>(ctx, st, a, f, threads, smem, nblocks);
-      JWC_QCASE(12) JWC_QCASE(14) JWC_QCASE(16) JWC_QCASE(18) JWC_QCASE(20)
+      JWC_QMF_L(JWC_QCASE)
 #undef JWC_QCASE
       default: break;
     }
   }
   switch (L) {
 #define JWC_CASE(LL) case LL: return launch_dwt_pass<LL, TREE, INV, false>(ctx, st, a, f, threads, smem, nblocks);
-    JWC_CASE(2) JWC_CASE(4) JWC_CASE(6) JWC_CASE(8) JWC_CASE(10) JWC_CASE(12) JWC_CASE(14) JWC_CASE(16) JWC_CASE(18)
-    JWC_CASE(20) JWC_CASE(22) JWC_CASE(24) JWC_CASE(26) JWC_CASE(28) JWC_CASE(30) JWC_CASE(32) JWC_CASE(34) JWC_CASE(36)
-    JWC_CASE(38) JWC_CASE(40)
+    JWC_ALL_L(JWC_CASE)
 #undef JWC_CASE
     default: return JWC_ERR_UNSUPPORTED;
   }
@@ -676,6 +712,8 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     const int64_t nblocks = (int64_t)a.tiles * a.nodes * batch;
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
     a.nblocks = (unsigned)nblocks;
+    a.log_tiles = 0;
+    while ((1 << a.log_tiles) < a.tiles) a.log_tiles++;   // tiles = h / T, both powers of two
     a.pf_dist = (p.mode == DWT_BULK) ? dwt_prefetch_distance(ctx, dev, p.smem, p.threads) : 0;
     int rc = tree ? dispatch_dwt_pass<true, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks)
                   : dispatch_dwt_pass<false, false>(ctx, st, a, f, L, p.threads, p.smem, nblocks);
@@ -764,6 +802,8 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     const int64_t nblocks = (int64_t)a.tiles * a.nodes * batch;
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
     a.nblocks = (unsigned)nblocks;
+    a.log_tiles = 0;
+    while ((1 << a.log_tiles) < a.tiles) a.log_tiles++;   // tiles = h / T, both powers of two
     a.pf_dist = (p.mode == DWT_BULK) ? dwt_prefetch_distance(ctx, dev, p.smem, p.threads) : 0;
     int rc = JWC_ERR_UNSUPPORTED;
     if (!tree)   // long signals: the tiled in-place kernel (jwc_dwt_whole.cu) takes passes of up to 3 levels

@@ -13,7 +13,30 @@
 
 namespace jwc {
 
-constexpr int kDwtR = 7;  // outputs (forward) / output pairs (inverse) per work item; odd => conflict-free LDS/STS
+#ifndef JWC_HD
+#ifdef __CUDACC__
+#define JWC_HD __host__ __device__
+#else
+#define JWC_HD
+#endif
+#endif
+
+// Rows per work item: outputs (forward) / output pairs (inverse) one thread computes with a sliding register window.
+// ODD counts only: the lanes of a warp then hit distinct banks (LDS.128 / STS.128 with a lane stride of R x 16 bytes).
+// kDwtR is the largest count and the padding of every node array in shared memory (an item at the end of a node reads
+// up to 2(R-1) doubles past it).  Filters longer than 10 taps use at most 5 rows (registers).
+constexpr int kDwtR = 7;
+JWC_HD inline constexpr int dwt_rmax(int L) { return L > 10 ? 5 : kDwtR; }
+
+// Rows per item of one level: as many as the build offers, unless that would leave more than 3/4 of the threads
+// without an item (deep, small levels) -- then 3, then 1.  (Round 2 measured the alternative "fewest rounds of items x
+// (R + overhead)", which picks 3 rows earlier: FWT Daubechies8 8 % slower, the fixed cost per item is what matters.)
+JWC_HD inline int dwt_pick_r(int L, int len, int parents, int nt) {
+  const int RM = dwt_rmax(L);
+  if (4 * parents * ((len + RM - 1) / RM) >= nt) return RM;
+  if (4 * parents * ((len + 2) / 3) >= nt) return 3;
+  return 1;
+}
 
 enum { DWT_BULK = 0, DWT_SCALAR = 2 };
 
@@ -61,15 +84,18 @@ inline int64_t dwt_inv_cap(bool tree, int L, int k, int64_t tlen) {
   return cap + (cap & 1);
 }
 
-inline int dwt_rmax(int L) { return L > 10 ? 5 : kDwtR; }   // rows per item of the kernels (register budget)
-
-inline int64_t dwt_items(const DwtPlanInput& in, int k, int jj, int64_t tlen) {
-  // forward level jj: children of length len_jj from every parent; inverse level jj: parents (depth jj-1) pairs
-  const int R = dwt_rmax(in.L);
+// outputs (forward) / output pairs (inverse) of level jj per parent node, as the kernels count them
+inline int64_t dwt_level_len(const DwtPlanInput& in, int k, int jj, int64_t tlen) {
+  if (!in.inverse) return dwt_fwd_len(in.L, k, jj, tlen);
+  return (dwt_inv_halo(in.L, jj - 1) >> 1) + (tlen >> jj);
+}
+// item-rounds x rows per item of level jj with `thr` threads: what the level costs in units of one output row
+inline double dwt_level_cost(const DwtPlanInput& in, int k, int jj, int64_t tlen, int thr) {
   const int64_t parents = in.tree ? ((int64_t)1 << (jj - 1)) : 1;
-  if (!in.inverse) return parents * ((dwt_fwd_len(in.L, k, jj, tlen) + R - 1) / R);
-  const int64_t pairs = (dwt_inv_len(in.L, jj - 1, tlen) + 1) / 2 + 1;
-  return parents * ((pairs + R - 1) / R);
+  const int64_t len = dwt_level_len(in, k, jj, tlen);
+  const int R = dwt_pick_r(in.L, (int)len, (int)parents, thr);
+  const int64_t items = parents * ((len + R - 1) / R);
+  return (double)((items + thr - 1) / thr) * (R + 2);
 }
 
 inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, double* est) {
@@ -95,11 +121,12 @@ inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, d
   const int thr = in.threads_override > 0 ? in.threads_override : 128;
   double eff;
   {
+    // useful output rows per thread vs. what the rounds of items actually cost (see dwt_pick_r)
     double useful = 0, issued = 0;
     for (int jj = 1; jj <= k; jj++) {
-      const int64_t it = dwt_items(in, k, jj, T);
-      useful += (double)it;
-      issued += (double)(((it + thr - 1) / thr) * thr);
+      const double parents = in.tree ? (double)((int64_t)1 << (jj - 1)) : 1.0;
+      useful += parents * (double)dwt_level_len(in, k, jj, T) / thr;
+      issued += dwt_level_cost(in, k, jj, T, thr);
     }
     eff = issued > 0 ? useful / issued : 1.0;
   }

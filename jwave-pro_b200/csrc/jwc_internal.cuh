@@ -33,6 +33,17 @@ void set_error(const char* fmt, ...);
     }                                \
   } while (0)
 
+// every even filter length the fused kernels are instantiated for.  -DJWC_ONLY_L=16 builds one length only (SASS /
+// register probes while tuning: tools/sass_probe.sh); the shipped library always has them all.
+#ifdef JWC_ONLY_L
+#define JWC_ALL_L(X) X(JWC_ONLY_L)
+#define JWC_QMF_L(X) X(JWC_ONLY_L)
+#else
+#define JWC_QMF_L(X) X(12) X(14) X(16) X(18) X(20)
+#define JWC_ALL_L(X)                                                                                                  \
+  X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
+#endif
+
 // ---- filters travel as kernel parameters (constant bank): statically indexed taps become
 //      immediate constant operands of DFMA, dynamically indexed ones an LDC.
 struct FilterPair {

@@ -100,13 +100,17 @@ __device__ __forceinline__ void fwd_item(const double* __restrict__ top, int s, 
 
 // row index modulo the decimated signal length: one conditional add/subtract covers every tile whose halo is shorter
 // than the signal; only the pathological multi-wrap shapes pay for the 64-bit modulo
+__device__ __noinline__ int64_t wrap_row_slow(int64_t i, int64_t nd) {
+  i %= nd;
+  return i < 0 ? i + nd : i;
+}
 __device__ __forceinline__ int64_t wrap_row(int64_t i, int64_t nd) {
   if (i < 0) {
     i += nd;
-    if (i < 0) { i %= nd; if (i < 0) i += nd; }
+    if (i < 0) i = wrap_row_slow(i, nd);   // pathological multi-wrap shapes only (halo longer than the signal)
   } else if (i >= nd) {
     i -= nd;
-    if (i >= nd) i %= nd;
+    if (i >= nd) i = wrap_row_slow(i, nd);
   }
   return i;
 }
@@ -132,11 +136,12 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
     }
   }
 
-  int64_t bid = blockIdx.x;
-  const int ti = (int)(bid % a.tiles_i);
-  bid /= a.tiles_i;
-  const int pg = (int)(bid % a.groups);
-  const int64_t b = bid / a.groups;
+  // CTA index taken apart with 32-bit divisions (nblocks < 2^31; a 64-bit division is a ~100-instruction subroutine)
+  unsigned bid = blockIdx.x;
+  const int ti = (int)(bid % (unsigned)a.tiles_i);
+  bid /= (unsigned)a.tiles_i;
+  const int pg = (int)(bid % (unsigned)a.groups);
+  const int64_t b = (int64_t)(bid / (unsigned)a.groups);
   const int64_t i0 = (int64_t)ti * a.T2;
   const int tlen2 = (int)((a.Nd - i0 < a.T2) ? (a.Nd - i0) : a.T2);
   const int ph0 = pg << a.logP;
@@ -162,9 +167,9 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
       }
       if (a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {
         // roughly one wave ahead: the CTA that will own tile blockIdx + pf_dist finds its input in L2
-        int64_t nb = (int64_t)blockIdx.x + a.pf_dist;
-        const int ti2 = (int)(nb % a.tiles_i);
-        const int64_t b2 = nb / a.tiles_i;   // groups == 1 in bulk mode
+        const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
+        const int ti2 = (int)(nb % (unsigned)a.tiles_i);
+        const int64_t b2 = (int64_t)(nb / (unsigned)a.tiles_i);   // groups == 1 in bulk mode
         const int64_t i2 = (int64_t)ti2 * a.T2;
         const int64_t l2 = (a.Nd - i2 < a.T2) ? (a.Nd - i2) : a.T2;
         ptx::bulk_prefetch_l2(a.in + b2 * a.in_sig + i2, (uint32_t)l2 * 8u);
@@ -314,9 +319,7 @@ int dispatch_fwd_pass(jwc_ctx* ctx, cudaStream_t st, const FwdPassArgs& a, const
                       size_t smem, int64_t nblocks) {
   switch (L) {
 #define JWC_CASE(LL) case LL: return launch_fwd_pass<LL>(ctx, st, a, f, threads, smem, nblocks);
-    JWC_CASE(2) JWC_CASE(4) JWC_CASE(6) JWC_CASE(8) JWC_CASE(10) JWC_CASE(12) JWC_CASE(14) JWC_CASE(16) JWC_CASE(18)
-    JWC_CASE(20) JWC_CASE(22) JWC_CASE(24) JWC_CASE(26) JWC_CASE(28) JWC_CASE(30) JWC_CASE(32) JWC_CASE(34) JWC_CASE(36)
-    JWC_CASE(38) JWC_CASE(40)
+    JWC_ALL_L(JWC_CASE)
 #undef JWC_CASE
     default: return JWC_ERR_UNSUPPORTED;
   }
@@ -472,6 +475,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
   const int P = 1 << a.logP;
   auto Vb = [&](int i) { return smem + (i & 1) * a.vcap; };          // always "smem + int": plain LDS/STS addressing
   auto Wb = [&](int i) { return smem + (2 + (i & 1)) * a.vcap; };
+  const bool bulk = (a.mode == MODE_BULK);
   const int oT = 4 * a.vcap;                       // tap copy (kTapDoubles), then the two mbarriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oT + kTapDoubles);
   if (L > kUniformTapsMax) {
@@ -481,11 +485,12 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
     }
   }
 
-  int64_t bid = blockIdx.x;
-  const int ti = (int)(bid % a.tiles_i);
-  bid /= a.tiles_i;
-  const int pg = (int)(bid % a.groups);
-  const int64_t b = bid / a.groups;
+  // CTA index taken apart with 32-bit divisions (nblocks < 2^31; a 64-bit division is a ~100-instruction subroutine)
+  unsigned bid = blockIdx.x;
+  const int ti = (int)(bid % (unsigned)a.tiles_i);
+  bid /= (unsigned)a.tiles_i;
+  const int pg = (int)(bid % (unsigned)a.groups);
+  const int64_t b = (int64_t)(bid / (unsigned)a.groups);
   const int64_t i0 = (int64_t)ti * a.T2;
   const int tlen2 = (int)((a.Nd - i0 < a.T2) ? (a.Nd - i0) : a.T2);
   const int ph0 = pg << a.logP;
@@ -493,7 +498,6 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
   const double* vin_b = a.vin + b * a.vin_sig;
   const double* co_b = a.coeffs + b * a.coeff_sig;
   double* vo_b = a.vout + b * a.vout_sig;
-  const bool bulk = (a.mode == MODE_BULK);
   // halo (decimated) needed by the level-jj inputs; in bulk mode rounded up to an even row count
   auto halo = [&](int jj) { const int h = (L - 1) * ((1 << jj) - 1); return bulk ? h + (h & 1) : h; };
 
@@ -507,9 +511,9 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
   }
   if (bulk && a.pf_dist > 0 && tid <= a.k && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {
     // one wave ahead: thread t pulls the W_{j0+t} tile (t = 1..k) resp. the V tile (t = 0) of CTA blockIdx + pf_dist into L2
-    int64_t nb = (int64_t)blockIdx.x + a.pf_dist;
-    const int ti2 = (int)(nb % a.tiles_i);
-    const int64_t b2 = nb / a.tiles_i;
+    const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
+    const int ti2 = (int)(nb % (unsigned)a.tiles_i);
+    const int64_t b2 = (int64_t)(nb / (unsigned)a.tiles_i);
     const int64_t i2 = (int64_t)ti2 * a.T2;
     const int64_t l2 = (a.Nd - i2 < a.T2) ? (a.Nd - i2) : a.T2;
     const double* src = (tid == 0) ? (a.vin + b2 * a.vin_sig) : (a.coeffs + b2 * a.coeff_sig + (int64_t)(a.j0 + tid - 1) * a.N);
@@ -607,9 +611,7 @@ int dispatch_inv_pass(jwc_ctx* ctx, cudaStream_t st, const InvPassArgs& a, const
                       size_t smem, int64_t nblocks) {
   switch (L) {
 #define JWC_CASE(LL) case LL: return launch_inv_pass<LL>(ctx, st, a, f, threads, smem, nblocks);
-    JWC_CASE(2) JWC_CASE(4) JWC_CASE(6) JWC_CASE(8) JWC_CASE(10) JWC_CASE(12) JWC_CASE(14) JWC_CASE(16) JWC_CASE(18)
-    JWC_CASE(20) JWC_CASE(22) JWC_CASE(24) JWC_CASE(26) JWC_CASE(28) JWC_CASE(30) JWC_CASE(32) JWC_CASE(34) JWC_CASE(36)
-    JWC_CASE(38) JWC_CASE(40)
+    JWC_ALL_L(JWC_CASE)
 #undef JWC_CASE
     default: return JWC_ERR_UNSUPPORTED;
   }

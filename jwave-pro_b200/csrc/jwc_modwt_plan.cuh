@@ -9,8 +9,17 @@
 // a two-roof (HBM, fp64) time model.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <vector>
+
+#ifndef JWC_HD
+#ifdef __CUDACC__
+#define JWC_HD __host__ __device__
+#else
+#define JWC_HD
+#endif
+#endif
 
 namespace jwc {
 
@@ -96,42 +105,79 @@ inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP,
   }
   if (best < 2) return false;
   if (best < Nd && best < H && in.tile_override <= 0) return false;  // halo would dominate the tile
-  out->j0 = j0; out->k = k; out->logP = logP; out->T2 = (int)best; out->Hp = (int)Hp; out->mode = mode;
+  // Candidates: the largest tile that fits and smaller ones in steps of 64 (down to 5/8 of it), each with 128 or 256
+  // threads.  Whole multiples of 128 threads only: a warp's scheduler is fixed by (warp index % 4), so 160- or
+  // 192-thread CTAs put twice the work on one or two of the four schedulers of the SM (the fp64 pipe then idles at
+  // 62-75 % of its rate however many CTAs are resident).  The tile length decides how well the items of every level
+  // fill whole rounds of threads; the model below weighs that against the halo overhead of a shorter tile.
+  double best_est = 1e300;
+  bool found = false;
+  const int64_t tmax = best;
+  // (forward only.  The inverse keeps the largest tile and picks among 128..256 threads in steps of 32 by lane
+  // efficiency, as in round 1: measured on Daubechies20 J = 8, the search below cost it 10 %.)
+  // ... and only for the fp64-bound long filters: the HBM-bound short ones want the largest tile (Daubechies4 on
+  // 100 000 samples: 2.42 ms with the largest tile and 256 threads, 2.62 ms with the searched 1984 x 128).
+  const bool legacy = in.inverse || in.L <= 10;
+  const int64_t tmin = (legacy || in.tile_override > 0 || tmax >= Nd || tmax < 512)
+                           ? tmax : std::max<int64_t>(H, (tmax * 5 / 8) & ~(int64_t)63);
+  int inv_thr = 256;
+  if (legacy) {
+    double e0 = 0;
+    const int Tf = (int)std::min<int64_t>(tmax, Nd);
+    for (int cand = 256; cand >= 128; cand -= 32) {
+      const double e = modwt_lane_efficiency(in.inverse, in.L, k, logP, Tf, cand);
+      if (e > e0 + 0.02) { e0 = e; inv_thr = cand; }
+    }
+  }
+  for (int64_t T2 = tmax; T2 >= tmin && T2 >= 2; T2 -= 64) {
+    const int Tfull = (int)std::min<int64_t>(T2, Nd);
+    for (int cand = 128; cand <= 256; cand += 128) {   // 128 first: smaller CTAs = more of them resident; 256 must win clearly
+      if ((in.threads_override > 0 || legacy) && cand != 128) continue;
+      const int thr = in.threads_override > 0 ? in.threads_override : (legacy ? inv_thr : cand);
+      const double eff = modwt_lane_efficiency(in.inverse, in.L, k, logP, Tfull, thr);
+      // time model per input sample (units: ps): memory and fp64 overlap only partly inside a CTA, short passes worst
+      const double T = (double)Tfull;
+      double avg_hrem = 0;
+      for (int jj = 1; jj <= k; jj++)
+        avg_hrem += in.inverse ? (double)(in.L - 1) * (double)(((int64_t)1 << (jj - 1)) - 1)
+                               : (double)(in.L - 1) * (double)(((int64_t)1 << k) - ((int64_t)1 << jj));
+      avg_hrem /= k;
+      const double sector = (j0 == 0) ? 1.0 : (P >= 4 ? 1.0 : (P == 2 ? 1.6 : 2.5));   // strided 16 B / 8 B rows waste sectors
+      const double bytes = sector * (8.0 * (k + 2) + 8.0 * (double)Hp / T * (in.inverse ? (k + 1) * 0.6 : 1.0));
+      // the last tile of a signal is shorter: its CTA costs a full tile's latency for a fraction of the work
+      const double tiles = std::ceil((double)Nd / T);
+      const double edge = (tiles * T) / (double)Nd;
+      const double flops = 4.0 * in.L * k * (1.0 + avg_hrem / T) / std::max(eff, 0.3);
+      const double tm = bytes / 5.5, tc = flops / 32.0;
+      double est = (std::max(tm, tc) + 0.35 * std::min(tm, tc)) * (0.5 + 0.5 * edge) + 2.0;
+      // a CTA costs about 4 ns of GPU time whatever it does (launch, barriers, mbarrier round trips): measured on
+      // windows of 512 samples, where a phase-split pass with 32-sample CTAs ran at 127 ps/sample
+      const double cta_samples = (double)P * T;
+      if (cta_samples < 1024.0) est += 4000.0 / cta_samples;
+      if (cand == 256) est *= 1.04;
+      if (!legacy) {   // too few resident warps cannot cover the load / barrier phases of the other CTAs of the SM
+        const double smem_bytes = (double)modwt_smem_doubles(in.inverse, P, (int)T2, (int)Hp, k) * 8 + 2048;
+        const int ctas = std::max(1, std::min(8, (int)(232448.0 / smem_bytes)));
+        const int warps = ctas * thr / 32;
+        if (warps < 12) est *= 1.0 + 0.05 * (12 - warps);
+      }
+      if (est < best_est - 1e-9) {
+        best_est = est;
+        found = true;
+        out->T2 = (int)T2;
+        out->threads = thr;
+      }
+    }
+  }
+  if (!found) return false;
+  best = out->T2;
+  out->j0 = j0; out->k = k; out->logP = logP; out->Hp = (int)Hp; out->mode = mode;
   const int64_t pad = (int64_t)kModwtR * P * ((int64_t)1 << (k - 1));
   int64_t vcap = (int64_t)P * (best + Hp) + pad;
   vcap += vcap & 1;
   out->vcap = (int)vcap;
   out->smem = (size_t)modwt_smem_doubles(in.inverse, P, (int)best, (int)Hp, k) * 8 + 1024 + 64;
-  // threads: the candidate with the best lane efficiency (ties -> more threads)
-  const int Tfull = (int)std::min<int64_t>(best, Nd);
-  int thr = 256;
-  double eff = 0;
-  if (in.threads_override > 0) {
-    thr = in.threads_override;
-    eff = modwt_lane_efficiency(in.inverse, in.L, k, logP, Tfull, thr);
-  } else {
-    for (int cand = 256; cand >= 128; cand -= 32) {
-      const double e = modwt_lane_efficiency(in.inverse, in.L, k, logP, Tfull, cand);
-      if (e > eff + 0.02) { eff = e; thr = cand; }
-    }
-  }
-  out->threads = thr;
-  // time model per input sample (units: ps): memory and fp64 overlap only partly inside a CTA, short passes worst
-  const double T = (double)Tfull;
-  double avg_hrem = 0;
-  for (int jj = 1; jj <= k; jj++)
-    avg_hrem += in.inverse ? (double)(in.L - 1) * (double)(((int64_t)1 << (jj - 1)) - 1)
-                           : (double)(in.L - 1) * (double)(((int64_t)1 << k) - ((int64_t)1 << jj));
-  avg_hrem /= k;
-  const double sector = (j0 == 0) ? 1.0 : (P >= 4 ? 1.0 : (P == 2 ? 1.6 : 2.5));   // strided 16 B / 8 B rows waste sectors
-  const double bytes = sector * (8.0 * (k + 2) + 8.0 * (double)Hp / T * (in.inverse ? (k + 1) * 0.6 : 1.0));
-  const double flops = 4.0 * in.L * k * (1.0 + avg_hrem / T) / std::max(eff, 0.3);
-  const double tm = bytes / 5.5, tc = flops / 32.0;
-  *est_time = std::max(tm, tc) + 0.35 * std::min(tm, tc) + 2.0;
-  // a CTA costs about 4 ns of GPU time whatever it does (launch, barriers, mbarrier round trips): measured on windows
-  // of 512 samples, where a phase-split pass with 32-sample CTAs ran at 127 ps/sample; the per-level kernels win there
-  const double cta_samples = (double)P * T;
-  if (cta_samples < 1024.0) *est_time += 4000.0 / cta_samples;
+  *est_time = best_est;
   return true;
 }
 

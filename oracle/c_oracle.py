@@ -157,6 +157,22 @@ def batch(op, x, level, f0, f1, nthreads=1):
     return out
 
 
+def parallel_wpt(x, level, f0, f1, reverse=False, nthreads=1):
+    """ParallelWaveletPacketTransform.forward / reverse (ParallelWaveletPacketTransform.java:79-147) on every row of x,
+    one signal after the other, each level's packets forked over `nthreads` workers when packet >= 64 and packets >= 8
+    (:155-158), leaves of at most 16 packets (:197-233).  f0 / f1: DeCom filters forward, ReCon filters reverse."""
+    x, f0, f1 = _c(x), _c(f0), _c(f1)
+    B, N = x.shape
+    out = np.empty((B, N))
+    fn = lib().jwo_parallel_wpt
+    fn.argtypes = [_dp, _dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_int,
+                   ctypes.c_int]
+    fn.restype = ctypes.c_int
+    rc = fn(_p(x), _p(out), B, N, level, _p(f0), _p(f1), len(f0), nthreads, 1 if reverse else 0)
+    assert rc == 0, rc
+    return out
+
+
 def batch2d(kind, x, lvl_m, lvl_n, f0, f1, reverse=False, nthreads=1):
     """2-D FWT / WPT of every matrix of x (batch, rows, cols), composed from the 1-D oracle exactly as the reference
     composes it: transforms/BasicTransform.java:361-399 (forward: every row with lvl_n, then every column of the result

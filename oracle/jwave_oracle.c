@@ -490,3 +490,121 @@ JWO_API int jwo_batch(int op, const double* in, double* out, int64_t batch, int 
   free(jobs);
   return rc;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * transforms/ParallelWaveletPacketTransform.java -- the CPU baseline north_star names for the WPT.
+ * Same arithmetic as WaveletPacketTransform (its own tests, ParallelWPTTest.java:154-178, require equality with the
+ * sequential transform to 1e-10); what differs is the SCHEDULE, restated here:
+ *   :79-110 / :113-147   level loop on ONE signal: h = N, N/2, ... (reverse: h = 2^(steps-level+1) ... N), packets = N / h
+ *   :155-158             a level runs in parallel only when packetSize >= 64 && packets >= 8, else sequentially (:163-184)
+ *   :197-233             WPTLevelTask: the packet range is halved recursively until a task holds <= 16 packets; the
+ *                        leaves run on a ForkJoinPool (work stealing), invoke() joins before the next level starts
+ * The ForkJoinPool is a persistent pool of `nthreads` workers; here: a persistent pthread pool, the leaves of a level in
+ * a shared array handed out by an atomic counter (the stand-in for work stealing), one barrier pair per parallel level
+ * (fork / join).  Signals of a batch go through one after the other, exactly as a caller looping over
+ * ParallelWaveletPacketTransform.forward would run them.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  pthread_barrier_t start, done;
+  int nthreads, stop;
+  /* the level in flight */
+  double* data;
+  int h, L, forward, nleaves;
+  const double *f0, *f1;
+  int (*leaves)[2];
+  int next;   /* atomic cursor into leaves */
+} jwo_pool;
+
+static void jwo_pwpt_packet(double* data, int h, int p, const double* f0, const double* f1, int L, int forward,
+                            double* ib, double* ob) {
+  /* :244-262 processPacket: copy the packet out, one Wavelet step, copy it back */
+  memcpy(ib, data + (size_t)p * h, sizeof(double) * (size_t)h);
+  if (forward) jwo_wavelet_forward(ib, h, f0, f1, L, ob);
+  else jwo_wavelet_reverse(ib, h, f0, f1, L, ob);
+  memcpy(data + (size_t)p * h, ob, sizeof(double) * (size_t)h);
+}
+
+static void jwo_pwpt_drain(jwo_pool* pl, double* ib, double* ob) {
+  for (;;) {
+    int i = __atomic_fetch_add(&pl->next, 1, __ATOMIC_RELAXED);
+    if (i >= pl->nleaves) break;
+    for (int p = pl->leaves[i][0]; p < pl->leaves[i][1]; p++)
+      jwo_pwpt_packet(pl->data, pl->h, p, pl->f0, pl->f1, pl->L, pl->forward, ib, ob);
+  }
+}
+
+typedef struct { jwo_pool* pl; int N; } jwo_pwpt_arg;
+
+static void* jwo_pwpt_worker(void* a) {
+  jwo_pwpt_arg* arg = (jwo_pwpt_arg*)a;
+  jwo_pool* pl = arg->pl;
+  double* ib = (double*)malloc(sizeof(double) * (size_t)arg->N);
+  double* ob = (double*)malloc(sizeof(double) * (size_t)arg->N);
+  for (;;) {
+    pthread_barrier_wait(&pl->start);
+    if (pl->stop) break;
+    jwo_pwpt_drain(pl, ib, ob);
+    pthread_barrier_wait(&pl->done);
+  }
+  free(ib);
+  free(ob);
+  return NULL;
+}
+
+/* :215-232 WPTLevelTask.compute: halve [a, b) until <= 16 packets */
+static void jwo_pwpt_split(int a, int b, int (*leaves)[2], int* n) {
+  if (b - a <= 16) { leaves[*n][0] = a; leaves[*n][1] = b; (*n)++; return; }
+  int mid = a + (b - a) / 2;
+  jwo_pwpt_split(a, mid, leaves, n);
+  jwo_pwpt_split(mid, b, leaves, n);
+}
+
+JWO_API int jwo_parallel_wpt(const double* in, double* out, int64_t batch, int N, int level, const double* f0,
+                             const double* f1, int L, int nthreads, int reverse) {
+  if (N < 1 || (N & (N - 1)) || level < 0) return -1;
+  int steps = 0;
+  while ((1 << steps) < N) steps++;
+  if (level > steps) return -1;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 1024) nthreads = 1024;
+  jwo_pool pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.nthreads = nthreads;
+  pl.f0 = f0; pl.f1 = f1; pl.L = L; pl.forward = !reverse;
+  pl.leaves = (int (*)[2])malloc(sizeof(int[2]) * (size_t)(N / 2 + 1));
+  pthread_barrier_init(&pl.start, NULL, (unsigned)nthreads);
+  pthread_barrier_init(&pl.done, NULL, (unsigned)nthreads);
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+  jwo_pwpt_arg arg = {&pl, N};
+  for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, jwo_pwpt_worker, &arg);
+  double* ib = (double*)malloc(sizeof(double) * (size_t)N);
+  double* ob = (double*)malloc(sizeof(double) * (size_t)N);
+  for (int64_t b = 0; b < batch; b++) {
+    double* d = out + (size_t)b * N;
+    memcpy(d, in + (size_t)b * N, sizeof(double) * (size_t)N);   /* Arrays.copyOf :88 / :122 */
+    int64_t h;
+    int l = 0;
+    if (!reverse) h = N;
+    else { h = 2; for (int q = level; q < steps; q++) h <<= 1; }
+    while (!reverse ? (h >= 2 && l < level) : (h <= N && h >= 2)) {
+      int packets = (int)(N / h);
+      if (h >= 64 && packets >= 8) {          /* shouldUseParallel :155-158 */
+        pl.data = d; pl.h = (int)h; pl.nleaves = 0; pl.next = 0;
+        jwo_pwpt_split(0, packets, pl.leaves, &pl.nleaves);
+        if (nthreads > 1) pthread_barrier_wait(&pl.start);   /* fork */
+        jwo_pwpt_drain(&pl, ib, ob);
+        if (nthreads > 1) pthread_barrier_wait(&pl.done);    /* join (invoke returns) */
+      } else {
+        for (int p = 0; p < packets; p++) jwo_pwpt_packet(d, (int)h, p, f0, f1, L, !reverse, ib, ob);   /* :163-184 */
+      }
+      if (!reverse) { h >>= 1; l++; } else h <<= 1;
+    }
+  }
+  pl.stop = 1;
+  if (nthreads > 1) pthread_barrier_wait(&pl.start);
+  for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+  pthread_barrier_destroy(&pl.start);
+  pthread_barrier_destroy(&pl.done);
+  free(th); free(ib); free(ob); free(pl.leaves);
+  return 0;
+}

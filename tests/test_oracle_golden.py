@@ -219,3 +219,23 @@ def test_2d_all_ones_concentrates_in_one_coefficient(W, oracle):
             exp = np.zeros((rows, cols))
             exp[0, 0] = math.sqrt(rows * cols)
             np.testing.assert_allclose(out, exp, atol=1e-9)
+
+
+def test_parallel_wpt_schedule_equals_sequential_wpt(oracle, jw):
+    """ParallelWPTTest.java:154-178: the parallel transform must equal WaveletPacketTransform to 1e-10 (here: bit for
+    bit, the arithmetic per packet is the same) for levels below and above the `packet >= 64 && packets >= 8` rule of
+    ParallelWaveletPacketTransform.java:155-158, forward and reverse, for any worker count."""
+    rng = np.random.default_rng(20251018)
+    for cls in ("Haar1", "Daubechies4", "Symlet8"):
+        w = jw.wavelets.create(cls)
+        sd, wd = w.getScalingDeComposition(), w.getWaveletDeComposition()
+        sr, wr = w.getScalingReConstruction(), w.getWaveletReConstruction()
+        for n, level in ((16384, 8), (1024, 10), (512, 3), (64, 6), (4, 2), (2, 0)):
+            x = rng.uniform(-1.0, 1.0, size=(2, n))
+            seq = oracle.batch("wpt_fwd", x, level, sd, wd)
+            for nt in (1, 3, 8):
+                par = oracle.parallel_wpt(x, level, sd, wd, nthreads=nt)
+                assert np.array_equal(par, seq), (cls, n, level, nt)
+                back = oracle.parallel_wpt(par, level, sr, wr, reverse=True, nthreads=nt)
+                assert np.array_equal(back, oracle.batch("wpt_rev", seq, level, sr, wr))
+                assert np.max(np.abs(back - x)) <= 1e-10
