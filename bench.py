@@ -560,11 +560,10 @@ def multi_device_check(jw, torch, ngpu):
         ok_i = all(torch.equal(xrs[p].to("cuda:0"), xr_ref[bounds[p]:bounds[p + 1]]) for p in range(ngpu))
         out["split_bit_identical"] = {"modwt_forward": bool(ok_f), "modwt_inverse": bool(ok_i)}
         del c_ref, cs
-        # FWT / WPT of one long series split over the devices (when the library has the entry points)
+        # FWT / WPT of one long series split over the devices: the per-device chunks come back in the local layout
+        # (include/jwavecuda.h); assembled band by band they must equal the unsplit transform
         for kind, T in (("fwt", jw.CudaFastWaveletTransform), ("wpt", jw.CudaWaveletPacketTransform)):
             tr1, trP = T(w, context=one), T(w, context=ctx)
-            if not hasattr(trP, "forwardSplitDevice"):
-                continue
             lv = 22 if kind == "fwt" else 6
             y_ref = torch.empty(n, dtype=torch.float64, device="cuda:0")
             z_ref = torch.empty(n, dtype=torch.float64, device="cuda:0")
@@ -575,10 +574,18 @@ def multi_device_check(jw, torch, ngpu):
             zs = [torch.empty_like(t) for t in ys]
             trP.forwardSplitDevice([t.data_ptr() for t in xs], [t.data_ptr() for t in ys], n, lv)
             trP.reverseSplitDevice([t.data_ptr() for t in ys], [t.data_ptr() for t in zs], n, lv)
-            okf = all(torch.equal(ys[p].to("cuda:0"), y_ref[bounds[p]:bounds[p + 1]]) for p in range(ngpu))
-            oki = all(torch.equal(zs[p].to("cuda:0"), z_ref[bounds[p]:bounds[p + 1]]) for p in range(ngpu))
-            out["split_bit_identical"][kind + "_forward"] = bool(okf)
-            out["split_bit_identical"][kind + "_inverse"] = bool(oki)
+            got = trP.splitLayoutToGlobal([t.cpu().numpy() for t in ys], n, lv)
+            yr, zr = y_ref.cpu().numpy(), z_ref.cpu().numpy()
+            back = np.concatenate([t.cpu().numpy() for t in zs])
+            ls = trP.splitLevels(n, lv)
+            scale = float(np.max(np.abs(x.cpu().numpy())))
+            out["split_bit_identical"][kind + "_forward"] = bool(np.array_equal(got[n >> ls:], yr[n >> ls:]) if kind == "fwt"
+                                                                 else np.array_equal(got, yr))
+            out["split_max_err"] = dict(out.get("split_max_err", {}), **{
+                kind + "_forward_vs_unsplit": float(np.max(np.abs(got - yr))) / scale,
+                kind + "_round_trip": float(np.max(np.abs(back - x.cpu().numpy()))) / scale,
+                kind + "_inverse_vs_unsplit": float(np.max(np.abs(back - zr))) / scale})
+            out["split_levels_" + kind] = int(ls)
         out["split_series"] = "%d samples, Daubechies4, MODWT J=%d / FWT 22 levels / WPT 6 levels, %d chunks" % (n, J, ngpu)
         # (ii) host-buffer e2e through the single context: C2 shape, 256 signals per device
         B, N2, J2 = 256 * ngpu, 65536, 6

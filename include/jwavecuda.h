@@ -119,6 +119,33 @@ JWC_API int jwc_modwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_x_c
 JWC_API int jwc_modwt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_coeff_chunks, double* const* d_x_chunks,
                                         int64_t n, int levels, const double* g, const double* h, int L, unsigned flags);
 
+/* FWT / WPT of one long series split over the context's devices (the decimated counterpart of the two calls above;
+ * reference loops: transforms/FastWaveletTransform.java:85-99,133-151, transforms/WaveletPacketTransform.java:98-120,167-187).
+ * n = 2^m, P = number of device slots = 2^q, chunk p = samples [p n/P, (p+1) n/P) on slot p.  The data never moves: after
+ * l levels slot p holds the (n/P)/2^l coefficients of every node whose support starts in its chunk; a fused pass pulls
+ * (L-2)(2^k-1) samples (forward, right neighbour's head) or <= L-2 coefficients per child array (inverse, left
+ * neighbour's tail) from the ring neighbour with cudaMemcpyPeerAsync.  No collective.
+ * Output ("local layout", input of the inverse): chunk p is the transform's own layout of a signal of length n/P filled
+ * with slot p's coefficients --
+ *   WPT:  [leaf 0 part | leaf 1 part | ...]; part c = leaf c of the reference at positions [p len_c/P, (p+1) len_c/P)
+ *   FWT:  [T_p | D_ls part | ... | D_1 part], D_l part = D_l[p (n/P)/2^l, (p+1) (n/P)/2^l); ls = jwc_dwt_split_levels()
+ *         levels run split (input part >= 2048 samples); the remaining pyramid on A_ls (n/2^ls samples, the small
+ *         remainder) is gathered on slot 0, transformed there, and its array [A_J | D_J .. D_{ls+1}] cut into P equal
+ *         contiguous pieces T_p.
+ * Concatenating the parts of a band over p gives that band of the unsplit result bit for bit.  WPT needs
+ * levels <= jwc_dwt_split_levels (packet parts of at least 1024 samples per device).  Chunk buffers must be ready on entry;
+ * the calls return after all devices have finished. */
+JWC_API int jwc_fwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_forward_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags);
+/* number of levels of an n-sample, `levels`-level transform that run split on this context (-1: shape not splittable) */
+JWC_API int jwc_dwt_split_levels(const jwc_ctx* ctx, int64_t n, int levels);
+
 /* Sliding-window analysis (the reference's motivating workload, test/.../MODWTSlidingWindowTest.java:20-70: 512-sample
  * windows, 8 levels, step 64): window w = series[w*hop .. w*hop + window), w = 0 .. (series_len - window)/hop, each
  * through forwardMODWT.  The windows are never materialised: the kernels read window w at series + w*hop.

@@ -31,6 +31,8 @@ SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal"
             "jwc_release_scratch"]
            + ["jwc_" + t for t in _TRANSFORMS] + ["jwc_" + t + "_dev" for t in _TRANSFORMS]
            + ["jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"]
+           + ["jwc_fwt_forward_split_dev", "jwc_fwt_inverse_split_dev", "jwc_wpt_forward_split_dev",
+              "jwc_wpt_inverse_split_dev", "jwc_dwt_split_levels"]
            + ["jwc_modwt_forward_windows", "jwc_modwt_forward_windows_dev", "jwc_compress_magnitude",
               "jwc_compress_magnitude_dev"]
            + ["jwc_diag_dfma_tflops", "jwc_diag_copy_gbs"]
@@ -123,7 +125,10 @@ def load():
         lib.jwc_diag_dfma_tflops.restype = _int
         lib.jwc_diag_copy_gbs.argtypes = [_vp, _int, ctypes.c_size_t, _dp]
         lib.jwc_diag_copy_gbs.restype = _int
-        for nm in ("jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev"):
+        lib.jwc_dwt_split_levels.argtypes = [_vp, _i64, _int]
+        lib.jwc_dwt_split_levels.restype = _int
+        for nm in ("jwc_modwt_forward_split_dev", "jwc_modwt_inverse_split_dev", "jwc_fwt_forward_split_dev",
+                   "jwc_fwt_inverse_split_dev", "jwc_wpt_forward_split_dev", "jwc_wpt_inverse_split_dev"):
             fn = getattr(lib, nm)
             fn.argtypes = [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _int, _dp, _dp, _int, _u32]
             fn.restype = _int

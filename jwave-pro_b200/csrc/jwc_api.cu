@@ -840,6 +840,49 @@ JWC_DEFINE_2D(fwt2d_inverse, Op::FwtInv)
 JWC_DEFINE_2D(wpt2d_forward, Op::WptFwd)
 JWC_DEFINE_2D(wpt2d_inverse, Op::WptInv)
 
+static int dwt_split_entry(jwc_ctx* ctx, bool inverse, bool tree, const double* const* d_in, double* const* d_out,
+                           int64_t n, int levels, const double* lo, const double* hi, int L, unsigned flags) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  JWC_REQUIRE(d_in != nullptr && d_out != nullptr && lo != nullptr && hi != nullptr, "NULL pointer");
+  JWC_REQUIRE(L >= 1 && L <= JWC_MAX_TAPS, "filter length %d outside 1..%d", L, JWC_MAX_TAPS);
+  JWC_REQUIRE(n >= 1 && (n & (n - 1)) == 0, "given array length is not 2^p (got %lld)", (long long)n);
+  int p2 = 0;
+  while (((int64_t)1 << (p2 + 1)) <= n) p2++;
+  JWC_REQUIRE(levels >= 0 && levels <= p2, "given level %d is out of range for given array of length %lld", levels, (long long)n);
+  JWC_REQUIRE((flags & (JWC_FLAG_EXACT | JWC_FLAG_FORCE_GENERIC)) == 0, "split transforms run on the fused kernels only");
+  for (size_t p = 0; p < ctx->slots.size(); p++)
+    JWC_REQUIRE(d_in[p] != nullptr && d_out[p] != nullptr, "chunk pointer %d is NULL", (int)p);
+  FilterPair fp;
+  load_filters(fp, lo, hi, L);
+  const int rc = split_dwt(ctx, inverse, tree, d_in, d_out, n, levels, fp, L);
+  if (rc == JWC_ERR_UNSUPPORTED && jwc_last_error()[0] == 0) set_error("shape outside the split FWT/WPT path");
+  return rc;
+}
+JWC_API int jwc_fwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags) {
+  return dwt_split_entry(ctx, false, false, d_in_chunks, d_out_chunks, n, levels, lo, hi, L, flags);
+}
+JWC_API int jwc_fwt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags) {
+  return dwt_split_entry(ctx, true, false, d_in_chunks, d_out_chunks, n, levels, lo, hi, L, flags);
+}
+JWC_API int jwc_wpt_forward_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags) {
+  return dwt_split_entry(ctx, false, true, d_in_chunks, d_out_chunks, n, levels, lo, hi, L, flags);
+}
+JWC_API int jwc_wpt_inverse_split_dev(jwc_ctx* ctx, const double* const* d_in_chunks, double* const* d_out_chunks, int64_t n,
+                                      int levels, const double* lo, const double* hi, int L, unsigned flags) {
+  return dwt_split_entry(ctx, true, true, d_in_chunks, d_out_chunks, n, levels, lo, hi, L, flags);
+}
+JWC_API int jwc_dwt_split_levels(const jwc_ctx* ctx, int64_t n, int levels) {
+  if (!ctx || n < 1 || (n & (n - 1)) || levels < 0) return -1;
+  const int P = (int)ctx->slots.size();
+  if (P < 1 || (P & (P - 1)) || n % P) return -1;
+  int steps = 0;
+  for (int64_t h = n; h >= 2 && steps < levels; h >>= 1) steps++;
+  return dwt_split_levels(n, P, steps, false);
+}
+
 JWC_API int jwc_modwt_forward_split_dev(jwc_ctx* ctx, const double* const* d_x_chunks, double* const* d_coeff_chunks,
                                         int64_t n, int levels, const double* g, const double* h, int L, unsigned flags) {
   return modwt_split(ctx, false, d_x_chunks, d_coeff_chunks, n, levels, g, h, L, flags);

@@ -15,6 +15,7 @@
 //   synthesis: reads R + L/2 - 1 (lo, hi) coefficient pairs (2 x LDS.64), 2*R*L DFMA -> R output pairs (STS.128)
 // R is odd, so the lane stride (R x 16 B resp. R x 8 B) maps the lanes of every quarter/half warp to distinct banks.
 #include <cstdlib>
+#include <memory>
 
 #include "jwc_dwt_plan.cuh"
 #include "jwc_internal.cuh"
@@ -54,30 +55,57 @@ struct DwtPassArgs {
                       // division is a ~100-instruction subroutine, and a CTA only lives for a few thousand)
   unsigned nblocks;
   int hl[16];             // inverse: left halo of the depth-jj arrays (dwt_inv_halo), precomputed on the host
+  // split-device mode (one long series in chunks on several devices, batch = 1): the arrays this pass reads are chunks
+  // of longer ones, so what lies past their end (forward) / before their start (inverse) comes from `halo`, a small
+  // buffer filled with the ring neighbour's boundary samples (cudaMemcpyPeerAsync), not from the periodic wrap.
+  //   forward: halo[node * halo_stride + i] = sample h + i of the node            (right neighbour's head)
+  //   inverse: slot s (halo_stride doubles) holds the samples before position 0, right-aligned (left neighbour's
+  //            tail); tree: slot = node * 2^k + leaf; pyramid: slot 0 = A_{l0+k}, slot 1 + (k - jj) = D_{l0+jj}
+  const double* halo;     // nullptr = ordinary periodic transform
+  int64_t halo_stride;
 };
 
-// circular bulk load of `len` doubles starting at node position `start` (any sign, any number of wraps) of a node of
-// length hn at `base` into dst.  One thread; the mbarrier must already expect the bytes.  start, hn, len are even.
+// bulk load of `len` doubles starting at node position `start` of a node of length hn at `base` into dst.  One thread;
+// the mbarrier must already expect the bytes.  start, hn, len are even.
+//   hi == nullptr && lo_end == nullptr: circular (any sign of start, any number of wraps)
+//   split-device mode: positions >= hn continue at hi[pos - hn], positions < 0 come from lo_end[pos] (single overhang)
 __device__ __forceinline__ void bulk_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
-                                               uint64_t* bar) {
+                                               uint64_t* bar, const double* hi = nullptr, const double* lo_end = nullptr) {
+  const bool circ = (hi == nullptr && lo_end == nullptr);
   // no 64-bit modulo here: it would be a subroutine call inside the level loop of the inverse kernel, and everything
   // live across that call (accumulator / tap registers of the other threads' code path) pays for it.  |start| is at
   // most a halo (tens of samples), so the two loops run a handful of times for one thread.
   int64_t pos = start;
-  while (pos < 0) pos += hn;
-  while (pos >= hn) pos -= hn;
+  if (circ) {
+    while (pos < 0) pos += hn;
+    while (pos >= hn) pos -= hn;
+  }
   int done = 0;
   while (done < len) {
-    int64_t run = hn - pos;
+    const double* src;
+    int64_t run;
+    if (pos < 0) { run = -pos; src = lo_end + pos; }
+    else if (pos >= hn) {
+      if (circ) { pos = 0; continue; }
+      run = len - done; src = hi + (pos - hn);
+    } else { run = hn - pos; src = base + pos; }
     if (run > len - done) run = len - done;
-    ptx::bulk_g2s(dst + done, base + pos, (uint32_t)run * 8u, bar);
+    ptx::bulk_g2s(dst + done, src, (uint32_t)run * 8u, bar);
     done += (int)run;
-    pos = 0;
+    pos += run;
   }
 }
 
 __device__ __forceinline__ void scalar_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
-                                                 int tid, int nt) {
+                                                 int tid, int nt, const double* hi = nullptr,
+                                                 const double* lo_end = nullptr) {
+  if (hi != nullptr || lo_end != nullptr) {   // split-device mode
+    for (int e = tid; e < len; e += nt) {
+      const int64_t pos = start + e;
+      dst[e] = pos < 0 ? lo_end[pos] : (pos >= hn ? hi[pos - hn] : base[pos]);
+    }
+    return;
+  }
   // node lengths are < 2^31 (checked by the callers): 32-bit remainder, no division subroutine
   const int h32 = (int)hn;
   int s32 = (int)(start % hn);
@@ -228,6 +256,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
   const double* node = a.in + b * a.in_sig + (int64_t)p * a.h;
   const bool bulk = (a.mode == DWT_BULK);
   const int H = (L - 2) * ((1 << a.k) - 1);
+  const double* fhalo = a.halo ? a.halo + (int64_t)p * a.halo_stride : nullptr;   // split-device mode: right neighbour's head
 
   // ---- load: node samples a0 .. a0 + tlen + H - 1 (periodic) ---------------------------------------------------------
   if (bulk) {
@@ -235,7 +264,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
       ptx::mbar_init(bar, 1);
       ptx::fence_mbar_init();
       ptx::mbar_expect_tx(bar, (uint32_t)(tlen + H) * 8u);
-      bulk_load_circ(smem, node, a0, tlen + H, a.h, bar);
+      bulk_load_circ(smem, node, a0, tlen + H, a.h, bar, fhalo);
       if (a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {   // one wave ahead into L2
         const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
         const int ti2 = (int)(nb & (unsigned)(a.tiles - 1));
@@ -248,7 +277,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) dwt_fwd_pass_kernel(con
     __syncthreads();
     ptx::mbar_wait(bar, 0);
   } else {
-    scalar_load_circ(smem, node, a0, tlen + H, a.h, tid, nt);
+    scalar_load_circ(smem, node, a0, tlen + H, a.h, tid, nt, fhalo);
     __syncthreads();
   }
 
@@ -441,6 +470,8 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
   const bool bulk = (a.mode == DWT_BULK);
   const double* in_b = a.in + b * a.in_sig;
 
+  // split-device mode: END of halo slot `slot` (the samples before position 0 of that array, right-aligned)
+  auto ihalo = [&](int slot) -> const double* { return a.halo ? a.halo + (int64_t)(slot + 1) * a.halo_stride : nullptr; };
   // geometry of depth jj: children arrays of length len = (tlen >> jj) + HLj, node length hn = h >> jj
   auto len_of = [&](int jj) { return (tlen >> jj) + s_hl[jj]; };
   auto stride_of = [&](int jj) { const int l = len_of(jj); return l + (l & 1) + 2 * kDwtR; };
@@ -479,9 +510,11 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
         if (tid == 0) ptx::mbar_expect_tx(&bars[0], (uint32_t)(leaves * len) * 8u);
         __syncthreads();
         if (tid < 32)
-          for (int c = tid; c < leaves; c += 32) bulk_load_circ(smem + c * st, src0 + c * hn, start, len, hn, &bars[0]);
+          for (int c = tid; c < leaves; c += 32)
+            bulk_load_circ(smem + c * st, src0 + c * hn, start, len, hn, &bars[0], nullptr, ihalo(p * leaves + c));
       } else {
-        for (int c = 0; c < leaves; c++) scalar_load_circ(smem + c * st, src0 + c * hn, start, len, hn, tid, nt);
+        for (int c = 0; c < leaves; c++)
+          scalar_load_circ(smem + c * st, src0 + c * hn, start, len, hn, tid, nt, nullptr, ihalo(p * leaves + c));
       }
     } else {
       const double* asrc = a.ain + b * a.ain_sig;                 // A_{l0+k}
@@ -489,12 +522,12 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
       if (bulk) {
         if (tid == 0) {
           ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)len * 8u);
-          bulk_load_circ(smem, asrc, start, len, hn, &bars[0]);
-          bulk_load_circ(smem + st, dsrc, start, len, hn, &bars[0]);
+          bulk_load_circ(smem, asrc, start, len, hn, &bars[0], nullptr, ihalo(0));
+          bulk_load_circ(smem + st, dsrc, start, len, hn, &bars[0], nullptr, ihalo(1));
         }
       } else {
-        scalar_load_circ(smem, asrc, start, len, hn, tid, nt);
-        scalar_load_circ(smem + st, dsrc, start, len, hn, tid, nt);
+        scalar_load_circ(smem, asrc, start, len, hn, tid, nt, nullptr, ihalo(0));
+        scalar_load_circ(smem + st, dsrc, start, len, hn, tid, nt, nullptr, ihalo(1));
       }
     }
   }
@@ -509,10 +542,10 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
       if (bulk) {
         if (tid == 0) {
           ptx::mbar_expect_tx(&bars[(u + 1) & 1], (uint32_t)len * 8u);
-          bulk_load_circ(smem + oout + st_out, dsrc, start, len, hn, &bars[(u + 1) & 1]);
+          bulk_load_circ(smem + oout + st_out, dsrc, start, len, hn, &bars[(u + 1) & 1], nullptr, ihalo(1 + a.k - (jj - 1)));
         }
       } else {
-        scalar_load_circ(smem + oout + st_out, dsrc, start, len, hn, tid, nt);
+        scalar_load_circ(smem + oout + st_out, dsrc, start, len, hn, tid, nt, nullptr, ihalo(1 + a.k - (jj - 1)));
       }
     }
     if (bulk && (!TREE || u == 0)) {
@@ -631,7 +664,7 @@ int dwt_prefetch_distance(jwc_ctx* ctx, const DeviceSlot& dev, size_t smem, int 
 }
 
 DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const void* p1, int64_t n, int steps, int L,
-                  bool tree, bool inverse, int64_t ld) {
+                  bool tree, bool inverse, int64_t ld, int group_cap = 0) {
   DwtPlanInput pin{};
   pin.n = n; pin.levels = steps; pin.L = L; pin.tree = tree; pin.inverse = inverse;
   pin.aligned16 = ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0 && (ld & 1) == 0;
@@ -642,6 +675,7 @@ DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const voi
   // (measured, Haar 2^20: k <= 3 gives 3.10 ms, the model's k = 5 gives 3.38 ms)
   if (inverse && !tree && pin.group_override <= 0) pin.group_override = 3;
   pin.threads_override = ctx->tune.dwt_threads;
+  if (group_cap > 0) pin.group_override = pin.group_override > 0 ? std::min(pin.group_override, group_cap) : group_cap;
   return dwt_plan(pin, steps);
 }
 
@@ -815,6 +849,287 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     asrc = a.out; asrc_sig = a.out_sig;
   }
   return JWC_OK;
+}
+
+// =========================================================================================================================
+// One long series split over the context's devices (FWT / WPT part).
+//
+// Device slot p holds samples [p*len, (p+1)*len) of the series, len = n / P (n and P powers of two).  Every analysis
+// level halves the local part: after l levels slot p owns the coefficients whose time support starts in its chunk,
+// (len >> l) per node, so the data never moves between devices -- only the halo does.  A fused pass of k levels reads
+// (L-2)(2^k-1) samples past the end of each local node part (forward) or at most L-2 coefficients before the start of
+// each child part (inverse): those come from the ring neighbour with cudaMemcpyPeerAsync (one copy per node / child
+// array), and the tile kernels take them from the small halo buffer instead of wrapping periodically.  Passes are
+// ordered across devices with events (a pass waits for both neighbours' previous pass); no collective, no host sync
+// inside.
+//
+// Result layout ("local layout"): chunk p of the output is the transform's own layout of a signal of length len, filled
+// with the coefficients slot p owns:
+//   WPT, J levels:  [leaf 0 part | leaf 1 part | ... ], part c = leaf c of the reference, positions [p*len/2^J, (p+1)*len/2^J)
+//   FWT:            [T_p | D_ls part | ... | D_1 part], D_l part = D_l[p*len/2^l, (p+1)*len/2^l); the first ls levels
+//                   run split (ls = dwt_split_levels); the remaining pyramid works on A_ls, n/2^ls samples -- the
+//                   "small remainder": it is gathered on slot 0, transformed there, and its result array
+//                   [A_J | D_J .. D_{ls+1}] is cut into P equal contiguous pieces T_p.
+// Concatenating the parts of one band over p gives that band of the reference's array, bit for bit: the arithmetic per
+// coefficient is the same tile kernel code on the same samples.
+// =========================================================================================================================
+int dwt_split_levels(int64_t n, int P, int steps, bool tree) {
+  (void)tree;
+  const int64_t len = n / P;
+  int ls = 0;
+  while (ls < steps && (len >> ls) >= 2048) ls++;   // a level runs split while its input part has >= 2048 samples
+  return ls;
+}
+
+namespace {
+
+struct SplitDev {
+  const DeviceSlot* dev = nullptr;
+  std::vector<cudaEvent_t> done;   // done[i]: pass i (in execution order) finished on this device
+};
+
+int split_fail(const char* what, cudaError_t e) {
+  set_error("split transform: %s failed: %s", what, cudaGetErrorString(e));
+  return JWC_ERR_CUDA;
+}
+
+}  // namespace
+
+int split_dwt(jwc_ctx* ctx, bool inverse, bool tree, const double* const* d_in, double* const* d_out, int64_t n,
+              int levels, const FilterPair& f, int L) {
+  const int P = (int)ctx->slots.size();
+  if (P < 1 || (P & (P - 1)) || n < 2 || (n & (n - 1)) || n % P || n >= ((int64_t)1 << 40)) {
+    set_error("split FWT/WPT needs a power-of-two length (got %lld) on a power-of-two number of devices (got %d)",
+              (long long)n, P);
+    return JWC_ERR_INVALID;
+  }
+  if (L < 2 || L > 40 || (L & 1)) return JWC_ERR_UNSUPPORTED;
+  const int64_t len = n / P;
+  if (len >= ((int64_t)1 << 31)) return JWC_ERR_UNSUPPORTED;
+  const int steps = steps_forward(n, levels);
+  const int ls = dwt_split_levels(n, P, steps, tree);
+  if (tree && steps > ls) {
+    set_error("split WPT: %d levels would leave packet parts shorter than 1024 samples per device (at most %d here)", steps, ls);
+    return JWC_ERR_UNSUPPORTED;
+  }
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  int rc = JWC_OK;
+  cudaError_t e = cudaSuccess;
+  std::vector<std::unique_ptr<Scratch>> ws;
+  for (int p = 0; p < P; p++) ws.emplace_back(new Scratch(ctx, ctx->slots[p], ctx->slots[p].stream));
+  auto stream = [&](int p) { return ctx->slots[p].stream; };
+  auto setdev = [&](int p) { return cudaSetDevice(ctx->slots[p].ordinal); };
+  auto alloc = [&](int p, int64_t doubles) -> double* {
+    setdev(p);
+    double* q = ws[p]->get((size_t)doubles);
+    if (!q) { set_error("split transform: scratch allocation failed on slot %d", p); rc = JWC_ERR_NOMEM; }
+    return q;
+  };
+
+  // ---- plan of the split levels (on one chunk) ----------------------------------------------------------------------
+  DwtPlan plan;
+  if (ls > 0) {
+    plan = make_plan(ctx, ctx->slots[0], d_in[0], d_out[0], len, ls, L, tree, inverse, len, 3);   // halo <= 7 (L - 2) per pass
+    bool aligned = true;
+    for (int p = 0; p < P; p++)
+      aligned = aligned && ((reinterpret_cast<uintptr_t>(d_in[p]) | reinterpret_cast<uintptr_t>(d_out[p])) & 15) == 0;
+    if (!plan.ok) return JWC_ERR_UNSUPPORTED;
+    if (!aligned) for (DwtPass& ps : plan.passes) ps.mode = DWT_SCALAR;
+  }
+  const int npass = (int)plan.passes.size();
+  std::vector<SplitDev> sd(P);
+  std::vector<cudaEvent_t> tail_ev(P, nullptr);
+  for (int p = 0; p < P && rc == JWC_OK; p++) {
+    setdev(p);
+    sd[p].dev = &ctx->slots[p];
+    sd[p].done.assign(npass, nullptr);
+    for (int i = 0; i < npass; i++)
+      if ((e = cudaEventCreateWithFlags(&sd[p].done[i], cudaEventDisableTiming)) != cudaSuccess) { rc = split_fail("cudaEventCreate", e); break; }
+    if (rc == JWC_OK && (e = cudaEventCreateWithFlags(&tail_ev[p], cudaEventDisableTiming)) != cudaSuccess) rc = split_fail("cudaEventCreate", e);
+  }
+  // copy of `count` doubles from slot q's memory into slot p's memory, issued on slot p's stream
+  auto peer = [&](int p, double* dst, int q, const double* src, int64_t count) {
+    if (rc != JWC_OK || count <= 0) return;
+    setdev(p);
+    e = cudaMemcpyPeerAsync(dst, ctx->slots[p].ordinal, src, ctx->slots[q].ordinal, (size_t)count * sizeof(double), stream(p));
+    if (e != cudaSuccess) rc = split_fail("cudaMemcpyPeerAsync", e);
+  };
+  auto wait_ev = [&](int p, cudaEvent_t ev) {
+    if (rc != JWC_OK || !ev) return;
+    if ((e = cudaStreamWaitEvent(stream(p), ev, 0)) != cudaSuccess) rc = split_fail("cudaStreamWaitEvent", e);
+  };
+  auto record = [&](int p, cudaEvent_t ev) {
+    if (rc != JWC_OK) return;
+    if ((e = cudaEventRecord(ev, stream(p))) != cudaSuccess) rc = split_fail("cudaEventRecord", e);
+  };
+  auto launch = [&](int p, DwtPassArgs& a, const DwtPass& ps) {
+    if (rc != JWC_OK) return;
+    setdev(p);
+    a.N = len; a.l0 = ps.l0; a.k = ps.k; a.T = ps.T; a.cap = ps.cap; a.mode = ps.mode;
+    a.h = len >> ps.l0;
+    a.tiles = (int)((a.h + ps.T - 1) / ps.T);
+    a.nodes = tree ? (1 << ps.l0) : 1;
+    for (int jj = 0; jj < 16; jj++) a.hl[jj] = (int)dwt_inv_halo(L, jj);
+    const int64_t nblocks = (int64_t)a.tiles * a.nodes;
+    a.nblocks = (unsigned)nblocks;
+    a.log_tiles = 0;
+    while ((1 << a.log_tiles) < a.tiles) a.log_tiles++;
+    a.pf_dist = 0;
+    const int r = tree ? (inverse ? dispatch_dwt_pass<true, true>(ctx, stream(p), a, f, L, ps.threads, ps.smem, nblocks)
+                                  : dispatch_dwt_pass<true, false>(ctx, stream(p), a, f, L, ps.threads, ps.smem, nblocks))
+                       : (inverse ? dispatch_dwt_pass<false, true>(ctx, stream(p), a, f, L, ps.threads, ps.smem, nblocks)
+                                  : dispatch_dwt_pass<false, false>(ctx, stream(p), a, f, L, ps.threads, ps.smem, nblocks));
+    if (r != JWC_OK) rc = r;
+  };
+  // ordinary (unsplit) transform of the gathered remainder on slot 0
+  auto whole_on_slot0 = [&](const double* src, double* dst, int64_t m, int lv, bool inv) {
+    if (rc != JWC_OK) return;
+    setdev(0);
+    int r = inv ? fast_dwt_inverse(ctx, ctx->slots[0], stream(0), src, dst, 1, m, lv, f, L, tree)
+                : fast_dwt_forward(ctx, ctx->slots[0], stream(0), src, dst, 1, m, lv, f, L, tree);
+    if (r == JWC_ERR_UNSUPPORTED)
+      r = inv ? generic_dwt_inverse(ctx, ctx->slots[0], stream(0), src, dst, 1, m, lv, f, L, tree, false)
+              : generic_dwt_forward(ctx, ctx->slots[0], stream(0), src, dst, 1, m, lv, f, L, tree, false);
+    if (r != JWC_OK) rc = r;
+  };
+
+  if (steps == 0) {   // zero levels: the transform is a copy
+    for (int p = 0; p < P; p++) peer(p, d_out[p], p, d_in[p], len);
+    for (int p = 0; p < P; p++) { setdev(p); cudaStreamSynchronize(stream(p)); }
+    cudaSetDevice(prev_dev);
+    return rc;
+  }
+  const int64_t tail_len = n >> ls;          // the remainder A_ls (FWT; the whole series when ls == 0)
+  const int64_t tail_part = tail_len / P;    // = len >> ls
+  const int tail_levels = steps - ls;
+
+  if (!inverse) {
+    // ================= forward =================
+    // per pass and device: source (A_{l0} part / node parts) and destinations
+    std::vector<std::vector<const double*>> src(npass + 1, std::vector<const double*>(P, nullptr));
+    std::vector<std::vector<double*>> dst(npass, std::vector<double*>(P, nullptr));    // tree: leaves; pyramid: A_{l0+k}
+    std::vector<std::vector<double*>> hb(npass, std::vector<double*>(P, nullptr));
+    for (int p = 0; p < P && rc == JWC_OK; p++) {
+      src[0][p] = d_in[p];
+      double* tmp = (tree && npass >= 2) ? alloc(p, len) : nullptr;
+      for (int i = 0; i < npass && rc == JWC_OK; i++) {
+        const DwtPass& ps = plan.passes[i];
+        const int64_t H = (int64_t)(L - 2) * ((1 << ps.k) - 1);
+        hb[i][p] = alloc(p, std::max<int64_t>(2, (tree ? ((int64_t)1 << ps.l0) : 1) * H));
+        if (tree) dst[i][p] = (((npass - 1 - i) & 1) == 0) ? d_out[p] : tmp;   // whole-array ping-pong, last pass in d_out
+        else dst[i][p] = (i == npass - 1 && tail_levels == 0) ? d_out[p] : alloc(p, len >> (ps.l0 + ps.k));
+        src[i + 1][p] = dst[i][p];
+      }
+    }
+    for (int i = 0; i < npass && rc == JWC_OK; i++) {
+      const DwtPass& ps = plan.passes[i];
+      const int64_t h = len >> ps.l0, H = (int64_t)(L - 2) * ((1 << ps.k) - 1);
+      const int nodes = tree ? (1 << ps.l0) : 1;
+      for (int p = 0; p < P && rc == JWC_OK; p++) {
+        setdev(p);
+        const int right = (p + 1) % P, left = (p + P - 1) % P;
+        if (i > 0) { wait_ev(p, sd[right].done[i - 1]); wait_ev(p, sd[left].done[i - 1]); }
+        for (int r = 0; r < nodes; r++) peer(p, hb[i][p] + (int64_t)r * H, right, src[i][right] + (int64_t)r * h, H);
+        DwtPassArgs a{};
+        a.in = src[i][p]; a.in_sig = len;
+        a.halo = hb[i][p]; a.halo_stride = H;
+        if (tree) { a.out = dst[i][p]; a.out_sig = len; }
+        else { a.out = d_out[p]; a.out_sig = len; a.aout = dst[i][p]; a.aout_sig = len >> (ps.l0 + ps.k); }
+        launch(p, a, ps);
+        record(p, sd[p].done[i]);
+      }
+    }
+    if (!tree && tail_levels > 0 && rc == JWC_OK) {
+      // gather A_ls on slot 0, finish the pyramid there, hand every slot its piece of the result array
+      double* tin = alloc(0, tail_len);
+      double* tout = alloc(0, tail_len);
+      for (int p = 0; p < P && rc == JWC_OK; p++) {
+        if (npass > 0) wait_ev(0, sd[p].done[npass - 1]);
+        peer(0, tin + (int64_t)p * tail_part, p, src[npass][p], tail_part);
+      }
+      whole_on_slot0(tin, tout, tail_len, tail_levels, false);
+      record(0, tail_ev[0]);
+      for (int p = 0; p < P && rc == JWC_OK; p++) {   // every slot fetches its piece on its own stream
+        wait_ev(p, tail_ev[0]);
+        peer(p, d_out[p], 0, tout + (int64_t)p * tail_part, tail_part);
+      }
+    }
+  } else {
+    // ================= inverse =================
+    // (1) the remainder: pieces T_p -> slot 0, inverse pyramid there, A_ls parts back to their slots
+    std::vector<const double*> asrc(P, nullptr);   // pyramid: A_{deepest split level} part; tree: whole local array
+    if (!tree) {
+      if (tail_levels > 0) {
+        double* tin = alloc(0, tail_len);
+        double* tout = alloc(0, tail_len);
+        for (int p = 0; p < P && rc == JWC_OK; p++) peer(0, tin + (int64_t)p * tail_part, p, d_in[p], tail_part);
+        whole_on_slot0(tin, tout, tail_len, tail_levels, true);
+        record(0, tail_ev[0]);
+        for (int p = 0; p < P && rc == JWC_OK; p++) {   // every slot fetches its A_ls part on its own stream
+          double* ap = (npass == 0) ? d_out[p] : alloc(p, tail_part);
+          wait_ev(p, tail_ev[0]);
+          peer(p, ap, 0, tout + (int64_t)p * tail_part, tail_part);
+          asrc[p] = ap;
+          record(p, tail_ev[p]);   // (slot 0 re-records its own event after its copy: later waits see both)
+        }
+      } else {
+        for (int p = 0; p < P; p++) asrc[p] = d_in[p];   // A_ls part is the head of the local layout
+      }
+    } else {
+      for (int p = 0; p < P; p++) asrc[p] = d_in[p];
+    }
+    // (2) the split passes, deepest first
+    std::vector<double*> tmp(P, nullptr);
+    if (tree && npass >= 2) for (int p = 0; p < P && rc == JWC_OK; p++) tmp[p] = alloc(p, len);
+    for (int i = npass - 1, step = 0; i >= 0 && rc == JWC_OK; --i, ++step) {
+      const DwtPass& ps = plan.passes[i];
+      const int64_t h = len >> ps.l0, hc = h >> ps.k;
+      const int64_t hs = dwt_inv_halo(L, ps.k);       // slot size = left halo of the deepest children
+      const int nodes = tree ? (1 << ps.l0) : 1, leaves = 1 << ps.k;
+      const int slots = tree ? nodes * leaves : ps.k + 1;
+      std::vector<double*> out(P, nullptr), hbuf(P, nullptr);
+      for (int p = 0; p < P && rc == JWC_OK; p++) {
+        hbuf[p] = alloc(p, std::max<int64_t>(2, (int64_t)slots * hs));
+        if (tree) out[p] = ((i & 1) == 0) ? d_out[p] : tmp[p];   // pass 0 (executed last) lands in d_out
+        else out[p] = (i == 0) ? d_out[p] : alloc(p, h);
+      }
+      for (int p = 0; p < P && rc == JWC_OK; p++) {
+        setdev(p);
+        const int right = (p + 1) % P, left = (p + P - 1) % P;
+        if (step > 0) { wait_ev(p, sd[left].done[i + 1]); wait_ev(p, sd[right].done[i + 1]); }
+        else if (!tree && tail_levels > 0) wait_ev(p, tail_ev[left]);   // the left neighbour's A_ls part has arrived
+        if (tree) {
+          for (int r = 0; r < slots; r++)   // child r (node-major): left neighbour's last hs coefficients
+            peer(p, hbuf[p] + (int64_t)r * hs, left, asrc[left] + (int64_t)(r + 1) * hc - hs, hs);
+        } else {
+          peer(p, hbuf[p], left, asrc[left] + hc - hs, hs);                       // slot 0: A_{l0+k}
+          for (int jj = ps.k; jj >= 1; --jj) {                                     // slot 1 + (k - jj): D_{l0+jj}
+            const int64_t hj = dwt_inv_halo(L, jj), part = h >> jj;
+            peer(p, hbuf[p] + (int64_t)(2 + ps.k - jj) * hs - hj, left, d_in[left] + (len >> (ps.l0 + jj)) + part - hj, hj);
+          }
+        }
+        DwtPassArgs a{};
+        a.halo = hbuf[p]; a.halo_stride = hs;
+        if (tree) { a.in = asrc[p]; a.in_sig = len; a.out = out[p]; a.out_sig = len; }
+        else { a.in = d_in[p]; a.in_sig = len; a.ain = asrc[p]; a.ain_sig = hc; a.out = out[p]; a.out_sig = (i == 0) ? len : h; }
+        launch(p, a, ps);
+        record(p, sd[p].done[i]);
+      }
+      for (int p = 0; p < P; p++) asrc[p] = out[p];
+    }
+  }
+  // ---- drain every device, release events and workspace ---------------------------------------------------------------
+  for (int p = 0; p < P; p++) {
+    setdev(p);
+    cudaError_t e2 = cudaStreamSynchronize(stream(p));
+    if (e2 != cudaSuccess && rc == JWC_OK) rc = split_fail("cudaStreamSynchronize", e2);
+    for (cudaEvent_t ev : sd[p].done) if (ev) cudaEventDestroy(ev);
+    if (tail_ev[p]) cudaEventDestroy(tail_ev[p]);
+  }
+  ws.clear();
+  cudaSetDevice(prev_dev);
+  return rc;
 }
 
 }  // namespace jwc

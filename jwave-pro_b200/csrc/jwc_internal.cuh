@@ -252,6 +252,11 @@ int fast_dwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
 int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
                      int64_t batch, int64_t n, int levels, const FilterPair& f, int L, bool tree, int64_t ld = 0);
 
+// one long series split over the context's devices: FWT / WPT (jwc_dwt_fast.cu); chunk p = samples [p n/P, (p+1) n/P)
+int dwt_split_levels(int64_t n, int P, int steps, bool tree);
+int split_dwt(jwc_ctx* ctx, bool inverse, bool tree, const double* const* d_in, double* const* d_out, int64_t n,
+              int levels, const FilterPair& f, int L);
+
 // The dynamic-shared-memory cap of a kernel is per-function state shared by every host thread: setting it to "what this
 // launch needs" races with a concurrent launch of the same instantiation that needs more (found by the concurrent
 // device-call test: cudaErrorInvalidValue at launch).  So every kernel gets the SAME cap once per device: the opt-in

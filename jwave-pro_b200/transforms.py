@@ -274,6 +274,82 @@ class _CudaPyramidBase(WaveletTransform):
                        self._wavelet.getWaveletReConstruction(), flags, stream, slot)
 
 
+    # ---- one long series split over the context's devices (halo exchange between ring neighbours) ------------------
+    def _split(self, direction, src_ptrs, dst_ptrs, n, level):
+        lib = _native.load()
+        self._check(n, level, direction)
+        P = self._context().num_devices()
+        if len(src_ptrs) != P or len(dst_ptrs) != P:
+            raise ValueError("need one chunk pointer per device of the context (%d)" % P)
+        w = self._wavelet
+        f0, f1 = ((w.getScalingDeComposition(), w.getWaveletDeComposition()) if direction == "forward"
+                  else (w.getScalingReConstruction(), w.getWaveletReConstruction()))
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        a = (ctypes.c_void_p * P)(*src_ptrs)
+        b = (ctypes.c_void_p * P)(*dst_ptrs)
+        fn = getattr(lib, "%s_%s_split_dev" % (self._fn, "forward" if direction == "forward" else "inverse"))
+        rc = fn(self._context().handle, a, b, n, level, _ptr(f0), _ptr(f1), len(f0), 0)
+        if rc != 0:
+            raise RuntimeError("split %s failed (%d): %s" % (direction, rc, _native.last_error()))
+
+    def forwardSplitDevice(self, d_in_chunks, d_out_chunks, n, level):
+        """d_in_chunks[p]: device address of x[n*p/P .. n*(p+1)/P) on device slot p; d_out_chunks[p]: n/P doubles in the
+        local layout described in include/jwavecuda.h (splitLayoutToGlobal maps it back to the reference's array)."""
+        self._split("forward", d_in_chunks, d_out_chunks, n, level)
+
+    def reverseSplitDevice(self, d_in_chunks, d_out_chunks, n, level):
+        self._split("reverse", d_in_chunks, d_out_chunks, n, level)
+
+    def splitLevels(self, n, level):
+        """levels of an n-sample transform that run split over this context's devices (the rest is the FWT remainder)"""
+        return int(_native.load().jwc_dwt_split_levels(self._context().handle, n, level))
+
+    def splitLayoutToGlobal(self, chunks, n, level):
+        """Assemble the reference's coefficient array from the per-device chunks of forwardSplitDevice (numpy arrays)."""
+        P = len(chunks)
+        ln = n // P
+        out = np.empty(n)
+        if self._fn == "jwc_wpt":
+            steps = min(level, self.calcExponent(n))
+            part = ln >> steps
+            for c in range(1 << steps):
+                for p in range(P):
+                    out[c * (n >> steps) + p * part:c * (n >> steps) + (p + 1) * part] = chunks[p][c * part:(c + 1) * part]
+            return out
+        ls = self.splitLevels(n, level)
+        tp = ln >> ls
+        for p in range(P):
+            out[p * tp:(p + 1) * tp] = chunks[p][:tp]
+        for l in range(ls, 0, -1):
+            part = ln >> l
+            for p in range(P):
+                out[(n >> l) + p * part:(n >> l) + (p + 1) * part] = chunks[p][part:2 * part]
+        return out
+
+    def globalToSplitLayout(self, coeffs, P, level):
+        """Inverse of splitLayoutToGlobal: the per-device chunks (list of numpy arrays) of a coefficient array."""
+        coeffs = _as_f64(coeffs)
+        n = len(coeffs)
+        ln = n // P
+        chunks = [np.empty(ln) for _ in range(P)]
+        if self._fn == "jwc_wpt":
+            steps = min(level, self.calcExponent(n))
+            part = ln >> steps
+            for c in range(1 << steps):
+                for p in range(P):
+                    chunks[p][c * part:(c + 1) * part] = coeffs[c * (n >> steps) + p * part:c * (n >> steps) + (p + 1) * part]
+            return chunks
+        ls = self.splitLevels(n, level)
+        tp = ln >> ls
+        for p in range(P):
+            chunks[p][:tp] = coeffs[p * tp:(p + 1) * tp]
+        for l in range(ls, 0, -1):
+            part = ln >> l
+            for p in range(P):
+                chunks[p][part:2 * part] = coeffs[(n >> l) + p * part:(n >> l) + (p + 1) * part]
+        return chunks
+
+
 class CudaFastWaveletTransform(_CudaPyramidBase):
     """Drop-in for transforms/FastWaveletTransform.java (same _name, :52)."""
 
