@@ -228,6 +228,15 @@ JWC_API int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, 
 JWC_API int jwc_compress_magnitude_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
                                        int64_t count, double threshold, double* d_magnitude);
 
+/* The sliding-window transform and the thresholding that follows it in the reference's compression path, chained on the
+ * device: coeffs [nwin][levels+1][window] as jwc_modwt_forward_windows_dev writes them, then CompressorMagnitude over ALL
+ * of them, in place.  The sum of |c| is taken in the transform's store epilogue (per-CTA partial sums, fixed reduction
+ * order), so no separate reduction pass reads the coefficients again; *d_magnitude (device memory) receives mean |c|. */
+JWC_API int jwc_modwt_forward_windows_compress_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_series,
+                                                   double* d_coeffs, int64_t series_len, int64_t window, int64_t hop,
+                                                   int levels, const double* g, const double* h, int L, unsigned flags,
+                                                   double threshold, double* d_magnitude);
+
 /* ---- arbitrary-length FWT / WPT: Ancient-Egyptian decomposition -----------------------------------------
  * transforms/AncientEgyptianDecomposition.java:97-181 with tools/MathToolKit.java:57-84 decompose(): a signal of any
  * length n >= 1 is cut into blocks of descending powers of two (42 = 32 | 8 | 2); every block is transformed on its own

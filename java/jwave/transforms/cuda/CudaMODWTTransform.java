@@ -2,6 +2,7 @@ package jwave.transforms.cuda;
 
 import java.lang.foreign.MemorySegment;
 
+import jwave.transforms.EfficientMODWTTransform;
 import jwave.transforms.MODWTTransform;
 import jwave.transforms.wavelets.Wavelet;
 
@@ -89,6 +90,59 @@ public class CudaMODWTTransform extends MODWTTransform {
     for (int r = 0; r <= maxLevel; r++) System.arraycopy(coefficients[r], 0, flat, r * n, n);
     double[][] f = filters();
     return JwcNative.run(JwcNative.MODWT_INVERSE, CudaContext.get(), flat, 1, n, maxLevel, n, f[0], f[1], 0);
+  }
+
+  /**
+   * The result of forwardMODWT in the reference's single-backing-array wire format
+   * ({@link EfficientMODWTTransform.MODWTCoefficients}, EfficientMODWTTransform.java:28-86; level views are
+   * {@link EfficientMODWTTransform.ArrayView}, :88-117): the flat array [W_1 | ... | W_J | V_J] the device writes IS the
+   * backing array, so wrapping a GPU result copies nothing.  Rows carry forwardMODWT's meaning (W_j = h~ conv V_{j-1},
+   * V_J last, MODWTTransform.java:298-303 / flat form :406-416); the reference's forwardMODWTEfficient (:151-170) labels
+   * its two branches the other way round and is covered by none of its tests, so that labelling is not reproduced.
+   */
+  public EfficientMODWTTransform.MODWTCoefficients forwardMODWTCoefficients(double[] data, int maxLevel) {
+    checkLevel(maxLevel);
+    if (data == null || data.length == 0)
+      return new EfficientMODWTTransform.MODWTCoefficients(new double[0], 0, maxLevel);
+    int n = data.length;
+    checkLimit(maxLevel, n);
+    double[][] f = filters();
+    double[] flat = JwcNative.run(JwcNative.MODWT_FORWARD, CudaContext.get(), data, 1, n, maxLevel,
+        (maxLevel + 1) * n, f[0], f[1], 0);
+    return new EfficientMODWTTransform.MODWTCoefficients(flat, n, maxLevel);
+  }
+
+  /**
+   * Inverse of {@link #forwardMODWTCoefficients}.  MODWTCoefficients keeps its backing array private, so the rows are
+   * read through its level views (one copy per row, as a caller of the reference class would have to do) and go to
+   * the device as one flat array.
+   */
+  public double[] inverseMODWTCoefficients(EfficientMODWTTransform.MODWTCoefficients coeffs, int signalLength,
+      int maxLevel) {
+    checkLevel(maxLevel);
+    if (coeffs == null || signalLength == 0) return new double[0];
+    if (coeffs.getTotalSize() != (maxLevel + 1) * signalLength)
+      throw new IllegalArgumentException("backing array length " + coeffs.getTotalSize()
+          + " != (levels + 1) * signalLength");
+    double[] flat = new double[(maxLevel + 1) * signalLength];
+    for (int r = 0; r <= maxLevel; r++) {
+      EfficientMODWTTransform.ArrayView v = coeffs.getView(r + 1);
+      for (int i = 0; i < signalLength; i++) flat[r * signalLength + i] = v.get(i);
+    }
+    double[][] f = filters();
+    return JwcNative.run(JwcNative.MODWT_INVERSE, CudaContext.get(), flat, 1, signalLength, maxLevel, signalLength,
+        f[0], f[1], 0);
+  }
+
+  /** Flat form of the inverse: coeffs = [W_1 | ... | W_J | V_J], the layout of MODWTTransform.forward(double[], level). */
+  public double[] inverseMODWTFlat(double[] flat, int signalLength, int maxLevel) {
+    checkLevel(maxLevel);
+    if (flat == null || signalLength == 0) return new double[0];
+    if (flat.length != (maxLevel + 1) * signalLength)
+      throw new IllegalArgumentException("coefficient array length " + flat.length + " != (levels + 1) * signalLength");
+    double[][] f = filters();
+    return JwcNative.run(JwcNative.MODWT_INVERSE, CudaContext.get(), flat, 1, signalLength, maxLevel, signalLength,
+        f[0], f[1], 0);
   }
 
   /**

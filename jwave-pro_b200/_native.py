@@ -34,7 +34,7 @@ SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal"
            + ["jwc_fwt_forward_split_dev", "jwc_fwt_inverse_split_dev", "jwc_wpt_forward_split_dev",
               "jwc_wpt_inverse_split_dev", "jwc_dwt_split_levels"]
            + ["jwc_modwt_forward_windows", "jwc_modwt_forward_windows_dev", "jwc_compress_magnitude",
-              "jwc_compress_magnitude_dev"]
+              "jwc_compress_magnitude_dev", "jwc_modwt_forward_windows_compress_dev"]
            + ["jwc_diag_dfma_tflops", "jwc_diag_copy_gbs"]
            + ["jwc_" + t for t in _TRANSFORMS_2D] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_2D]
            + ["jwc_" + t for t in _TRANSFORMS_AED] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_AED])
@@ -103,6 +103,9 @@ def load():
         lib.jwc_modwt_forward_windows_dev.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _int, _dp, _dp, _int,
                                                       _u32]
         lib.jwc_modwt_forward_windows_dev.restype = _int
+        lib.jwc_modwt_forward_windows_compress_dev.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _int, _dp, _dp,
+                                                               _int, _u32, ctypes.c_double, _vp]
+        lib.jwc_modwt_forward_windows_compress_dev.restype = _int
         lib.jwc_compress_magnitude.argtypes = [_vp, _vp, _vp, _i64, ctypes.c_double, _dp]
         lib.jwc_compress_magnitude.restype = _int
         lib.jwc_compress_magnitude_dev.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, ctypes.c_double, _vp]

@@ -815,6 +815,50 @@ JWC_API int jwc_modwt_forward_windows_dev(jwc_ctx* ctx, int slot, void* stream, 
                  h, L, flags, d2);
 }
 
+// MODWTSlidingWindowTest.java:20-70 followed by CompressorMagnitude.compress (CompressorMagnitude.java:78-90 +
+// Compressor.java:97-112) over ALL coefficients of all windows: the sum of |c| is taken in the transform's store epilogue
+// (one partial per CTA), so the chain moves (J+1) n written + one read + one write per window, no separate reduction
+// pass.  Shapes the whole-window kernel does not take run the ordinary transform and the separate reduction.
+JWC_API int jwc_modwt_forward_windows_compress_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_series,
+                                                   double* d_coeffs, int64_t series_len, int64_t window, int64_t hop,
+                                                   int levels, const double* g, const double* h, int L, unsigned flags,
+                                                   double threshold, double* d_magnitude) {
+  if (!ctx) { set_error("context is NULL"); return JWC_ERR_INVALID; }
+  JWC_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), "device slot %d out of range", slot);
+  if (window < 1 || hop < 1 || series_len < window) {
+    set_error("need 1 <= window <= series length and hop >= 1 (window %lld, hop %lld, series %lld)", (long long)window,
+              (long long)hop, (long long)series_len);
+    return JWC_ERR_INVALID;
+  }
+  JWC_REQUIRE(d_magnitude != nullptr, "NULL pointer");
+  JWC_REQUIRE(threshold > 0.0, "Compressor - given threshold should be larger than zero!");
+  const int64_t nwin = (series_len - window) / hop + 1;
+  Dim2 d2;
+  d2.hop = hop;
+  int rc = validate(Op::ModwtFwd, d_series, d_coeffs, nwin, window, levels, g, h, L, d2);
+  if (rc != JWC_OK) return rc;
+  FilterPair fp;
+  load_filters(fp, g, h, L);
+  const DeviceSlot& dev = ctx->slots[slot];
+  DeviceGuard guard(dev.ordinal);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", dev.ordinal); return JWC_ERR_CUDA; }
+  cudaStream_t st = stream ? (cudaStream_t)stream : dev.stream;
+  const int64_t count = nwin * (int64_t)(levels + 1) * window;
+  Scratch ws(ctx, dev, st);
+  AbsSum abs;
+  abs.ws = &ws;
+  rc = JWC_ERR_UNSUPPORTED;
+  if (!(flags & (JWC_FLAG_EXACT | JWC_FLAG_FORCE_GENERIC)) && ctx->tune.force_generic == 0)
+    rc = small_modwt_forward(ctx, dev, st, d_series, d_coeffs, nwin, window, levels, fp, L, hop, &abs);
+  if (rc == JWC_ERR_UNSUPPORTED) {
+    rc = run_device(ctx, dev, st, Op::ModwtFwd, d_series, d_coeffs, nwin, window, levels, fp, L, flags, d2);
+    if (rc != JWC_OK) return rc;
+    return compress_magnitude(ctx, dev, st, d_coeffs, d_coeffs, count, threshold, d_magnitude);
+  }
+  if (rc != JWC_OK) return rc;
+  return compress_select_from_parts(ctx, dev, st, d_coeffs, d_coeffs, count, threshold, d_magnitude, abs.parts, abs.nparts);
+}
+
 #define JWC_DEFINE_AED(name, OP)                                                                                    \
   JWC_API int jwc_##name(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t n, const double* f0,   \
                          const double* f1, int L, unsigned flags) {                                                 \

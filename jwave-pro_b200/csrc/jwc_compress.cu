@@ -32,11 +32,11 @@ __global__ void __launch_bounds__(kThreads) abs_sum_partials_kernel(const double
   if (threadIdx.x == 0) parts[blockIdx.x] = red[0];
 }
 
-__global__ void __launch_bounds__(kThreads) magnitude_kernel(const double* __restrict__ parts, int nparts, int64_t count,
+__global__ void __launch_bounds__(kThreads) magnitude_kernel(const double* __restrict__ parts, int64_t nparts, int64_t count,
                                                              double* __restrict__ magnitude) {
   __shared__ double red[kThreads];
   double s = 0.0;
-  for (int i = threadIdx.x; i < nparts; i += kThreads) s += parts[i];
+  for (int64_t i = threadIdx.x; i < nparts; i += kThreads) s += parts[i];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int w = kThreads / 2; w > 0; w >>= 1) {
@@ -75,6 +75,19 @@ int compress_magnitude(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   if (blocks > cap) blocks = cap;
   threshold_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_in, d_out, count, d_mag, threshold);
   count_launch(ctx, 3);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+int compress_select_from_parts(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                               int64_t count, double threshold, double* d_mag, const double* d_parts, int64_t nparts) {
+  if (count <= 0) return JWC_OK;
+  magnitude_kernel<<<1, kThreads, 0, st>>>(d_parts, nparts, count, d_mag);
+  int64_t blocks = (count + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)dev.sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  threshold_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_in, d_out, count, d_mag, threshold);
+  count_launch(ctx, 2);
   JWC_CUDA_CHECK(cudaGetLastError());
   return JWC_OK;
 }

@@ -223,8 +223,16 @@ int tile_dwt_inverse_pass(jwc_ctx* ctx, cudaStream_t st, const double* ain, int6
                           int64_t din_sig, double* out, int64_t out_sig, int64_t N, int l0, int k, int64_t batch,
                           const FilterPair& f, int L);
 // whole-signal-in-shared-memory forward MODWT for short signals / analysis windows (jwc_modwt_small.cu)
+// abs != nullptr: the kernel also leaves sum |coefficient| of each CTA in abs->parts (allocated from abs->ws)
+struct AbsSum {
+  Scratch* ws = nullptr;
+  double* parts = nullptr;
+  int64_t nparts = 0;
+  bool fused = false;
+};
 int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
-                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0);
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig = 0,
+                        AbsSum* abs = nullptr);
 // warp-per-signal deep end of the FWT pyramid for short signals (jwc_dwt_tail.cu)
 constexpr int kDwtTailLen = 512;        // block length at which the tail takes over
 constexpr int64_t kDwtTailMaxN = 16384; // longest signal that uses it
@@ -237,6 +245,10 @@ int dwt_tail_inverse(jwc_ctx* ctx, cudaStream_t st, const double* d_in, int64_t 
 // magnitude thresholding of a coefficient buffer (jwc_compress.cu); d_mag = one device double for the magnitude
 int compress_magnitude(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
                        int64_t count, double threshold, double* d_mag);
+// same, with the sum of |c| already available as `nparts` partial sums in d_parts (fused into the transform's stores):
+// the magnitude is their fixed-order total / count, then ONE select pass
+int compress_select_from_parts(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_in, double* d_out,
+                               int64_t count, double threshold, double* d_mag, const double* d_parts, int64_t nparts);
 
 // column passes of the 2-D FWT / WPT (jwc_dwt2d.cu); d_src / d_in must not overlap the destination
 int dwt2d_column_steps(int64_t rows, int levels);

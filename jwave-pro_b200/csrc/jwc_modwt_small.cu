@@ -24,6 +24,7 @@ struct SmallArgs {
   int64_t batch;
   int n, J, L;
   int per_cta;       // signals per CTA
+  double* abs_parts; // fused magnitude: sum |coefficient| over everything this CTA writes goes to abs_parts[blockIdx.x]
 };
 
 constexpr int kChain = 5;   // outputs per work item of the register-blocked path; ODD: chains start 5 strides apart, so a
@@ -34,10 +35,14 @@ constexpr int kChain = 5;   // outputs per work item of the register-blocked pat
 // Register-blocked path (LT > 0, n divisible by the stride): a thread produces the kChain outputs
 // t0, t0 + s, ..., t0 + (kChain-1) s, which share their inputs -- kChain + L - 1 shared-memory loads instead of
 // kChain * L.  Other shapes (any n, any L) take the one-output-at-a-time loop.
-template <int LT>
+// ABS: the magnitude sum of compressions/CompressorMagnitude.java:78-90 (sum of |c| over all coefficients) is taken in
+// the store epilogue -- every W_j[t] and the final V_J[t] adds its absolute value to a per-thread sum as it leaves the
+// registers -- so the thresholding that follows needs one select pass only (no extra read of the coefficients).
+template <int LT, bool ABS = false>
 __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_constant__ SmallArgs a,
                                                                    const __grid_constant__ FilterPair f) {
   extern __shared__ double sm[];
+  double asum = 0.0;
   const int tps = kThreads / a.per_cta;            // threads per signal
   const int s_local = threadIdx.x / tps, r = threadIdx.x % tps;
   const int64_t sig = (int64_t)blockIdx.x * a.per_cta + s_local;
@@ -94,7 +99,8 @@ __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_
               if (b0 + q < per_class) {
                 const int t = t0 + q * step;
                 w_row[t] = aw[q];
-                if (last) v_row[t] = av[q];
+                if (ABS) asum += fabs(aw[q]);
+                if (last) { v_row[t] = av[q]; if (ABS) asum += fabs(av[q]); }
                 else nxt[t] = av[q];
               }
             }
@@ -114,13 +120,26 @@ __global__ void __launch_bounds__(kThreads) modwt_small_fwd_kernel(const __grid_
             if (idx < 0) idx += n;
           }
           w_row[t] = sw;
-          if (last) v_row[t] = sv;
+          if (ABS) asum += fabs(sw);
+          if (last) { v_row[t] = sv; if (ABS) asum += fabs(sv); }
           else nxt[t] = sv;
         }
       }
     }
     __syncthreads();
     double* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (ABS) {   // fixed-shape reduction: lanes, then the four warps -> abs_parts[blockIdx.x] (no atomics: deterministic)
+    __shared__ double red[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) asum += __shfl_down_sync(0xffffffffu, asum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = asum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kThreads / 32; w++) tot += red[w];
+      a.abs_parts[blockIdx.x] = tot;
+    }
   }
 }
 
@@ -218,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) modwt_small_inv_kernel(const __grid_
 
 // Returns JWC_ERR_UNSUPPORTED when the shape is not one this kernel is meant for.
 int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const double* d_x, double* d_coeffs,
-                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig) {
+                        int64_t batch, int64_t n, int levels, const FilterPair& f, int L, int64_t x_sig, AbsSum* abs) {
   (void)dev;
   if (x_sig <= 0) x_sig = n;
   const int mode = ctx->tune.modwt_small;
@@ -232,12 +251,26 @@ int small_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, co
   const int64_t ctas = (batch + a.per_cta - 1) / a.per_cta;
   if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
   const size_t smem = (size_t)a.per_cta * 2 * (size_t)n * sizeof(double);
+  if (abs) {   // magnitude sum fused into the stores: one partial per CTA
+    abs->parts = abs->ws->get((size_t)ctas);
+    if (!abs->parts) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+    abs->nparts = ctas;
+    abs->fused = true;
+    a.abs_parts = abs->parts;
+  }
   switch (L) {
-#define JWC_SCASE(LL) case LL: modwt_small_fwd_kernel<LL><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+#define JWC_SCASE(LL)                                                                          \
+  case LL:                                                                                     \
+    if (abs) modwt_small_fwd_kernel<LL, true><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);   \
+    else modwt_small_fwd_kernel<LL, false><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);      \
+    break;
     JWC_SCASE(2) JWC_SCASE(4) JWC_SCASE(6) JWC_SCASE(8) JWC_SCASE(10) JWC_SCASE(12) JWC_SCASE(14) JWC_SCASE(16)
     JWC_SCASE(18) JWC_SCASE(20)
 #undef JWC_SCASE
-    default: modwt_small_fwd_kernel<0><<<(unsigned)ctas, kThreads, smem, st>>>(a, f); break;
+    default:
+      if (abs) modwt_small_fwd_kernel<0, true><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);
+      else modwt_small_fwd_kernel<0, false><<<(unsigned)ctas, kThreads, smem, st>>>(a, f);
+      break;
   }
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());

@@ -651,6 +651,23 @@ class CudaMODWTTransform(WaveletTransform):
             raise RuntimeError("jwc_modwt_forward_windows failed (%d): %s" % (rc, _native.last_error()))
         return out
 
+    def forwardMODWTWindowsCompressDevice(self, d_series, d_coeffs, series_len, window, hop, maxLevel, threshold,
+                                          d_magnitude, stream=0, flags=0, slot=0):
+        """The reference's compression chain on device buffers: forwardMODWT of every window (as forwardMODWTWindows),
+        then CompressorMagnitude(threshold).compress over all coefficients, in place in d_coeffs
+        ([nwin][maxLevel+1][window]); the sum of |c| is taken in the transform's store epilogue, mean |c| lands in the
+        device double d_magnitude.  Arguments are raw device addresses."""
+        self._check_levels(maxLevel, window)
+        g, h = self._filters()
+        lib = _native.load()
+        g, h = _as_f64(g), _as_f64(h)
+        rc = lib.jwc_modwt_forward_windows_compress_dev(
+            self._context().handle, slot, ctypes.c_void_p(stream if stream else 1), ctypes.c_void_p(d_series),
+            ctypes.c_void_p(d_coeffs), series_len, window, hop, maxLevel, _ptr(g), _ptr(h), len(g), flags,
+            float(threshold), ctypes.c_void_p(d_magnitude))
+        if rc != 0:
+            raise RuntimeError("jwc_modwt_forward_windows_compress_dev failed (%d): %s" % (rc, _native.last_error()))
+
     def forwardMODWTCoefficients(self, data, maxLevel, flags=0):
         """The result of forwardMODWT in the MODWTCoefficients wire format (one backing array, level views).  Rows
         carry forwardMODWT's meaning (W_j = h~ conv V, V_J last); the reference's forwardMODWTEfficient

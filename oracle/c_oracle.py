@@ -173,6 +173,18 @@ def parallel_wpt(x, level, f0, f1, reverse=False, nthreads=1):
     return out
 
 
+def compress_magnitude(x, threshold=1.0):
+    """CompressorMagnitude.compress (CompressorMagnitude.java:78-139 + Compressor.java:97-170) on an array of any rank:
+    returns (compressed array, magnitude)."""
+    x = _c(x)
+    out = np.empty_like(x)
+    fn = lib().jwo_compress_magnitude
+    fn.argtypes = [_dp, ctypes.c_int64, ctypes.c_double, _dp]
+    fn.restype = ctypes.c_double
+    mag = fn(_p(x), x.size, float(threshold), _p(out))
+    return out, float(mag)
+
+
 def batch2d(kind, x, lvl_m, lvl_n, f0, f1, reverse=False, nthreads=1):
     """2-D FWT / WPT of every matrix of x (batch, rows, cols), composed from the 1-D oracle exactly as the reference
     composes it: transforms/BasicTransform.java:361-399 (forward: every row with lvl_n, then every column of the result

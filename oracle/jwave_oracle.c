@@ -608,3 +608,17 @@ JWO_API int jwo_parallel_wpt(const double* in, double* out, int64_t batch, int N
   free(th); free(ib); free(ob); free(pl.leaves);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * compressions/CompressorMagnitude.java:78-90 (compress(double[]): magnitude = left-to-right sum of |c| / length;
+ * the double[][] :97-113 and double[][][] :120-139 overloads run the same sum in row-major order, which is this loop
+ * on the flattened array) + compressions/Compressor.java:97-112 (keep c where |c| >= magnitude * threshold, else 0).
+ * Returns the magnitude.
+ * ---------------------------------------------------------------------------------------- */
+JWO_API double jwo_compress_magnitude(const double* in, int64_t count, double threshold, double* out) {
+  double magnitude = 0.0;
+  for (int64_t i = 0; i < count; i++) magnitude += fabs(in[i]);
+  magnitude /= (double)count;
+  for (int64_t i = 0; i < count; i++) out[i] = (fabs(in[i]) >= magnitude * threshold) ? in[i] : 0.0;
+  return magnitude;
+}

@@ -499,6 +499,38 @@ def test_fwt_wpt_single_series_split_over_devices(jw, oracle, kind, cls, n, lvl)
     ctx.close()
 
 
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+def test_2d_device_buffers_aligned_to_8_bytes_only(jw, gpu_ctx, kind):
+    """Device pointers at an odd element offset (16-byte alignment lost): the fused column launches stage rows with
+    16-byte cp.async, and the packet transform's ping-pong reads the caller's OUTPUT buffer from the second launch on,
+    so both pointers decide whether the fused launches may run (round-1 advice: only the input was checked)."""
+    import torch
+    B, rows, cols, lm, ln = 2, 512, 256, 6, 4     # deep column pass: three or more column launches
+    w = jw.wavelets.Symlet8()
+    t = (jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform)(w)
+    x = torch.from_numpy(splitmix_uniform(77, (B * rows * cols,))).cuda()
+    ref = torch.empty_like(x)
+    t.forward2DDevice(x.data_ptr(), ref.data_ptr(), B, rows, cols, lm, ln)
+    back_ref = torch.empty_like(x)
+    t.reverse2DDevice(ref.data_ptr(), back_ref.data_ptr(), B, rows, cols, lm, ln)
+    for in_off, out_off in ((1, 0), (0, 1), (1, 1)):
+        xi = torch.empty(x.numel() + 2, dtype=torch.float64, device="cuda")
+        yo = torch.full((x.numel() + 2,), 7.0, dtype=torch.float64, device="cuda")
+        xi[in_off:in_off + x.numel()] = x
+        assert xi[in_off:].data_ptr() % 16 == (8 if in_off else 0)
+        t.forward2DDevice(xi[in_off:].data_ptr(), yo[out_off:].data_ptr(), B, rows, cols, lm, ln)
+        torch.cuda.synchronize()
+        got = yo[out_off:out_off + x.numel()]
+        assert float((got - ref).abs().max()) <= 1e-12
+        zi = torch.empty(x.numel() + 2, dtype=torch.float64, device="cuda")
+        zi[in_off:in_off + x.numel()] = ref
+        zo = torch.empty(x.numel() + 2, dtype=torch.float64, device="cuda")
+        t.reverse2DDevice(zi[in_off:].data_ptr(), zo[out_off:].data_ptr(), B, rows, cols, lm, ln)
+        torch.cuda.synchronize()
+        assert float((zo[out_off:out_off + x.numel()] - back_ref).abs().max()) <= 1e-12
+        assert float((back_ref - x).abs().max()) <= 1e-10
+
+
 def test_split_wpt_declines_too_many_levels(jw):
     import torch
     devs = [i % torch.cuda.device_count() for i in range(2)]
@@ -665,16 +697,20 @@ def test_modwt_sliding_windows(jw, oracle, cls, total, window, hop, J):
 
 @pytest.mark.parametrize("shape,thr", [((1000,), 1.0), ((64, 513), 0.5), ((3, 7, 4096), 2.0), ((1,), 1.0),
                                        ((5_000_000,), 1.3)])
-def test_compressor_magnitude(jw, gpu_ctx, shape, thr):
-    """CompressorMagnitude.java:78-140 + Compressor.java:97-110: keep |c| >= mean|c| * threshold, zero the rest."""
+def test_compressor_magnitude(jw, gpu_ctx, oracle, shape, thr):
+    """CompressorMagnitude.java:78-140 + Compressor.java:97-110: keep |c| >= mean|c| * threshold, zero the rest.
+    Checked against the oracle's restatement (left-to-right sum, like the JVM): the device sum is a fixed-shape tree, so
+    the magnitude agrees to O(1e-16) relative and the select can only differ for values within that of the cut."""
     x = splitmix_uniform(17 + len(shape), shape) * 3.0
     c = jw.CompressorMagnitude(thr)
     y = c.compress(x)
-    mag = float(np.mean(np.abs(x)))
+    exp, mag = oracle.compress_magnitude(x, thr)
     assert abs(c.getMagnitude() - mag) <= 1e-13 * mag
     cut = mag * thr
-    sure = np.abs(np.abs(x) - cut) > 1e-12 * max(cut, 1.0)     # the summation order differs from the JVM's by O(1e-16)
-    exp = np.where(np.abs(x) >= cut, x, 0.0)
+    differ = y != exp
+    assert np.all(np.abs(np.abs(x[differ]) - cut) <= 1e-13 * max(cut, 1.0))
+    assert np.count_nonzero(differ) <= 2
+    sure = np.abs(np.abs(x) - cut) > 1e-12 * max(cut, 1.0)
     assert np.array_equal(y[sure], exp[sure])
     assert np.all((y == x) | (y == 0.0))
     assert c.calcCompressionRate(y) == pytest.approx(100.0 * np.count_nonzero(y == 0.0) / y.size)
@@ -715,6 +751,38 @@ def test_windows_then_compressor_on_device(jw, gpu_ctx, oracle):
     y = dc.cpu().numpy()
     sure = np.abs(np.abs(ref) - mag) > 1e-9
     assert np.array_equal(y[sure] != 0.0, (np.abs(ref) >= mag)[sure])
+
+
+@pytest.mark.parametrize("cls,window,hop,J,thr", [("Daubechies4", 512, 64, 8, 1.0), ("Haar1", 256, 32, 5, 0.5),
+                                                  ("Symlet8", 1024, 100, 4, 2.0), ("Daubechies4", 4096, 512, 6, 1.0)])
+def test_windows_compress_fused(jw, gpu_ctx, oracle, cls, window, hop, J, thr):
+    """SURVEY 8f row 4 as worded: the thresholding fused into the transform's store.  jwc_modwt_forward_windows_compress_dev
+    = window transform with sum |c| taken in the store epilogue + ONE select pass, against the oracle chain
+    (forwardMODWT per window, then the CompressorMagnitude restatement over all coefficients).  The last shape is one the
+    whole-window kernel declines (tile kernels + separate reduction): same result."""
+    import torch
+    w = jw.wavelets.create(cls)
+    t = jw.CudaMODWTTransform(w)
+    total = 40 * hop + window
+    x = chirp(1, total)[0] + 0.1 * splitmix_uniform(5, (total,))
+    nwin = (total - window) // hop + 1
+    dx = torch.from_numpy(x).cuda()
+    dc = torch.empty((nwin, J + 1, window), dtype=torch.float64, device="cuda")
+    dm = torch.zeros(1, dtype=torch.float64, device="cuda")
+    t.forwardMODWTWindowsCompressDevice(dx.data_ptr(), dc.data_ptr(), total, window, hop, J, thr, dm.data_ptr(),
+                                        stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    wins = np.ascontiguousarray(np.lib.stride_tricks.sliding_window_view(x, window)[::hop][:nwin])
+    ref, _ = _modwt_oracle(oracle, w, wins, J)
+    exp, mag = oracle.compress_magnitude(ref, thr)
+    assert abs(float(dm.item()) - mag) <= 1e-12 * mag
+    y = dc.cpu().numpy()
+    cut = mag * thr
+    sure = np.abs(np.abs(ref) - cut) > 1e-9
+    assert np.array_equal(y[sure] != 0.0, (exp != 0.0)[sure])
+    kept = sure & (exp != 0.0)
+    assert _maxerr(y[kept], exp[kept], x) <= TOL
+    assert 0 < np.count_nonzero(y == 0.0) < y.size
 
 
 @pytest.mark.parametrize("cls,n,lvl,batch,force", [
