@@ -19,6 +19,7 @@
  */
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -196,7 +197,7 @@ JWO_API int jwo_modwt_inverse(const double* coeffs, int N, int J, const double* 
 /* ------------------------------------------------------------------------------------------
  * FFT circular convolution -- the reference's DEFAULT (AUTO) MODWT path, used only as the timed
  * CPU baseline (it is 1.6e-12 away from exact at N = 65536).
- * Power-of-two lengths only (Bluestein, FastFourierTransform.java:259-324, is not restated).
+ * Power-of-two lengths run Cooley-Tukey, every other length Bluestein's chirp-z (FastFourierTransform.java:153-163).
  * ---------------------------------------------------------------------------------------- */
 
 /* transforms/FastFourierTransform.java:172-212 (fftCooleyTukey): bit reversal, radix-2 DIT,
@@ -248,6 +249,79 @@ static void fft_cooley_tukey(double* re, double* im, int n, int inverse) {
   }
 }
 
+/* transforms/FastFourierTransform.java:218-244 (fftCooleyTukeyInternal): the same butterflies, never normalised */
+static void fft_cooley_tukey_internal(double* re, double* im, int n, int inverse) {
+  fft_cooley_tukey(re, im, n, inverse);
+  if (inverse) {   // undo the 1/n of fft_cooley_tukey: multiply back (n is a power of two, so this is exact)
+    for (int i = 0; i < n; i++) {
+      re[i] = re[i] * (double)n;
+      im[i] = im[i] * (double)n;
+    }
+  }
+}
+
+/* transforms/FastFourierTransform.java:259-324 (fftBluestein): chirp z-transform for arbitrary n through two forward
+ * and one inverse power-of-two FFT of length m >= 2n - 1.  Complex products as datatypes/natives/Complex.java. */
+static void fft_bluestein(double* xr, double* xi, int n, int inverse) {
+  int m = 1;
+  while (m < 2 * n - 1) m *= 2;
+  double* cr = (double*)calloc(2 * (size_t)n, sizeof(double));
+  double* ci = cr + n;
+  double* ar = (double*)calloc(4 * (size_t)m, sizeof(double));
+  double* ai = ar + m;
+  double* br = ai + m;
+  double* bi = br + m;
+  for (int i = 0; i < n; i++) {
+    double angle = M_PI * i * i / n * (inverse ? 1 : -1);   /* ((pi * i) * i) / n, all in double as in Java */
+    cr[i] = cos(angle);
+    ci[i] = sin(angle);
+  }
+  for (int i = 0; i < n; i++) {                              /* a = x * chirp */
+    ar[i] = xr[i] * cr[i] - xi[i] * ci[i];
+    ai[i] = xr[i] * ci[i] + xi[i] * cr[i];
+  }
+  br[0] = cr[0];
+  bi[0] = -ci[0];
+  for (int i = 1; i < n; i++) {                              /* b = conjugate chirp, mirrored */
+    br[i] = cr[i];       bi[i] = -ci[i];
+    br[m - i] = cr[i];   bi[m - i] = -ci[i];
+  }
+  fft_cooley_tukey_internal(ar, ai, m, 0);
+  fft_cooley_tukey_internal(br, bi, m, 0);
+  for (int i = 0; i < m; i++) {
+    double pr = ar[i] * br[i] - ai[i] * bi[i];
+    double pi = ar[i] * bi[i] + ai[i] * br[i];
+    ar[i] = pr;
+    ai[i] = pi;
+  }
+  fft_cooley_tukey_internal(ar, ai, m, 1);
+  double sm = 1.0 / m;
+  for (int i = 0; i < m; i++) {
+    ar[i] = ar[i] * sm;
+    ai[i] = ai[i] * sm;
+  }
+  for (int i = 0; i < n; i++) {
+    double rr = ar[i] * cr[i] - ai[i] * ci[i];
+    double ri = ar[i] * ci[i] + ai[i] * cr[i];
+    if (inverse) {
+      double sn = 1.0 / n;
+      rr = rr * sn;
+      ri = ri * sn;
+    }
+    xr[i] = rr;
+    xi[i] = ri;
+  }
+  free(cr);
+  free(ar);
+}
+
+/* FastFourierTransform.java:153-163 / :130-142: Cooley-Tukey for 2^p, Bluestein otherwise */
+static void fft_any(double* re, double* im, int n, int inverse) {
+  if (n <= 1) return;
+  if ((n & (n - 1)) == 0) fft_cooley_tukey(re, im, n, inverse);
+  else fft_bluestein(re, im, n, inverse);
+}
+
 /* transforms/MODWTTransform.java:729-741 (wrapFilterToSignalLength), :752-786 (circularConvolveFFT),
  * :798-837 (circularConvolveFFTAdjoint, conjugates the filter spectrum).  ws = 4*N doubles. */
 static void conv_fft(const double* x, int N, const double* f, int M, int adjoint, double* out, double* ws) {
@@ -262,8 +336,8 @@ static void conv_fft(const double* x, int N, const double* f, int M, int adjoint
     fi[i] = 0.0;
   }
   for (int i = 0; i < M; i++) fr[i % N] += f[i];
-  fft_cooley_tukey(sr, si, N, 0);
-  fft_cooley_tukey(fr, fi, N, 0);
+  fft_any(sr, si, N, 0);
+  fft_any(fr, fi, N, 0);
   for (int i = 0; i < N; i++) {
     double br = fr[i], bi = adjoint ? -fi[i] : fi[i];
     double pr = sr[i] * br - si[i] * bi;
@@ -271,12 +345,12 @@ static void conv_fft(const double* x, int N, const double* f, int M, int adjoint
     sr[i] = pr;
     si[i] = pi;
   }
-  fft_cooley_tukey(sr, si, N, 1);
+  fft_any(sr, si, N, 1);
   for (int i = 0; i < N; i++) out[i] = sr[i];
 }
 
 JWO_API int jwo_modwt_forward_fft(const double* x, int N, int J, const double* g, const double* h, int L, double* out) {
-  if (N <= 0 || (N & (N - 1)) != 0 || J < 1) return -1;
+  if (N <= 0 || J < 1) return -1;
   size_t maxM = (size_t)(L - 1) * ((size_t)1 << (J - 1)) + 1;
   double* v = (double*)malloc(sizeof(double) * (size_t)N);
   double* vn = (double*)malloc(sizeof(double) * (size_t)N);
@@ -299,7 +373,7 @@ JWO_API int jwo_modwt_forward_fft(const double* x, int N, int J, const double* g
 }
 
 JWO_API int jwo_modwt_inverse_fft(const double* coeffs, int N, int J, const double* g, const double* h, int L, double* x) {
-  if (N <= 0 || (N & (N - 1)) != 0 || J < 1) return -1;
+  if (N <= 0 || J < 1) return -1;
   size_t maxM = (size_t)(L - 1) * ((size_t)1 << (J - 1)) + 1;
   double* v = (double*)malloc(sizeof(double) * (size_t)N);
   double* a = (double*)malloc(sizeof(double) * (size_t)N);
@@ -504,8 +578,24 @@ JWO_API int jwo_batch(int op, const double* in, double* out, int64_t batch, int 
  * (fork / join).  Signals of a batch go through one after the other, exactly as a caller looping over
  * ParallelWaveletPacketTransform.forward would run them.
  * ---------------------------------------------------------------------------------------- */
+/* fork / join of a level: a sense-reversing spin barrier (ForkJoinPool workers spin before they park; a futex-based
+ * pthread_barrier costs tens of microseconds per level on a 16-thread VM, several times the work of a level) */
+typedef struct { int count, gen, n; } jwo_spin_barrier;
+static void jwo_spin_init(jwo_spin_barrier* b, int n) { b->count = 0; b->gen = 0; b->n = n; }
+static void jwo_spin_wait(jwo_spin_barrier* b) {
+  const int gen = __atomic_load_n(&b->gen, __ATOMIC_ACQUIRE);
+  if (__atomic_add_fetch(&b->count, 1, __ATOMIC_ACQ_REL) == b->n) {
+    __atomic_store_n(&b->count, 0, __ATOMIC_RELAXED);
+    __atomic_store_n(&b->gen, gen + 1, __ATOMIC_RELEASE);
+  } else {
+    int spins = 0;
+    while (__atomic_load_n(&b->gen, __ATOMIC_ACQUIRE) == gen)
+      if (++spins > 20000) { sched_yield(); spins = 0; }
+  }
+}
+
 typedef struct {
-  pthread_barrier_t start, done;
+  jwo_spin_barrier start, done;
   int nthreads, stop;
   /* the level in flight */
   double* data;
@@ -541,10 +631,10 @@ static void* jwo_pwpt_worker(void* a) {
   double* ib = (double*)malloc(sizeof(double) * (size_t)arg->N);
   double* ob = (double*)malloc(sizeof(double) * (size_t)arg->N);
   for (;;) {
-    pthread_barrier_wait(&pl->start);
+    jwo_spin_wait(&pl->start);
     if (pl->stop) break;
     jwo_pwpt_drain(pl, ib, ob);
-    pthread_barrier_wait(&pl->done);
+    jwo_spin_wait(&pl->done);
   }
   free(ib);
   free(ob);
@@ -572,8 +662,8 @@ JWO_API int jwo_parallel_wpt(const double* in, double* out, int64_t batch, int N
   pl.nthreads = nthreads;
   pl.f0 = f0; pl.f1 = f1; pl.L = L; pl.forward = !reverse;
   pl.leaves = (int (*)[2])malloc(sizeof(int[2]) * (size_t)(N / 2 + 1));
-  pthread_barrier_init(&pl.start, NULL, (unsigned)nthreads);
-  pthread_barrier_init(&pl.done, NULL, (unsigned)nthreads);
+  jwo_spin_init(&pl.start, nthreads);
+  jwo_spin_init(&pl.done, nthreads);
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
   jwo_pwpt_arg arg = {&pl, N};
   for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, jwo_pwpt_worker, &arg);
@@ -591,9 +681,9 @@ JWO_API int jwo_parallel_wpt(const double* in, double* out, int64_t batch, int N
       if (h >= 64 && packets >= 8) {          /* shouldUseParallel :155-158 */
         pl.data = d; pl.h = (int)h; pl.nleaves = 0; pl.next = 0;
         jwo_pwpt_split(0, packets, pl.leaves, &pl.nleaves);
-        if (nthreads > 1) pthread_barrier_wait(&pl.start);   /* fork */
+        if (nthreads > 1) jwo_spin_wait(&pl.start);   /* fork */
         jwo_pwpt_drain(&pl, ib, ob);
-        if (nthreads > 1) pthread_barrier_wait(&pl.done);    /* join (invoke returns) */
+        if (nthreads > 1) jwo_spin_wait(&pl.done);    /* join (invoke returns) */
       } else {
         for (int p = 0; p < packets; p++) jwo_pwpt_packet(d, (int)h, p, f0, f1, L, !reverse, ib, ob);   /* :163-184 */
       }
@@ -601,10 +691,8 @@ JWO_API int jwo_parallel_wpt(const double* in, double* out, int64_t batch, int N
     }
   }
   pl.stop = 1;
-  if (nthreads > 1) pthread_barrier_wait(&pl.start);
+  if (nthreads > 1) jwo_spin_wait(&pl.start);
   for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
-  pthread_barrier_destroy(&pl.start);
-  pthread_barrier_destroy(&pl.done);
   free(th); free(ib); free(ob); free(pl.leaves);
   return 0;
 }

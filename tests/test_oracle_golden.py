@@ -257,3 +257,20 @@ def test_compressor_magnitude_restatement(oracle, jw):
     comp, m = oracle.compress_magnitude(c, 1.0)
     assert m == np.add.reduce(np.abs(c)) / 16 or abs(m - np.mean(np.abs(c))) < 1e-15
     assert np.all((comp == c) | (comp == 0.0)) and np.array_equal(comp != 0.0, np.abs(c) >= m)
+
+
+@pytest.mark.parametrize("n", [100, 1000, 777, 96, 31, 3])
+def test_fft_path_on_non_power_of_two_lengths(oracle, jw, n):
+    """MODWTInverseTest.java:20-92 runs the reference's default (FFT) MODWT on lengths that are not 2^p: those go
+    through Bluestein's chirp-z (FastFourierTransform.java:259-324).  The restated FFT path must agree with the direct
+    convolution and reconstruct the signal to that test's 1e-10."""
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1.0, 1.0, n)
+    for cls in ("Haar1", "Daubechies4"):
+        w = jw.wavelets.create(cls)
+        g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+        J = max(1, min(4, int(np.log2(n)) - 1))
+        a = oracle.modwt_forward(x, J, g, h)
+        b = oracle.modwt_forward(x, J, g, h, fft=True)
+        np.testing.assert_allclose(b, a, atol=1e-10)
+        np.testing.assert_allclose(oracle.modwt_inverse(b, g, h, fft=True), x, atol=1e-10)
