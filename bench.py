@@ -697,6 +697,7 @@ def main():
 
     clock = ClockSampler(devices[0]) if (rank == 0 and not os.environ.get("JWC_NO_CLOCK_SAMPLER")) else None
     peak, peak_src = measured_peak()
+    fp64_peak_cold = ctx.dfma_tflops()   # fp64 FMA rate of this device before anything has heated it (burst clocks)
 
     # ---- headline workload, device-resident ---------------------------------------------------------------------------
     run = DeviceRun(jw, torch, ctx, devices, rank, args.workload, batch_override=args.batch, flags=args.flags)
@@ -705,7 +706,10 @@ def main():
     unit = run.unit
     samples_per_step = 2.0 * run.batch * unit * n_gpus
     value = samples_per_step / (res["ms_per_step"] * 1e-3) / 1e9
-    fp64_peak = ctx.dfma_tflops()   # fp64 FMA rate of this device, measured now with the library's own kernel
+    # fp64 FMA rate of this device measured with the library's own kernel, before the run (burst clocks) and right
+    # after it (under the power cap the timed steps ran at); fractions are quoted against the LARGER of the two
+    fp64_peak_after = ctx.dfma_tflops()
+    fp64_peak = max(fp64_peak_cold, fp64_peak_after)
     fr = run.fractions(res, peak, fp64_peak)
 
     # ---- roofline of the dominant kernel = the longer direction of a step ------------------------------------------
@@ -730,6 +734,7 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": names[dom], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fr[dom]["algorithmic_bytes"], "avg_ms": fr[dom]["ms"],
                 "fp64_frac": fr[dom]["fp64_frac"], "fp64_peak_tflops_measured_in_run": fp64_peak,
+                "fp64_peak_tflops_before_and_after_timed_region": [fp64_peak_cold, fp64_peak_after],
                 "other_direction": {"kernel": names[oth], "achieved": fr[oth]["gbs"], "frac": fr[oth]["hbm_frac"],
                                     "avg_ms": fr[oth]["ms"], "fp64_frac": fr[oth]["fp64_frac"]}}
 
