@@ -622,6 +622,7 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "dwt_tile_inv")) return &t.dwt_tile_inv;
   if (!strcmp(key, "wpt2d_fuse")) return &t.wpt2d_fuse;
   if (!strcmp(key, "modwt_small")) return &t.modwt_small;
+  if (!strcmp(key, "small_per_cta")) return &t.small_per_cta;
   if (!strcmp(key, "force_generic")) return &t.force_generic;
   if (!strcmp(key, "l2_prefetch")) return &t.l2_prefetch;
   return nullptr;

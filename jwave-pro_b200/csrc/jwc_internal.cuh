@@ -62,6 +62,7 @@ struct Tuning {
   int dwt_smem = 0;
   int dwt_qmf = 0;          // -1 = never use the register-resident-taps (QMF) kernel variants
   int h2d_chunk_mb = 0;     // host pipeline chunk, 0 = auto
+  int small_per_cta = 0;    // signals per CTA of the whole-signal MODWT kernels: 0 = auto (4 / 2 / 1 by length), else 1, 2 or 4
   int modwt_small = 0;      // whole-signal forward MODWT kernel for n <= 2048: 0 = auto, -1 = off, 1 = whenever it fits
   int wpt2d_fuse = 0;       // two column levels per launch in the 2-D packet transform (forward): 0 = auto, -1 = off
   int dwt_tile_inv = 0;     // tiled in-place kernel for the pyramid-inverse passes of long signals: 1 = on (default off: slower)
