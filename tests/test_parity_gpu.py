@@ -531,6 +531,14 @@ def test_2d_device_buffers_aligned_to_8_bytes_only(jw, gpu_ctx, kind):
         assert float((back_ref - x).abs().max()) <= 1e-10
 
 
+def test_diagnostic_rooflines(jw, gpu_ctx):
+    """jwc_diag_dfma_tflops / jwc_diag_copy_gbs: the in-run denominators of bench.py's fp64_frac / copy ceiling."""
+    tf = gpu_ctx.dfma_tflops()
+    gb = gpu_ctx.copy_gbs(1 << 28)
+    assert 10.0 < tf < 60.0, tf        # B200: ~31-34 TFLOP/s fp64 FMA
+    assert 1000.0 < gb < 9000.0, gb    # B200: ~6 TB/s read + write
+
+
 def test_split_wpt_declines_too_many_levels(jw):
     import torch
     devs = [i % torch.cuda.device_count() for i in range(2)]
