@@ -531,6 +531,31 @@ def test_2d_device_buffers_aligned_to_8_bytes_only(jw, gpu_ctx, kind):
         assert float((back_ref - x).abs().max()) <= 1e-10
 
 
+def test_many_short_lived_streams_do_not_pile_up_workspace(jw, oracle):
+    """Workspace arenas are keyed by (device, caller stream); callers that come with ever new streams made them grow
+    without bound (round-1 advice).  Beyond 48 arenas the idle ones are returned to the driver: 80 streams, one
+    multi-pass transform each (needs scratch), results stay right."""
+    import torch
+    ctx = jw.Context()
+    w = jw.wavelets.Daubechies20()
+    t = jw.CudaMODWTTransform(w, context=ctx)
+    x = splitmix_uniform(99, (2, 8192))
+    g, h = oracle.modwt_filters(w.getScalingDeComposition(), w.getWaveletDeComposition())
+    ref = oracle.batch("modwt_fwd", x, 8, g, h)
+    dx = torch.from_numpy(x).cuda()
+    outs = []
+    for i in range(80):
+        st = torch.cuda.Stream()
+        dc = torch.empty((2, 9, 8192), dtype=torch.float64, device="cuda")
+        st.wait_stream(torch.cuda.current_stream())
+        t.forwardMODWTDevice(dx.data_ptr(), dc.data_ptr(), 2, 8192, 8, stream=st.cuda_stream)
+        outs.append((st, dc))
+    for st, dc in outs[::13] + outs[-1:]:
+        st.synchronize()
+        assert _maxerr(dc.cpu().numpy(), ref, x) <= TOL
+    ctx.close()
+
+
 def test_diagnostic_rooflines(jw, gpu_ctx):
     """jwc_diag_dfma_tflops / jwc_diag_copy_gbs: the in-run denominators of bench.py's fp64_frac / copy ceiling."""
     tf = gpu_ctx.dfma_tflops()
