@@ -625,6 +625,10 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "small_per_cta")) return &t.small_per_cta;
   if (!strcmp(key, "force_generic")) return &t.force_generic;
   if (!strcmp(key, "l2_prefetch")) return &t.l2_prefetch;
+  if (!strcmp(key, "pf_inv")) return &t.pf_inv;
+  if (!strcmp(key, "modwt_logp")) return &t.modwt_logp;
+  if (!strcmp(key, "top_barrier")) return &t.top_barrier;
+  if (!strcmp(key, "modwt_tile_deep")) return &t.modwt_tile_deep;
   return nullptr;
 }
 JWC_API int jwc_set_tuning(jwc_ctx* ctx, const char* key, int value) {

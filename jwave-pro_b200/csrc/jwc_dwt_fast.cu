@@ -51,6 +51,7 @@ struct DwtPassArgs {
   int64_t h;           // node length at depth l0 (= N >> l0)
   int l0, k, T, tiles, nodes, cap, mode;
   int pf_dist;        // L2 prefetch distance in CTAs (0 = off)
+  int top_barrier;    // inverse: 1 = round-1 form of the tile wait (see the level loop)
   int log_tiles;      // tiles and nodes are powers of two: the CTA index is taken apart with shifts (a 64-bit
                       // division is a ~100-instruction subroutine, and a CTA only lives for a few thousand)
   unsigned nblocks;
@@ -550,11 +551,15 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
     }
     if (bulk && (!TREE || u == 0)) {
       const uint32_t par = (uint32_t)((u >> 1) & 1);
-      if (tid == 0) ptx::mbar_wait(&bars[u & 1], par);
-      __syncthreads();
+      if (a.top_barrier) {   // round-1 form: one sleeper on the mbarrier, the rest on a block barrier
+        if (tid == 0) ptx::mbar_wait(&bars[u & 1], par);
+        __syncthreads();
+      }
+      // every thread takes its own acquire on the TMA-written tiles; the block barrier that ends the previous level
+      // has already ordered the generic-proxy traffic, so the top of a level needs no second one
       ptx::mbar_wait(&bars[u & 1], par);
-    } else {
-      __syncthreads();
+    } else if (u == 0 || a.top_barrier) {
+      __syncthreads();   // scalar prologue loads (all threads) -> visible
     }
     const int hl_out = s_hl[jj - 1], hl_in = s_hl[jj];
     const int np = (hl_out >> 1) + (tlen >> jj);          // output pairs per parent
@@ -839,6 +844,8 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     a.log_tiles = 0;
     while ((1 << a.log_tiles) < a.tiles) a.log_tiles++;   // tiles = h / T, both powers of two
     a.pf_dist = (p.mode == DWT_BULK) ? dwt_prefetch_distance(ctx, dev, p.smem, p.threads) : 0;
+    if (ctx->tune.pf_inv != 0) a.pf_dist = (p.mode == DWT_BULK && ctx->tune.pf_inv > 0) ? ctx->tune.pf_inv : 0;
+    a.top_barrier = ctx->tune.top_barrier;
     int rc = JWC_ERR_UNSUPPORTED;
     if (!tree)   // long signals: the tiled in-place kernel (jwc_dwt_whole.cu) takes passes of up to 3 levels
       rc = tile_dwt_inverse_pass(ctx, st, a.ain, a.ain_sig, a.in, a.in_sig, a.out, a.out_sig, n, p.l0, p.k, batch, f, L);

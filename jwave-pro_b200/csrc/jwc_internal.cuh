@@ -71,6 +71,10 @@ struct Tuning {
   int h2d_buffers = 0;      // host pipeline staging depth (1..4), 0 = auto
   int force_generic = 0;
   int l2_prefetch = 0;      // 0 = auto (one wave of CTAs ahead), -1 = off, > 0 = distance in CTAs
+  int pf_inv = 0;           // L2 prefetch of the FWT / WPT inverse passes on its own: 0 = auto, -1 = off, > 0 = distance in CTAs
+  int top_barrier = 0;      // 1 = inverse tile kernels wait for their TMA tiles with one thread + a block barrier (round-1 form)
+  int modwt_logp = 0;       // phases per CTA (log2) of the phase-split MODWT passes: 0 = auto, 1 or 2 = forced
+  int modwt_tile_deep = 0;  // tile override (decimated samples) of the phase-split MODWT passes only, 0 = auto
 };
 
 // One host-buffer call in flight owns one lane (three streams: kernels, H2D, D2H), so concurrent calls on a context --

@@ -341,6 +341,7 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
   pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
   pin.threads_override = ctx->tune.modwt_threads;
+  pin.logp_override = ctx->tune.modwt_logp; pin.tile_deep_override = ctx->tune.modwt_tile_deep;
   pin.inverse = false;
   const ModwtPlan plan = modwt_plan(pin);
   if (plan.passes.empty()) return JWC_ERR_UNSUPPORTED;
@@ -403,6 +404,7 @@ struct InvPassArgs {
   int64_t N, Nd;
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
   int pf_dist;
+  int top_barrier;   // 1 = round-1 form of the tile wait (one thread on the mbarrier, the rest on a block barrier)
   unsigned nblocks;
 };
 
@@ -463,6 +465,31 @@ __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst
       const int r = e >> a.logP, p = e & (P - 1);
       const int64_t i = wrap_row(i_start + r, a.Nd);
       dst[e] = src_b[i * S0 + ph0 + p];
+    }
+  }
+}
+
+// one level of a tile: every work item = R consecutive rows of one column (see the file header)
+template <int L, int R>
+__device__ __forceinline__ void inv_level(double* smem, int ovin, int owin, int ovout, int sh, int len, int rows,
+                                          const FilterPair& f, const double* __restrict__ ctaps, int tid, int nt) {
+  const int s = 1 << sh;
+  const int nrb = (rows + R - 1) / R;
+  const int items = nrb << sh;
+  const int span = (R - 1) << sh;
+#pragma unroll 1
+  for (int w = tid; w < items; w += nt) {
+    const int rb = w >> sh, c = w & (s - 1);
+    const int rel0 = ((rb * R) << sh) + c;
+    double o[R];
+    inv_item<L, R>(smem + ovin + rel0, smem + owin + rel0, s, f, ctaps, o);
+    if (rel0 + span < len) {
+#pragma unroll
+      for (int q = 0; q < R; q++) smem[ovout + rel0 + (q << sh)] = o[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < R; q++)
+        if (rel0 + (q << sh) < len) smem[ovout + rel0 + (q << sh)] = o[q];
     }
   }
 }
@@ -536,9 +563,16 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
     }
     if (bulk) {
       const uint32_t par = (uint32_t)((u >> 1) & 1);
-      if (tid == 0) ptx::mbar_wait(&bars[wb], par);   // one sleeper on the mbarrier, the rest on the hardware barrier
-      __syncthreads();
-      ptx::mbar_wait(&bars[wb], par);                 // complete already: per-thread acquire of the TMA-written tiles
+      if (!a.top_barrier) {
+        // every thread takes its own acquire on the mbarrier: the block barrier at the end of the previous level has
+        // already ordered the shared-memory traffic, so the top of a level needs no second one (measured on C2:
+        // 3.50 -> 3.33 ms against one sleeper on the mbarrier + a block barrier for the rest)
+        ptx::mbar_wait(&bars[wb], par);
+      } else {
+        if (tid == 0) ptx::mbar_wait(&bars[wb], par);   // one sleeper on the mbarrier, the rest on the hardware barrier
+        __syncthreads();
+        ptx::mbar_wait(&bars[wb], par);                 // complete already: per-thread acquire of the TMA-written tiles
+      }
     } else {
       if (a.mode == MODE_VEC2) {
         if (jj > 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -552,24 +586,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
     const int len = P * (tlen2 + hout);
     const int ovin = (u & 1) * a.vcap, owin = (2 + wb) * a.vcap, ovout = ((u + 1) & 1) * a.vcap;
     const int rows = (len + s - 1) >> sh;
-    const int nrb = (rows + R - 1) / R;
-    const int items = nrb << sh;
-    const int span = (R - 1) << sh;
-  #pragma unroll 1
-  for (int w = tid; w < items; w += nt) {
-      const int rb = w >> sh, c = w & (s - 1);
-      const int rel0 = ((rb * R) << sh) + c;
-      double o[R];
-      inv_item<L, R>(smem + ovin + rel0, smem + owin + rel0, s, f, ctaps, o);
-      if (rel0 + span < len) {
-#pragma unroll
-        for (int q = 0; q < R; q++) smem[ovout + rel0 + (q << sh)] = o[q];
-      } else {
-#pragma unroll
-        for (int q = 0; q < R; q++)
-          if (rel0 + (q << sh) < len) smem[ovout + rel0 + (q << sh)] = o[q];
-      }
-    }
+    inv_level<L, R>(smem, ovin, owin, ovout, sh, len, rows, f, ctaps, tid, nt);
     if (bulk && jj == 1) ptx::fence_proxy_async();
     __syncthreads();
   }
@@ -630,6 +647,7 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
   pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
   pin.threads_override = ctx->tune.modwt_threads;
+  pin.logp_override = ctx->tune.modwt_logp; pin.tile_deep_override = ctx->tune.modwt_tile_deep;
   pin.inverse = true;
   const ModwtPlan plan = modwt_plan(pin);
   // the inverse starts at the deepest level: it can only be fused if the whole chain is (no generic head)
@@ -663,6 +681,7 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
     a.nblocks = (unsigned)nblocks;
     a.pf_dist = (p.mode == MODE_BULK && ctx->tune.l2_prefetch > 0) ? ctx->tune.l2_prefetch : 0;   // off by default: measured slower
+    a.top_barrier = ctx->tune.top_barrier;
     int rc = dispatch_inv_pass(ctx, st, a, f, L, p.threads, p.smem, nblocks);
     if (rc != JWC_OK) return rc;
     vin = a.vout; vin_sig = a.vout_sig;

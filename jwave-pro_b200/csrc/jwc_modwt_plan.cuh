@@ -44,6 +44,7 @@ struct ModwtPlanInput {
   bool aligned16;      // every base pointer 16-byte aligned
   int smem_budget;     // bytes per CTA the plan may use
   int tile_override, group_override, threads_override;
+  int logp_override = 0, tile_deep_override = 0;   // phase-split passes (j0 > 0) only
   bool inverse;        // inverse needs (V ping-pong + W double buffer), forward (V ping-pong + W staging)
 };
 
@@ -92,7 +93,8 @@ inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP,
   const int64_t budget = in.smem_budget / 8 - 8 - 128;   // mbarriers + shared-memory tap copy
   // largest even T2 that fits
   int64_t lo = 2, hi = std::max<int64_t>(2, Nd + (Nd & 1)), best = 0;
-  if (in.tile_override > 0) hi = std::min<int64_t>(hi, in.tile_override);
+  const int tile_ov = (j0 > 0 && in.tile_deep_override > 0) ? in.tile_deep_override : in.tile_override;
+  if (tile_ov > 0) hi = std::min<int64_t>(hi, tile_ov);
   if (modwt_smem_doubles(in.inverse, P, (int)hi, (int)Hp, k) <= budget) best = hi;
   else {
     while (lo <= hi) {
@@ -104,7 +106,7 @@ inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP,
     if (best >= 128) best &= ~(int64_t)63;   // keep tiles 512-byte multiples
   }
   if (best < 2) return false;
-  if (best < Nd && best < H && in.tile_override <= 0) return false;  // halo would dominate the tile
+  if (best < Nd && best < H && tile_ov <= 0) return false;  // halo would dominate the tile
   // Candidates: the largest tile that fits and smaller ones in steps of 64 (down to 5/8 of it), each with 128 or 256
   // threads.  Whole multiples of 128 threads only: a warp's scheduler is fixed by (warp index % 4), so 160- or
   // 192-thread CTAs put twice the work on one or two of the four schedulers of the SM (the fp64 pipe then idles at
@@ -118,7 +120,7 @@ inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP,
   // ... and only for the fp64-bound long filters: the HBM-bound short ones want the largest tile (Daubechies4 on
   // 100 000 samples: 2.42 ms with the largest tile and 256 threads, 2.62 ms with the searched 1984 x 128).
   const bool legacy = in.inverse || in.L <= 10;
-  const int64_t tmin = (legacy || in.tile_override > 0 || tmax >= Nd || tmax < 512)
+  const int64_t tmin = (legacy || tile_ov > 0 || tmax >= Nd || tmax < 512)
                            ? tmax : std::max<int64_t>(H, (tmax * 5 / 8) & ~(int64_t)63);
   int inv_thr = 256;
   if (legacy) {
@@ -186,6 +188,7 @@ inline bool modwt_make_pass(const ModwtPlanInput& in, int j0, int k, ModwtPass* 
   bool ok = false;
   double bt = 1e300;
   for (int logP = std::min(j0, 2); logP >= 1; --logP) {   // 4 phases (32-byte rows) or 2 (16-byte rows)
+    if (in.logp_override > 0 && logP != std::min(j0, in.logp_override)) continue;
     ModwtPass p;
     double t;
     if (modwt_make_pass_p(in, j0, k, logP, &p, &t) && t < bt) { bt = t; *out = p; ok = true; }
