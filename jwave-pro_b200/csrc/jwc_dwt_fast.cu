@@ -680,6 +680,7 @@ DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const voi
   // (measured, Haar 2^20: k <= 3 gives 3.10 ms, the model's k = 5 gives 3.38 ms)
   if (inverse && !tree && pin.group_override <= 0) pin.group_override = 3;
   pin.threads_override = ctx->tune.dwt_threads;
+  pin.k0_override = ctx->tune.dwt_k0;
   if (group_cap > 0) pin.group_override = pin.group_override > 0 ? std::min(pin.group_override, group_cap) : group_cap;
   return dwt_plan(pin, steps);
 }

@@ -50,6 +50,7 @@ struct DwtPlanInput {
   int levels, L;
   bool tree, inverse, aligned16;
   int smem_budget, tile_override, group_override, threads_override;
+  int k0_override = 0;   // > 0: depth of the first pass (l0 = 0) is forced (experiments)
 };
 
 // ---- forward geometry -------------------------------------------------------------------------------------------------
@@ -168,6 +169,7 @@ inline DwtPlan dwt_plan(const DwtPlanInput& in, int steps) {
     for (int k = 1; k <= kmax; k++) {
       DwtPass p;
       double t;
+      if (l0 == 0 && in.k0_override > 0 && k != std::min(in.k0_override, steps)) continue;
       if (!dwt_make_pass(in, l0, k, &p, &t)) continue;
       if (best[l0 + k] < 1e299 && t + best[l0 + k] < best[l0]) {
         best[l0] = t + best[l0 + k];

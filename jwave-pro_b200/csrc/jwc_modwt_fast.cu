@@ -238,13 +238,26 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
         if (direct_w) {
           // virtual position e -> row r = (e - eW) >> logP, phase p = (e - eW) & (P - 1); rows of one item are s/P apart
           const int v0 = ef - eW;   // may be negative for an item that starts in the halo
-          double* g0 = gw + ((int64_t)(v0 >> a.logP)) * S0 + (v0 & (P - 1));
+          if (full && v0 >= 0) {
+            // the common case, no predicates: 32-bit element offsets from the level's row origin (tile-local, < N < 2^31)
+            double* gp = gw + ((unsigned)(v0 >> a.logP) * (unsigned)S0 + (unsigned)(v0 & (P - 1)));
+            int so = oout + ef;
 #pragma unroll
-          for (int q = 0; q < R; q++) {
-            const int e = ef + (q << sh);
-            if (full || rel0 + (q << sh) < len) {
-              smem[oout + e] = av[q];
-              if (e >= eW) g0[q * gstep] = aw[q];
+            for (int q = 0; q < R; q++) {
+              smem[so] = av[q];
+              *gp = aw[q];
+              so += s;
+              gp += gstep;
+            }
+          } else {
+            double* g0 = gw + ((int64_t)(v0 >> a.logP)) * S0 + (v0 & (P - 1));
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+              const int e = ef + (q << sh);
+              if (full || rel0 + (q << sh) < len) {
+                smem[oout + e] = av[q];
+                if (e >= eW) g0[q * gstep] = aw[q];
+              }
             }
           }
         } else if (full && ef >= eW) {

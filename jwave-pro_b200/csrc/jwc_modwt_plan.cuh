@@ -130,6 +130,9 @@ inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP,
       const double e = modwt_lane_efficiency(in.inverse, in.L, k, logP, Tf, cand);
       if (e > e0 + 0.02) { e0 = e; inv_thr = cand; }
     }
+    // fp64-bound long filters: whole multiples of 128 threads only (see above) -- the 160-thread CTAs this search liked
+    // for the phase-split inverse passes of Daubechies20 put two of their five warps on one scheduler (33.5 -> 33.1 ms)
+    if (in.inverse && in.L > 10) inv_thr = 128;
   }
   for (int64_t T2 = tmax; T2 >= tmin && T2 >= 2; T2 -= 64) {
     const int Tfull = (int)std::min<int64_t>(T2, Nd);
