@@ -629,6 +629,8 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "modwt_logp")) return &t.modwt_logp;
   if (!strcmp(key, "top_barrier")) return &t.top_barrier;
   if (!strcmp(key, "dwt_k0")) return &t.dwt_k0;
+  if (!strcmp(key, "dwt_fixed")) return &t.dwt_fixed;
+  if (!strcmp(key, "modwt_force_wrap")) return &t.modwt_force_wrap;
   if (!strcmp(key, "modwt_tile_deep")) return &t.modwt_tile_deep;
   return nullptr;
 }

@@ -681,6 +681,7 @@ DwtPlan make_plan(jwc_ctx* ctx, const DeviceSlot& dev, const void* p0, const voi
   if (inverse && !tree && pin.group_override <= 0) pin.group_override = 3;
   pin.threads_override = ctx->tune.dwt_threads;
   pin.k0_override = ctx->tune.dwt_k0;
+  pin.fixed_override = ctx->tune.dwt_fixed;
   if (group_cap > 0) pin.group_override = pin.group_override > 0 ? std::min(pin.group_override, group_cap) : group_cap;
   return dwt_plan(pin, steps);
 }

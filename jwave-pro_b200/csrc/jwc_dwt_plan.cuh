@@ -51,6 +51,7 @@ struct DwtPlanInput {
   bool tree, inverse, aligned16;
   int smem_budget, tile_override, group_override, threads_override;
   int k0_override = 0;   // > 0: depth of the first pass (l0 = 0) is forced (experiments)
+  int fixed_override = 0;   // > 0: per-pass fixed cost of the pyramid model in 0.01 ps per sample (experiments)
 };
 
 // ---- forward geometry -------------------------------------------------------------------------------------------------
@@ -147,7 +148,7 @@ inline bool dwt_make_pass(const DwtPlanInput& in, int l0, int k, DwtPass* out, d
   const double tm = bytes / 5.5, tc = flops / 32.0;
   const double frac = in.tree ? 1.0 : 1.0 / (double)((int64_t)1 << l0);   // FWT passes shrink geometrically
   // every level is a block-wide barrier whose latency is only partly hidden by the other resident CTAs
-  *est = frac * (std::max(tm, tc) + 0.35 * std::min(tm, tc) + 0.25 * k) + (in.tree ? 1.0 : 0.2);
+  *est = frac * (std::max(tm, tc) + 0.35 * std::min(tm, tc) + 0.25 * k) + (in.tree ? 1.0 : (in.fixed_override > 0 ? 0.01 * in.fixed_override : 0.05));
   return true;
 }
 

@@ -44,6 +44,27 @@ int prefetch_distance(jwc_ctx* ctx, const DeviceSlot& dev, size_t smem, int thre
   return dev.sm_count;   // measured on B200 (C2 forward, 2 CTAs/SM): half a wave ahead 3.15 ms, a wave 3.19, two waves 3.32
 }
 
+// Element offset of row i (0 <= i < Nd) of a phase-split pass.  When 2^j0 divides N the rows of one phase are
+// i 2^j0 apart; otherwise the walk t -> t + 2^j0 (mod N) closes after N / gcd(2^j0, N) positions and row i sits at
+// (i (2^j0 mod N)) mod N (jwc_modwt_plan.cuh, modwt_cycles).  The quotient comes from one fp64 multiply (off by at
+// most one, corrected) -- a 64-bit integer modulo is a ~100-instruction subroutine.
+struct RowMap {
+  int64_t S0, Sm, N;   // 2^j0, 2^j0 mod N, signal length
+  double invN;
+  int wrap;            // 0: offset = i * S0 (kernels instantiated with WRAP = false: the code of the round-1 paths)
+  // RT: the WRAP instantiation serves every shape and tests `wrap` at run time (long-filter forward kernel, see there)
+  template <bool WRAP, bool RT = false>
+  __device__ __forceinline__ int64_t at(int64_t i, int64_t s0) const {   // s0 = 2^j0 as the caller already has it
+    if (!WRAP || (RT && !wrap)) return i * s0;
+    const uint64_t prod = (uint64_t)i * (uint64_t)Sm;   // < 2^62
+    const uint64_t q = (uint64_t)((double)prod * invN);
+    int64_t r = (int64_t)(prod - q * (uint64_t)N);
+    while (r < 0) r += N;
+    while (r >= N) r -= N;
+    return r;
+  }
+};
+
 struct FwdPassArgs {
   const double* in;   // V_{j0}
   double* coeffs;     // coefficient block base
@@ -53,6 +74,7 @@ struct FwdPassArgs {
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
   int pf_dist;   // L2 prefetch distance in CTAs (0 = off): the tile of CTA blockIdx + pf_dist is pulled into L2
   unsigned nblocks;
+  RowMap rm;     // address of a decimated row (cycle index) of a phase-split pass
 };
 
 // Long filters: 2L taps do not fit the uniform-register file (63 x 32 bit), and ptxas then feeds every DFMA through
@@ -115,10 +137,22 @@ __device__ __forceinline__ int64_t wrap_row(int64_t i, int64_t nd) {
   return i;
 }
 
-template <int L, int R>
-__global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
+#ifndef JWC_FWD_MINB
+#define JWC_FWD_MINB 2
+#endif
+#ifndef JWC_INV_MINB
+#define JWC_INV_MINB 2
+#endif
+template <int L, int R, bool WRAP>
+__global__ void __launch_bounds__(256, (L > 10 ? JWC_FWD_MINB : 3)) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
   // shared memory is addressed as smem[int offset] everywhere: keeps the accesses plain LDS/STS with register offsets
+  // Long filters run ONE instantiation (WRAP = true) for every shape and test RowMap::wrap at run time: with both
+  // store paths in the item loop ptxas settles on 64 registers and spreads the 46 shared loads of an item evenly between
+  // its 560 DFMAs, where the WRAP = false code takes 124 registers and front-loads 29 of them -- measured on
+  // Daubechies20 J = 8: forward 27.5 -> 26.2 ms.  (The inverse kernel and the short filters lose 3-4 % with the
+  // same trick and keep their compile-time split.)
+  constexpr bool RT = (L > kUniformTapsMax);
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = 1 << a.logP;
@@ -184,7 +218,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
     for (int q = tid; q < chunks; q += nt) {
       const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
       const int64_t i = wrap_row(i0 - a.Hp + r, a.Nd);
-      ptx::cp_async16(smem + r * P + pp, in_b + i * S0 + ph0 + pp);
+      ptx::cp_async16(smem + r * P + pp, in_b + a.rm.template at<WRAP, RT>(i, S0) + ph0 + pp);
     }
     ptx::cp_async_commit_wait_all();
     __syncthreads();
@@ -193,7 +227,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
     for (int e = tid; e < total; e += nt) {
       const int r = e >> a.logP, p = e & (P - 1);
       const int64_t i = wrap_row(i0 - a.Hp + r, a.Nd);
-      smem[e] = in_b[i * S0 + ph0 + p];
+      smem[e] = in_b[a.rm.template at<WRAP, RT>(i, S0) + ph0 + p];
     }
     __syncthreads();
   }
@@ -214,8 +248,11 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
     const int nrb = (rows + R - 1) / R;
     const int items = nrb << sh;
     const int span = (R - 1) << sh;
-    double* gw = co_b + (int64_t)(a.j0 + jj - 1) * a.N + i0 * S0 + ph0;   // direct_w: W row of this level, tile origin
-    const int64_t gstep = ((int64_t)s >> a.logP) * S0;                      // global distance of two rows of an item
+    // direct_w: W row of this level at the phase origin (gw) and, when 2^j0 divides N, at the tile origin (gwt)
+    double* gw = co_b + (int64_t)(a.j0 + jj - 1) * a.N + ph0;
+    const bool plain = !WRAP || (RT && !a.rm.wrap);
+    double* gwt = gw + (plain ? i0 * S0 : 0);
+    const int64_t gstep = ((int64_t)s >> a.logP) * S0;          // global distance of two rows of an item (2^j0 | N)
   #pragma unroll 1
   for (int w = tid; w < items; w += nt) {
       const int rb = w >> sh, c = w & (s - 1);
@@ -238,9 +275,9 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
         if (direct_w) {
           // virtual position e -> row r = (e - eW) >> logP, phase p = (e - eW) & (P - 1); rows of one item are s/P apart
           const int v0 = ef - eW;   // may be negative for an item that starts in the halo
-          if (full && v0 >= 0) {
-            // the common case, no predicates: 32-bit element offsets from the level's row origin (tile-local, < N < 2^31)
-            double* gp = gw + ((unsigned)(v0 >> a.logP) * (unsigned)S0 + (unsigned)(v0 & (P - 1)));
+          if (plain && full && v0 >= 0) {
+            // the common case, no predicates: 32-bit element offset from the tile origin (tile-local, < N < 2^31)
+            double* gp = gwt + ((unsigned)(v0 >> a.logP) * (unsigned)S0 + (unsigned)(v0 & (P - 1)));
             int so = oout + ef;
 #pragma unroll
             for (int q = 0; q < R; q++) {
@@ -249,14 +286,23 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
               so += s;
               gp += gstep;
             }
-          } else {
-            double* g0 = gw + ((int64_t)(v0 >> a.logP)) * S0 + (v0 & (P - 1));
+          } else if (plain) {
+            double* g0 = gwt + ((int64_t)(v0 >> a.logP)) * S0 + (v0 & (P - 1));
 #pragma unroll
             for (int q = 0; q < R; q++) {
               const int e = ef + (q << sh);
               if (full || rel0 + (q << sh) < len) {
                 smem[oout + e] = av[q];
                 if (e >= eW) g0[q * gstep] = aw[q];
+              }
+            }
+          } else {   // rows addressed along the cycles of the circular signal
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+              const int e = ef + (q << sh);
+              if (full || rel0 + (q << sh) < len) {
+                smem[oout + e] = av[q];
+                if (e >= eW) gw[a.rm.template at<true>(i0 + ((e - eW) >> a.logP), S0) + ((e - eW) & (P - 1))] = aw[q];
               }
             }
           }
@@ -302,13 +348,13 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
           for (int q = tid; q < chunks; q += nt) {
             const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
             const double2 val = *reinterpret_cast<const double2*>(src + r * P + pp);
-            *reinterpret_cast<double2*>(dst + (i0 + r) * S0 + ph0 + pp) = val;
+            *reinterpret_cast<double2*>(dst + a.rm.template at<WRAP, RT>(i0 + r, S0) + ph0 + pp) = val;
           }
         } else {
           const int total = tlen2 * P;
           for (int e = tid; e < total; e += nt) {
             const int r = e >> a.logP, p = e & (P - 1);
-            dst[(i0 + r) * S0 + ph0 + p] = src[e];
+            dst[a.rm.template at<WRAP, RT>(i0 + r, S0) + ph0 + p] = src[e];
           }
         }
       }
@@ -320,9 +366,16 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_fwd_pass_kernel(c
 template <int L>
 int launch_fwd_pass(jwc_ctx* ctx, cudaStream_t st, const FwdPassArgs& a, const FilterPair& f, int threads, size_t smem,
                     int64_t nblocks) {
-  auto kern = modwt_fwd_pass_kernel<L, kModwtR>;
-  JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
-  kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  if (a.rm.wrap || L > kUniformTapsMax) {   // 2^j0 does not divide N (rows addressed along the cycles of the circular
+                                            // signal), and every shape of the long filters (see the kernel)
+    auto kern = modwt_fwd_pass_kernel<L, kModwtR, true>;
+    JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
+    kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  } else if constexpr (L <= kUniformTapsMax) {
+    auto kern = modwt_fwd_pass_kernel<L, kModwtR, false>;
+    JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
+    kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  }
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());
   return JWC_OK;
@@ -380,10 +433,13 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     a.coeffs = d_coeffs; a.coeff_sig = cs;
     if (last) { a.vout = d_coeffs + (int64_t)levels * n; a.vout_sig = cs; }
     else { a.vout = vbuf[pi & 1]; a.vout_sig = n; }
-    a.N = n; a.Nd = n >> p.j0;
+    const int64_t cycles = modwt_cycles(n, p.j0);   // = 2^j0 when that divides n
+    a.N = n; a.Nd = n / cycles;
     a.j0 = p.j0; a.k = p.k; a.logP = p.logP; a.T2 = p.T2; a.Hp = p.Hp;
     a.tiles_i = (int)((a.Nd + p.T2 - 1) / p.T2);
-    a.groups = (int)(((int64_t)1 << p.j0) >> p.logP);
+    a.groups = (int)(cycles >> p.logP);
+    a.rm.S0 = (int64_t)1 << p.j0; a.rm.N = n; a.rm.Sm = a.rm.S0 % n; a.rm.invN = 1.0 / (double)n;
+    a.rm.wrap = (n % a.rm.S0) != 0 || (ctx->tune.modwt_force_wrap > 0 && p.j0 > 0);
     a.vcap = p.vcap; a.mode = p.mode;
     const int64_t nblocks = (int64_t)a.tiles_i * a.groups * batch;
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
@@ -417,6 +473,7 @@ struct InvPassArgs {
   int64_t N, Nd;
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
   int pf_dist;
+  RowMap rm;
   int top_barrier;   // 1 = round-1 form of the tile wait (one thread on the mbarrier, the rest on a block barrier)
   unsigned nblocks;
 };
@@ -453,6 +510,7 @@ __device__ __forceinline__ void inv_item(const double* __restrict__ pv, const do
 }
 
 // rows [i_start, i_start + rows) of the decimated index (circular), P phases each, into dst (virtual layout r*P + p)
+template <bool WRAP>
 __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst, const double* src_b, int64_t i_start,
                                                int rows, int ph0, uint64_t* bar, int tid, int nt) {
   const int P = 1 << a.logP;
@@ -469,7 +527,7 @@ __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst
     for (int q = tid; q < chunks; q += nt) {
       const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
       const int64_t i = wrap_row(i_start + r, a.Nd);
-      ptx::cp_async16(dst + r * P + pp, src_b + i * S0 + ph0 + pp);
+      ptx::cp_async16(dst + r * P + pp, src_b + a.rm.template at<WRAP>(i, S0) + ph0 + pp);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   } else {
@@ -477,7 +535,7 @@ __device__ __forceinline__ void inv_issue_load(const InvPassArgs& a, double* dst
     for (int e = tid; e < total; e += nt) {
       const int r = e >> a.logP, p = e & (P - 1);
       const int64_t i = wrap_row(i_start + r, a.Nd);
-      dst[e] = src_b[i * S0 + ph0 + p];
+      dst[e] = src_b[a.rm.template at<WRAP>(i, S0) + ph0 + p];
     }
   }
 }
@@ -507,8 +565,8 @@ __device__ __forceinline__ void inv_level(double* smem, int ovin, int owin, int 
   }
 }
 
-template <int L, int R>
-__global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(const __grid_constant__ InvPassArgs a,
+template <int L, int R, bool WRAP>
+__global__ void __launch_bounds__(256, (L > 10 ? JWC_INV_MINB : 3)) modwt_inv_pass_kernel(const __grid_constant__ InvPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -563,8 +621,8 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
   {
     const int rows = tlen2 + halo(a.k);
     if (bulk && tid == 0) ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)rows * 8u);
-    inv_issue_load(a, Vb(0), vin_b, i0, rows, ph0, &bars[0], tid, nt);
-    inv_issue_load(a, Wb(0), co_b + (int64_t)(a.j0 + a.k - 1) * a.N, i0, rows, ph0, &bars[0], tid, nt);
+    inv_issue_load<WRAP>(a, Vb(0), vin_b, i0, rows, ph0, &bars[0], tid, nt);
+    inv_issue_load<WRAP>(a, Wb(0), co_b + (int64_t)(a.j0 + a.k - 1) * a.N, i0, rows, ph0, &bars[0], tid, nt);
   }
   const double* ctaps = const_taps(f);
   for (int jj = a.k, u = 0; jj >= 1; --jj, ++u) {
@@ -572,7 +630,7 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
     if (jj > 1) {  // prefetch W_{j0+jj-1} into the other W buffer (last read two barriers ago)
       const int rows = tlen2 + halo(jj - 1);
       if (bulk && tid == 0) ptx::mbar_expect_tx(&bars[wb ^ 1], (uint32_t)rows * 8u);
-      inv_issue_load(a, Wb(wb ^ 1), co_b + (int64_t)(a.j0 + jj - 2) * a.N, i0, rows, ph0, &bars[wb ^ 1], tid, nt);
+      inv_issue_load<WRAP>(a, Wb(wb ^ 1), co_b + (int64_t)(a.j0 + jj - 2) * a.N, i0, rows, ph0, &bars[wb ^ 1], tid, nt);
     }
     if (bulk) {
       const uint32_t par = (uint32_t)((u >> 1) & 1);
@@ -615,13 +673,13 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
     const int hp2 = P >> 1, chunks = tlen2 * hp2;
     for (int q = tid; q < chunks; q += nt) {
       const int r = q >> (a.logP - 1), pp = (q & (hp2 - 1)) * 2;
-      *reinterpret_cast<double2*>(vo_b + (i0 + r) * S0 + ph0 + pp) = *reinterpret_cast<const double2*>(res + r * P + pp);
+      *reinterpret_cast<double2*>(vo_b + a.rm.template at<WRAP>(i0 + r, S0) + ph0 + pp) = *reinterpret_cast<const double2*>(res + r * P + pp);
     }
   } else {
     const int total = tlen2 * P;
     for (int e = tid; e < total; e += nt) {
       const int r = e >> a.logP, p = e & (P - 1);
-      vo_b[(i0 + r) * S0 + ph0 + p] = res[e];
+      vo_b[a.rm.template at<WRAP>(i0 + r, S0) + ph0 + p] = res[e];
     }
   }
 }
@@ -629,9 +687,15 @@ __global__ void __launch_bounds__(256, (L > 10 ? 2 : 3)) modwt_inv_pass_kernel(c
 template <int L>
 int launch_inv_pass(jwc_ctx* ctx, cudaStream_t st, const InvPassArgs& a, const FilterPair& f, int threads, size_t smem,
                     int64_t nblocks) {
-  auto kern = modwt_inv_pass_kernel<L, kModwtR>;
-  JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
-  kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  if (a.rm.wrap) {
+    auto kern = modwt_inv_pass_kernel<L, kModwtR, true>;
+    JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
+    kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  } else {
+    auto kern = modwt_inv_pass_kernel<L, kModwtR, false>;
+    JWC_CUDA_CHECK(allow_max_dynamic_smem(kern));
+    kern<<<(unsigned)nblocks, threads, smem, st>>>(a, f);
+  }
   count_launch(ctx);
   JWC_CUDA_CHECK(cudaGetLastError());
   return JWC_OK;
@@ -685,10 +749,13 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     a.coeffs = d_coeffs; a.coeff_sig = cs;
     if (pi == 0) { a.vout = d_x; a.vout_sig = n; }
     else { a.vout = vbuf[step & 1]; a.vout_sig = n; }
-    a.N = n; a.Nd = n >> p.j0;
+    const int64_t cycles = modwt_cycles(n, p.j0);   // = 2^j0 when that divides n
+    a.N = n; a.Nd = n / cycles;
     a.j0 = p.j0; a.k = p.k; a.logP = p.logP; a.T2 = p.T2; a.Hp = p.Hp;
     a.tiles_i = (int)((a.Nd + p.T2 - 1) / p.T2);
-    a.groups = (int)(((int64_t)1 << p.j0) >> p.logP);
+    a.groups = (int)(cycles >> p.logP);
+    a.rm.S0 = (int64_t)1 << p.j0; a.rm.N = n; a.rm.Sm = a.rm.S0 % n; a.rm.invN = 1.0 / (double)n;
+    a.rm.wrap = (n % a.rm.S0) != 0 || (ctx->tune.modwt_force_wrap > 0 && p.j0 > 0);
     a.vcap = p.vcap; a.mode = p.mode;
     const int64_t nblocks = (int64_t)a.tiles_i * a.groups * batch;
     if (nblocks > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;

@@ -50,6 +50,15 @@ struct ModwtPlanInput {
 
 inline int64_t modwt_halo(int L, int k) { return (int64_t)(L - 1) * (((int64_t)1 << k) - 1); }
 
+// The walk t -> t + 2^j0 (mod n) on a circular signal splits it into G = gcd(2^j0, n) interleaved cycles of n / G
+// positions each (G = 2^j0 when 2^j0 divides n: the plain phase subsequences).  Along a cycle, every level of a pass
+// that starts at depth j0 is a stride-2^(jj-1) filter in the cycle index, so the tile scheme works for ANY n; only the
+// address of cycle index i changes from i 2^j0 to (i 2^j0) mod n.
+inline int64_t modwt_cycles(int64_t n, int j0) {
+  const int64_t S0 = (int64_t)1 << j0, low = n & (-n);
+  return std::min(S0, low);
+}
+
 // shared-memory doubles for one CTA of a pass
 inline int64_t modwt_smem_doubles(bool inverse, int P, int T2, int Hp, int k) {
   const int64_t pad = (int64_t)kModwtR * P * ((int64_t)1 << (k - 1));
@@ -81,10 +90,14 @@ inline double modwt_lane_efficiency(bool inverse, int L, int k, int logP, int T2
 }
 
 inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP, ModwtPass* out, double* est_time) {
-  const int64_t S0 = (int64_t)1 << j0;
-  if (j0 > 0 && (in.n % S0) != 0) return false;
-  const int64_t Nd = in.n >> j0;
+  const int64_t G = modwt_cycles(in.n, j0);
   const int P = 1 << logP;
+  if (P > G) return false;                 // the phases of a CTA are consecutive cycles
+  // odd n: one cycle, every row is a lone 8-byte gather / scatter (a quarter of each 32-byte sector used).  Worth it for
+  // the fp64-bound long filters (Daubechies20 J = 8 on 99 999 samples: 48 ms fused against 129 ms on the per-level
+  // kernels), not for the HBM-bound short ones (Daubechies4 J = 10: 43 ms against 41 ms)
+  if (j0 > 0 && G == 1 && in.L <= 10) return false;
+  const int64_t Nd = in.n / G;             // cycle length (= n >> j0 when 2^j0 divides n)
   int64_t H = modwt_halo(in.L, k);
   int mode;
   if (j0 == 0) mode = (in.aligned16 && (in.n % 2) == 0 && H + 1 <= in.n) ? MODE_BULK : MODE_SCALAR;
@@ -131,8 +144,11 @@ inline bool modwt_make_pass_p(const ModwtPlanInput& in, int j0, int k, int logP,
       if (e > e0 + 0.02) { e0 = e; inv_thr = cand; }
     }
     // fp64-bound long filters: whole multiples of 128 threads only (see above) -- the 160-thread CTAs this search liked
-    // for the phase-split inverse passes of Daubechies20 put two of their five warps on one scheduler (33.5 -> 33.1 ms)
+    // for the phase-split inverse passes of Daubechies20 put two of their five warps on one scheduler.  With 128 the
+    // model then prefers levels 5-7 + level 8 over 5-6 + 7-8 behind the first pass: 34.0 ms against 34.7 (and 36.4
+    // with the 160-thread plan) on one box.
     if (in.inverse && in.L > 10) inv_thr = 128;
+
   }
   for (int64_t T2 = tmax; T2 >= tmin && T2 >= 2; T2 -= 64) {
     const int Tfull = (int)std::min<int64_t>(T2, Nd);
@@ -192,6 +208,7 @@ inline bool modwt_make_pass(const ModwtPlanInput& in, int j0, int k, ModwtPass* 
   double bt = 1e300;
   for (int logP = std::min(j0, 2); logP >= 1; --logP) {   // 4 phases (32-byte rows) or 2 (16-byte rows)
     if (in.logp_override > 0 && logP != std::min(j0, in.logp_override)) continue;
+    if (((int64_t)1 << logP) > modwt_cycles(in.n, j0)) continue;
     ModwtPass p;
     double t;
     if (modwt_make_pass_p(in, j0, k, logP, &p, &t) && t < bt) { bt = t; *out = p; ok = true; }
@@ -205,8 +222,8 @@ inline bool modwt_make_pass(const ModwtPlanInput& in, int j0, int k, ModwtPass* 
   return ok;
 }
 
-// dynamic programme over pass boundaries; levels that cannot be fused (e.g. 2^j0 does not divide n) fall to the
-// generic per-level kernels (24 B/sample/level, no fusion).
+// dynamic programme over pass boundaries; levels that cannot be fused (no tile fits the budget) fall to the generic
+// per-level kernels (24 B/sample/level, no fusion).
 inline ModwtPlan modwt_plan(const ModwtPlanInput& in) {
   const int J = in.J;
   std::vector<double> best(J + 1, 1e300);

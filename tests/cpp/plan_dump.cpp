@@ -20,14 +20,15 @@ int main(int argc, char** argv) {
     printf("{\"all_fused\": %d, \"generic_from\": %d, \"R\": %d, \"passes\": [", (int)p.all_fused, p.generic_from, kModwtR);
     for (size_t i = 0; i < p.passes.size(); i++) {
       const ModwtPass& q = p.passes[i];
-      printf("%s{\"j0\": %d, \"k\": %d, \"logP\": %d, \"T2\": %d, \"Hp\": %d, \"mode\": %d, \"vcap\": %d, \"threads\": %d, \"smem\": %zu}",
-             i ? ", " : "", q.j0, q.k, q.logP, q.T2, q.Hp, q.mode, q.vcap, q.threads, q.smem);
+      printf("%s{\"j0\": %d, \"k\": %d, \"logP\": %d, \"T2\": %d, \"Hp\": %d, \"mode\": %d, \"vcap\": %d, \"threads\": %d, \"smem\": %zu, \"cycles\": %lld}",
+             i ? ", " : "", q.j0, q.k, q.logP, q.T2, q.Hp, q.mode, q.vcap, q.threads, q.smem, (long long)modwt_cycles(n, q.j0));
     }
     printf("]}\n");
   } else {
     DwtPlanInput in{};
     in.n = n; in.levels = levels; in.L = L; in.tree = !strcmp(kind, "wpt"); in.inverse = inverse != 0; in.aligned16 = true;
     in.smem_budget = budget;
+    if (argc > 7) in.group_override = atoi(argv[7]);   // optional: maximum levels per pass
     DwtPlan p = dwt_plan(in, levels);
     printf("{\"ok\": %d, \"R\": %d, \"passes\": [", (int)p.ok, kDwtR);
     for (size_t i = 0; i < p.passes.size(); i++) {

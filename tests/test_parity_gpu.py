@@ -131,6 +131,12 @@ def _inputs(seed, batch, n):
     ("Daubechies4", 40000, 7, 3),
     ("Daubechies4", 65537, 4, 2),       # odd length
     ("Symlet8", 8, 3, 2),               # filter longer than the signal (MODWTFFTConvolutionTest.java:42-56)
+    # 2^j0 does not divide n: the deeper fused passes walk the gcd(2^j0, n) interleaved cycles of the circular signal
+    ("Daubechies20", 99999, 8, 2),      # odd: one cycle, single-phase passes
+    ("Daubechies20", 100000, 8, 2),     # 2^5 | n: 32 cycles at j0 = 6
+    ("Daubechies8", 65538, 9, 2),       # 2 x odd: two cycles, 16-byte rows
+    ("Daubechies4", 3000, 11, 2),       # 8 cycles of 375 positions, deep passes with halos longer than a cycle
+    ("Haar1", 12345, 10, 3),
 ])
 def test_modwt_matches_oracle(jw, gpu_ctx, oracle, cls, n, J, batch):
     w = jw.wavelets.create(cls)

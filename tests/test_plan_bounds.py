@@ -5,6 +5,7 @@ grid of shapes the plan is dumped (tests/cpp/plan_dump.cpp, host-only C++) and e
 can touch under that plan -- following the formulas in jwc_modwt_fast.cu / jwc_dwt_fast.cu -- must stay inside the
 buffers, the buffers inside the dynamic shared-memory size, and the passes must cover the levels exactly once."""
 import json
+import math
 import os
 import subprocess
 
@@ -42,9 +43,14 @@ def test_modwt_plan_bounds(dump, L, n, J, inverse, budget):
         j += p["k"]
         P = 1 << p["logP"]
         S0 = 1 << p["j0"]
-        assert p["j0"] == 0 or n % S0 == 0, "phase split needs 2^j0 | n"
-        assert P <= S0 and p["T2"] >= 2 and p["T2"] % 2 == 0 and p["vcap"] % 2 == 0
-        Nd = n >> p["j0"]
+        G = math.gcd(S0, n)   # interleaved cycles of the walk t -> t + 2^j0 (mod n); = 2^j0 when that divides n
+        assert p["cycles"] == G and n % G == 0
+        assert P <= G and p["T2"] >= 2 and p["T2"] % 2 == 0 and p["vcap"] % 2 == 0
+        Nd = n // G
+        # along a cycle, i -> (i 2^j0) mod n visits every position of the cycle's residue class exactly once
+        if n <= 70000 and p["j0"] > 0:
+            seen = {(i * S0) % n for i in range(Nd)}
+            assert len(seen) == Nd and all(t % G == 0 for t in seen) and max(seen) + G <= n
         tlen2 = min(p["T2"], Nd)
         H = (L - 1) * ((1 << p["k"]) - 1)
         assert p["Hp"] >= H
