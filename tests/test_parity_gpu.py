@@ -895,6 +895,44 @@ def test_fwt_inverse_tiled_in_place_variant(jw, oracle, cls, n, lvl):
     ctx.close()
 
 
+@pytest.mark.parametrize("cls,n,J,batch", [("Daubechies20", 65536, 8, 3), ("Daubechies4", 65536, 11, 3),
+                                            ("Symlet8", 1 << 17, 9, 2), ("Daubechies8", 40000, 6, 2)])
+def test_modwt_cycle_walk_and_tile_wait_variants_agree(jw, oracle, cls, n, J, batch):
+    """Two code paths that ordinary shapes do not reach on their own: (1) the cycle-walk instantiation of the fused MODWT
+    passes (rows of a phase-split pass addressed as (i 2^j0) mod n -- what lengths 2^j0 does not divide run) forced onto
+    lengths where it must give the plain phase addressing, (2) the round-1 form of the inverse tile wait (one thread on
+    the mbarrier + a block barrier).  Both must reproduce the default kernels BIT FOR BIT: same arithmetic, only
+    addresses / synchronisation differ."""
+    w = jw.wavelets.create(cls)
+    X = _inputs(n + J, batch, n)
+    base = jw.CudaMODWTTransform(w)
+    c0 = base.forwardMODWTBatch(X, J)
+    x0 = base.inverseMODWTBatch(c0)
+    ref, (g, h) = _modwt_oracle(oracle, w, X[:1], J)
+    assert _maxerr(c0[:1], ref, X) <= TOL
+    for key in ("modwt_force_wrap", "top_barrier"):
+        ctx = jw.Context([0])
+        ctx.set_tuning(key, 1)
+        t = jw.CudaMODWTTransform(w, context=ctx)
+        assert np.array_equal(t.forwardMODWTBatch(X, J), c0), key
+        assert np.array_equal(t.inverseMODWTBatch(c0), x0), key
+        ctx.close()
+
+
+def test_fwt_wpt_tile_wait_variants_agree(jw):
+    """Round-1 tile wait (top_barrier = 1) against the default in the FWT / WPT inverse tile kernels: bit-identical."""
+    X = _inputs(5, 3, 1 << 17)
+    for T, cls, lvl in ((jw.CudaFastWaveletTransform, "Daubechies8", 17), (jw.CudaFastWaveletTransform, "Haar1", 17),
+                        (jw.CudaWaveletPacketTransform, "Symlet8", 6)):
+        w = jw.wavelets.create(cls)
+        c = T(w).forwardBatch(X, lvl)
+        x0 = T(w).reverseBatch(c, lvl)
+        ctx = jw.Context([0])
+        ctx.set_tuning("top_barrier", 1)
+        assert np.array_equal(T(w, context=ctx).reverseBatch(c, lvl), x0), (cls, lvl)
+        ctx.close()
+
+
 def test_workspace_arenas_under_concurrent_device_calls(jw, oracle):
     """Multi-pass transforms take their workspace from the context's per-stream arenas.  Six host threads enqueue 2-D
     FWTs and deep 1-D FWTs on ONE context at once -- three on the context's shared stream, three on private streams --
