@@ -45,5 +45,10 @@ for r in rows[2:]:
         if k in idx:
             v = r[idx[k]]
             u = units[idx[k]]
-            parts.append("%s=%s%s" % (lab, v[:9], ("" if u in ("", "%", "ratio", "inst", "register/thread", "block", "warp") else " " + u)))
+            try:   # integers in full (instruction counts have 10 digits), everything else to 6 significant digits
+                fv = float(v.replace(",", ""))
+                v = ("%d" % fv) if fv == int(fv) and abs(fv) >= 1000 else ("%.6g" % fv)
+            except ValueError:
+                pass
+            parts.append("%s=%s%s" % (lab, v, ("" if u in ("", "%", "ratio", "inst", "register/thread", "block", "warp") else " " + u)))
     print("   " + "  ".join(parts))
