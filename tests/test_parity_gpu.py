@@ -716,6 +716,9 @@ def test_ancient_egyptian_decomposition(jw, gpu_ctx, oracle, kind, cls, n, batch
     ("Daubechies2", 300000, 65536, 32768, 9),
     ("Daubechies20", 9000, 1024, 512, 5),
     ("Daubechies3", 64, 64, 5, 3),           # a single window
+    ("Daubechies20", 40000, 3001, 777, 8),   # odd window longer than the whole-window kernels take, deep levels:
+                                             # tile passes that walk the single cycle of the circular window
+    ("Daubechies8", 50000, 6002, 1500, 9),   # window = 2 x odd: two cycles
 ])
 def test_modwt_sliding_windows(jw, oracle, cls, total, window, hop, J):
     ctx = jw.Context([0])
