@@ -408,6 +408,7 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
   pin.threads_override = ctx->tune.modwt_threads;
   pin.logp_override = ctx->tune.modwt_logp; pin.tile_deep_override = ctx->tune.modwt_tile_deep;
+  pin.plan_override = ctx->tune.modwt_plan_fwd;
   pin.inverse = false;
   const ModwtPlan plan = modwt_plan(pin);
   if (plan.passes.empty()) return JWC_ERR_UNSUPPORTED;
@@ -725,6 +726,7 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
   pin.threads_override = ctx->tune.modwt_threads;
   pin.logp_override = ctx->tune.modwt_logp; pin.tile_deep_override = ctx->tune.modwt_tile_deep;
+  pin.plan_override = ctx->tune.modwt_plan_inv;
   pin.inverse = true;
   const ModwtPlan plan = modwt_plan(pin);
   // the inverse starts at the deepest level: it can only be fused if the whole chain is (no generic head)

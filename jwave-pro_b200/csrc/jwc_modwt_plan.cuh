@@ -45,6 +45,7 @@ struct ModwtPlanInput {
   int smem_budget;     // bytes per CTA the plan may use
   int tile_override, group_override, threads_override;
   int logp_override = 0, tile_deep_override = 0;   // phase-split passes (j0 > 0) only
+  int plan_override = 0;   // > 0: pass depths as decimal digits, first pass first (422 = 4 + 2 + 2 levels); experiments
   bool inverse;        // inverse needs (V ping-pong + W double buffer), forward (V ping-pong + W staging)
 };
 
@@ -246,6 +247,25 @@ inline ModwtPlan modwt_plan(const ModwtPlanInput& in) {
         choice[j0] = k;
         pass_at[j0] = p;
       }
+    }
+  }
+  if (in.plan_override > 0) {   // follow the digits as far as they go and as far as passes can be made
+    int digits[12], nd = 0;
+    for (int v = in.plan_override; v > 0 && nd < 12; v /= 10) digits[nd++] = v % 10;
+    ModwtPlan forced;
+    int j = 0;
+    for (int d = nd - 1; d >= 0 && j < J; d--) {
+      const int k = std::min(digits[d], J - j);
+      ModwtPass p;
+      double t;
+      if (k < 1 || !modwt_make_pass(in, j, k, &p, &t)) break;
+      forced.passes.push_back(p);
+      j += k;
+    }
+    if (j == J) {
+      forced.generic_from = J;
+      forced.all_fused = true;
+      return forced;
     }
   }
   ModwtPlan plan;
