@@ -23,7 +23,10 @@
 
 namespace jwc {
 
-constexpr int kModwtR = 7;  // outputs per work item; odd => conflict-free LDS.64/STS.64 for every stride (see kernel)
+#ifndef JWC_MODWT_R
+#define JWC_MODWT_R 7
+#endif
+constexpr int kModwtR = JWC_MODWT_R;  // outputs per work item; odd => conflict-free LDS.64/STS.64 for every stride (see kernel)
 
 enum { MODE_BULK = 0, MODE_VEC2 = 1, MODE_SCALAR = 2 };
 
