@@ -375,9 +375,15 @@ class DeviceRun:
         total_ms = max(e[0].elapsed_time(e[-1]) for e in ev)
         fwd_ms = max(sum(e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(steps)) for e in ev) / steps
         inv_ms = max(sum(e[2 * k + 1].elapsed_time(e[2 * k + 2]) for k in range(steps)) for e in ev) / steps
-        total_ms, fwd_ms, inv_ms = reduce_max([total_ms, fwd_ms, inv_ms])   # device time = max over ranks
+        # the same events, step by step: the first and the last (up to) ten steps of the timed region on their own -- a long
+        # region runs into the board's power cap (sw_power_cap) and its steps get slower as the SM clock comes down
+        w = min(10, steps)
+        head_ms = max(e[0].elapsed_time(e[2 * w]) for e in ev) / w
+        tail_ms = max(e[2 * (steps - w)].elapsed_time(e[2 * steps]) for e in ev) / w
+        total_ms, fwd_ms, inv_ms, head_ms, tail_ms = reduce_max([total_ms, fwd_ms, inv_ms, head_ms, tail_ms])   # device time = max over ranks
         return {"ms_per_step": total_ms / steps, "fwd_ms": fwd_ms, "inv_ms": inv_ms, "round_trip_max_err": pr,
-                "launches": int(launches), "t0": t0, "t1": t1, "steps": steps, "warmup": warmup}
+                "launches": int(launches), "t0": t0, "t1": t1, "steps": steps, "warmup": warmup,
+                "ms_first_steps": head_ms, "ms_last_steps": tail_ms, "window_steps": w}
 
     def fractions(self, res, peak_gbs, fp64_tflops):
         bps = algorithmic_bytes_per_sample(self.kind, self.levels, self.n)
@@ -840,7 +846,9 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GiB read per direction vs 126 MB L2)" % (
                            (levels + 1 if kind in ("modwt", "windows") else 1) * batch * unit * 8 / 2 ** 30),
                        "sharding": "by signal, no collective", "numa": numa, "tune": args.tune, "flags": args.flags,
-                       "round_trip_max_err": res["round_trip_max_err"]},
+                       "round_trip_max_err": res["round_trip_max_err"],
+                       "ms_per_step_first_%d_steps" % res["window_steps"]: res["ms_first_steps"],
+                       "ms_per_step_last_%d_steps" % res["window_steps"]: res["ms_last_steps"]},
             "roofline": roofline, "directions": fr, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": res["launches"],
         }
