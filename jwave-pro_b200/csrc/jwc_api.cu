@@ -631,6 +631,7 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "dwt_k0")) return &t.dwt_k0;
   if (!strcmp(key, "dwt_fixed")) return &t.dwt_fixed;
   if (!strcmp(key, "modwt_force_wrap")) return &t.modwt_force_wrap;
+  if (!strcmp(key, "modwt_threads_fwd")) return &t.modwt_threads_fwd;
   if (!strcmp(key, "modwt_plan_fwd")) return &t.modwt_plan_fwd;
   if (!strcmp(key, "modwt_plan_inv")) return &t.modwt_plan_inv;
   if (!strcmp(key, "modwt_tile_deep")) return &t.modwt_tile_deep;

@@ -73,6 +73,7 @@ struct Tuning {
   int l2_prefetch = 0;      // 0 = auto (one wave of CTAs ahead), -1 = off, > 0 = distance in CTAs
   int pf_inv = 0;           // L2 prefetch of the FWT / WPT inverse passes on its own: 0 = auto, -1 = off, > 0 = distance in CTAs
   int modwt_plan_fwd = 0, modwt_plan_inv = 0;   // > 0: levels per fused MODWT pass as decimal digits (2222, 431): experiments
+  int modwt_threads_fwd = 0; // threads per CTA of the forward MODWT passes only (experiments)
   int modwt_force_wrap = 0; // 1 = phase-split MODWT passes always run the cycle-walk (WRAP) kernel instantiation (experiments / tests)
   int dwt_fixed = 0;        // > 0: per-pass fixed cost of the FWT planner's model, 0.01 ps per sample (experiments)
   int dwt_k0 = 0;           // > 0: levels fused by the first FWT / WPT pass (experiments; 0 = planner's choice)

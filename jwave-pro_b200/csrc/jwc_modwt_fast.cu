@@ -143,8 +143,12 @@ __device__ __forceinline__ int64_t wrap_row(int64_t i, int64_t nd) {
 #ifndef JWC_INV_MINB
 #define JWC_INV_MINB 2
 #endif
+#ifndef JWC_FWD_MAXT
+#define JWC_FWD_MAXT 256        // launch bounds of the forward kernel (experiments: 512 x 2 for the short filters)
+#define JWC_FWD_MINB_SHORT 3
+#endif
 template <int L, int R, bool WRAP>
-__global__ void __launch_bounds__(256, (L > 10 ? JWC_FWD_MINB : 3)) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
+__global__ void __launch_bounds__(JWC_FWD_MAXT, (L > 10 ? JWC_FWD_MINB : JWC_FWD_MINB_SHORT)) modwt_fwd_pass_kernel(const __grid_constant__ FwdPassArgs a,
                                                              const __grid_constant__ FilterPair f) {
   // shared memory is addressed as smem[int offset] everywhere: keeps the accesses plain LDS/STS with register offsets
   // Long filters run ONE instantiation (WRAP = true) for every shape and test RowMap::wrap at run time: with both
@@ -406,7 +410,7 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
   pin.smem_budget = ctx->tune.modwt_smem > 0 ? ctx->tune.modwt_smem : (L <= 10 ? 113000 : 75776);
   if (pin.smem_budget > dev.max_smem_optin) pin.smem_budget = dev.max_smem_optin;
   pin.tile_override = ctx->tune.modwt_tile; pin.group_override = ctx->tune.modwt_group;
-  pin.threads_override = ctx->tune.modwt_threads;
+  pin.threads_override = ctx->tune.modwt_threads_fwd > 0 ? ctx->tune.modwt_threads_fwd : ctx->tune.modwt_threads;
   pin.logp_override = ctx->tune.modwt_logp; pin.tile_deep_override = ctx->tune.modwt_tile_deep;
   pin.plan_override = ctx->tune.modwt_plan_fwd;
   pin.inverse = false;
