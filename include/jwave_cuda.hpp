@@ -120,11 +120,18 @@ class WaveletTransform : public BasicTransform {
     const int rc = fn(ctx_->handle(), in, out, batch, rows, cols, lvlM, lvlN, f0.data(), f1.data(), (int)f0.size(), flags);
     if (rc != JWC_OK) throw std::runtime_error(std::string(what) + " failed: " + jwc_last_error());
   }
+  using Fn3 = int (*)(jwc_ctx*, const double*, double*, int64_t, int64_t, int64_t, int64_t, int, int, int, const double*, const double*, int, unsigned);
+  void call3d(Fn3 fn, const char* what, const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r, int lvlP,
+              int lvlQ, int lvlR, const std::vector<double>& f0, const std::vector<double>& f1, unsigned flags = 0) const {
+    const int rc = fn(ctx_->handle(), in, out, batch, p, q, r, lvlP, lvlQ, lvlR, f0.data(), f1.data(), (int)f0.size(), flags);
+    if (rc != JWC_OK) throw std::runtime_error(std::string(what) + " failed: " + jwc_last_error());
+  }
   Wavelet wavelet_;
   std::shared_ptr<Context> ctx_;
 };
 
 using Matrix = std::vector<std::vector<double>>;
+using Space = std::vector<Matrix>;   // double[][][] of the reference's 3-D overloads
 
 namespace detail {
 inline std::vector<double> flatten(const Matrix& m) {
@@ -141,6 +148,22 @@ inline Matrix unflatten(const std::vector<double>& flat, size_t rows, size_t col
   Matrix m(rows, std::vector<double>(cols));
   for (size_t i = 0; i < rows; i++) std::copy(flat.begin() + (long)(i * cols), flat.begin() + (long)((i + 1) * cols), m[i].begin());
   return m;
+}
+inline std::vector<double> flatten3(const Space& s) {
+  std::vector<double> flat;
+  for (const auto& m : s) {
+    if (m.size() != s[0].size()) throw JWaveFailure("BasicTransform - given space is not a box");
+    const std::vector<double> f = flatten(m);
+    if (!m.empty() && m[0].size() != s[0][0].size()) throw JWaveFailure("BasicTransform - given space is not a box");
+    flat.insert(flat.end(), f.begin(), f.end());
+  }
+  return flat;
+}
+inline Space unflatten3(const std::vector<double>& flat, size_t p, size_t q, size_t r) {
+  Space s(p);
+  for (size_t i = 0; i < p; i++)
+    s[i] = unflatten(std::vector<double>(flat.begin() + (long)(i * q * r), flat.begin() + (long)((i + 1) * q * r)), q, r);
+  return s;
 }
 }  // namespace detail
 
@@ -213,6 +236,40 @@ class CudaFastWaveletTransform : public WaveletTransform {
   Matrix reverse(const Matrix& matHilb) const {
     return reverse(matHilb, calcExponent((int64_t)matHilb.size()), calcExponent((int64_t)matHilb.at(0).size()));
   }
+
+  // 3-D: BasicTransform.java:487-640 forward / reverse(double[][][][, lvlP, lvlQ, lvlR]): the 2-D transform of every matrix
+  //      spc[i] with (lvlP, lvlQ) -- rows of length r with lvlQ, columns of length q with lvlP --, then every line along
+  //      the first axis (length p) with lvlR; the reverse keeps that order.  [batch][p][q][r] row-major for the batch form.
+  void forward3DBatch(const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r, int lvlP, int lvlQ, int lvlR) const {
+    detail::check_pyramid("FastWaveletTransform", "forward", r, lvlQ);
+    detail::check_pyramid("FastWaveletTransform", "forward", q, lvlP);
+    detail::check_pyramid("FastWaveletTransform", "forward", p, lvlR);
+    call3d(jwc_fwt3d_forward, "jwc_fwt3d_forward", in, out, batch, p, q, r, lvlP, lvlQ, lvlR, wavelet_.getScalingDeComposition(), wavelet_.getWaveletDeComposition());
+  }
+  void reverse3DBatch(const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r, int lvlP, int lvlQ, int lvlR) const {
+    detail::check_pyramid("FastWaveletTransform", "reverse", r, lvlQ);
+    detail::check_pyramid("FastWaveletTransform", "reverse", q, lvlP);
+    detail::check_pyramid("FastWaveletTransform", "reverse", p, lvlR);
+    call3d(jwc_fwt3d_inverse, "jwc_fwt3d_inverse", in, out, batch, p, q, r, lvlP, lvlQ, lvlR, wavelet_.getScalingReConstruction(), wavelet_.getWaveletReConstruction());
+  }
+  Space forward(const Space& spcTime, int lvlP, int lvlQ, int lvlR) const {
+    const std::vector<double> flat = detail::flatten3(spcTime);
+    std::vector<double> out(flat.size());
+    forward3DBatch(flat.data(), out.data(), 1, (int64_t)spcTime.size(), (int64_t)spcTime.at(0).size(), (int64_t)spcTime.at(0).at(0).size(), lvlP, lvlQ, lvlR);
+    return detail::unflatten3(out, spcTime.size(), spcTime[0].size(), spcTime[0][0].size());
+  }
+  Space forward(const Space& spcTime) const {   // :490-493: the exponents of the three dimensions, in this order
+    return forward(spcTime, calcExponent((int64_t)spcTime.size()), calcExponent((int64_t)spcTime.at(0).size()), calcExponent((int64_t)spcTime.at(0).at(0).size()));
+  }
+  Space reverse(const Space& spcHilb, int lvlP, int lvlQ, int lvlR) const {
+    const std::vector<double> flat = detail::flatten3(spcHilb);
+    std::vector<double> out(flat.size());
+    reverse3DBatch(flat.data(), out.data(), 1, (int64_t)spcHilb.size(), (int64_t)spcHilb.at(0).size(), (int64_t)spcHilb.at(0).at(0).size(), lvlP, lvlQ, lvlR);
+    return detail::unflatten3(out, spcHilb.size(), spcHilb[0].size(), spcHilb[0][0].size());
+  }
+  Space reverse(const Space& spcHilb) const {
+    return reverse(spcHilb, calcExponent((int64_t)spcHilb.size()), calcExponent((int64_t)spcHilb.at(0).size()), calcExponent((int64_t)spcHilb.at(0).at(0).size()));
+  }
 };
 
 class CudaWaveletPacketTransform : public WaveletTransform {
@@ -273,6 +330,40 @@ class CudaWaveletPacketTransform : public WaveletTransform {
   }
   Matrix reverse(const Matrix& matHilb) const {
     return reverse(matHilb, calcExponent((int64_t)matHilb.size()), calcExponent((int64_t)matHilb.at(0).size()));
+  }
+
+  // 3-D: BasicTransform.java:487-640 forward / reverse(double[][][][, lvlP, lvlQ, lvlR]): the 2-D transform of every matrix
+  //      spc[i] with (lvlP, lvlQ) -- rows of length r with lvlQ, columns of length q with lvlP --, then every line along
+  //      the first axis (length p) with lvlR; the reverse keeps that order.  [batch][p][q][r] row-major for the batch form.
+  void forward3DBatch(const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r, int lvlP, int lvlQ, int lvlR) const {
+    detail::check_pyramid("WaveletPacketTransform", "forward", r, lvlQ);
+    detail::check_pyramid("WaveletPacketTransform", "forward", q, lvlP);
+    detail::check_pyramid("WaveletPacketTransform", "forward", p, lvlR);
+    call3d(jwc_wpt3d_forward, "jwc_wpt3d_forward", in, out, batch, p, q, r, lvlP, lvlQ, lvlR, wavelet_.getScalingDeComposition(), wavelet_.getWaveletDeComposition());
+  }
+  void reverse3DBatch(const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r, int lvlP, int lvlQ, int lvlR) const {
+    detail::check_pyramid("WaveletPacketTransform", "reverse", r, lvlQ);
+    detail::check_pyramid("WaveletPacketTransform", "reverse", q, lvlP);
+    detail::check_pyramid("WaveletPacketTransform", "reverse", p, lvlR);
+    call3d(jwc_wpt3d_inverse, "jwc_wpt3d_inverse", in, out, batch, p, q, r, lvlP, lvlQ, lvlR, wavelet_.getScalingReConstruction(), wavelet_.getWaveletReConstruction());
+  }
+  Space forward(const Space& spcTime, int lvlP, int lvlQ, int lvlR) const {
+    const std::vector<double> flat = detail::flatten3(spcTime);
+    std::vector<double> out(flat.size());
+    forward3DBatch(flat.data(), out.data(), 1, (int64_t)spcTime.size(), (int64_t)spcTime.at(0).size(), (int64_t)spcTime.at(0).at(0).size(), lvlP, lvlQ, lvlR);
+    return detail::unflatten3(out, spcTime.size(), spcTime[0].size(), spcTime[0][0].size());
+  }
+  Space forward(const Space& spcTime) const {   // :490-493: the exponents of the three dimensions, in this order
+    return forward(spcTime, calcExponent((int64_t)spcTime.size()), calcExponent((int64_t)spcTime.at(0).size()), calcExponent((int64_t)spcTime.at(0).at(0).size()));
+  }
+  Space reverse(const Space& spcHilb, int lvlP, int lvlQ, int lvlR) const {
+    const std::vector<double> flat = detail::flatten3(spcHilb);
+    std::vector<double> out(flat.size());
+    reverse3DBatch(flat.data(), out.data(), 1, (int64_t)spcHilb.size(), (int64_t)spcHilb.at(0).size(), (int64_t)spcHilb.at(0).at(0).size(), lvlP, lvlQ, lvlR);
+    return detail::unflatten3(out, spcHilb.size(), spcHilb[0].size(), spcHilb[0][0].size());
+  }
+  Space reverse(const Space& spcHilb) const {
+    return reverse(spcHilb, calcExponent((int64_t)spcHilb.size()), calcExponent((int64_t)spcHilb.at(0).size()), calcExponent((int64_t)spcHilb.at(0).at(0).size()));
   }
 };
 

@@ -217,6 +217,36 @@ JWC_API int jwc_wpt2d_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const do
                                   int64_t batch, int64_t rows, int64_t cols, int lvl_m, int lvl_n, const double* lo,
                                   const double* hi, int L, unsigned flags);
 
+/* ---- 3-D FWT / WPT ----------------------------------------------------------------------------------
+ * The reference's space overloads: transforms/BasicTransform.java:487-565 forward(double[][][] spcTime, lvlP, lvlQ, lvlR)
+ * sends every matrix spcTime[i] ([q][r]) through the 2-D forward(mat, lvlP, lvlQ) -- i.e. its rows (length r) with lvlQ
+ * levels and its columns (length q) with lvlP levels -- and then every line along the first axis (length p) through the
+ * 1-D forward(line, lvlR); :579-640 reverse(double[][][], lvlP, lvlQ, lvlR) keeps that order (2-D reverse of every
+ * matrix first, then the first axis).  The level arguments are passed through exactly as the reference uses them, so
+ * lvl_p must be <= log2(q), lvl_q <= log2(r) and lvl_r <= log2(p) (for a cube: any level up to log2 of the edge).
+ * in, out: [batch][p][q][r] row-major, p, q, r all 2^p.  The first-axis pass is the 2-D column pass on the view
+ * [batch][p][q * r], in place on the row-major space (no transposes). */
+JWC_API int jwc_fwt3d_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r,
+                              int lvl_p, int lvl_q, int lvl_r, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt3d_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r,
+                              int lvl_p, int lvl_q, int lvl_r, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt3d_forward(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r,
+                              int lvl_p, int lvl_q, int lvl_r, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt3d_inverse(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t p, int64_t q, int64_t r,
+                              int lvl_p, int lvl_q, int lvl_r, const double* lo, const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt3d_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out, int64_t batch,
+                                  int64_t p, int64_t q, int64_t r, int lvl_p, int lvl_q, int lvl_r, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+JWC_API int jwc_fwt3d_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out, int64_t batch,
+                                  int64_t p, int64_t q, int64_t r, int lvl_p, int lvl_q, int lvl_r, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt3d_forward_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out, int64_t batch,
+                                  int64_t p, int64_t q, int64_t r, int lvl_p, int lvl_q, int lvl_r, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+JWC_API int jwc_wpt3d_inverse_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out, int64_t batch,
+                                  int64_t p, int64_t q, int64_t r, int lvl_p, int lvl_q, int lvl_r, const double* lo,
+                                  const double* hi, int L, unsigned flags);
+
 /* ---- magnitude thresholding of a coefficient buffer ---------------------------------------------------------
  * compressions/CompressorMagnitude.java:78-140 + compressions/Compressor.java:97-170: magnitude = mean |c| over all
  * `count` values (array, matrix or space alike); out[i] = in[i] if |in[i]| >= magnitude * threshold, else 0.

@@ -65,6 +65,29 @@ public class CudaFastWaveletTransform extends FastWaveletTransform {
         _wavelet.getScalingReConstruction(), _wavelet.getWaveletReConstruction(), 0);
   }
 
+  /**
+   * 3-D forward, BasicTransform.java:509-565: the 2-D forward(mat, lvlP, lvlQ) of every matrix spcTime[i] -- rows of
+   * length r with lvlQ, columns of length q with lvlP -- then every line along the first axis with lvlR; here the 2-D
+   * passes of all matrices and one in-place first-axis pass on the device (jwc_fwt3d_forward).  forward(double[][][])
+   * (:487-495) delegates here with the exponents of the three dimensions.
+   */
+  @Override public double[][][] forward(double[][][] spcTime, int lvlP, int lvlQ, int lvlR) throws JWaveException {
+    check(spcTime[0][0].length, lvlQ, "forward");
+    check(spcTime[0].length, lvlP, "forward");
+    check(spcTime.length, lvlR, "forward");
+    return JwcNative.run3d(JwcNative.FWT3D_FORWARD, CudaContext.get(), spcTime, lvlP, lvlQ, lvlR,
+        _wavelet.getScalingDeComposition(), _wavelet.getWaveletDeComposition(), 0);
+  }
+
+  /** 3-D reverse, BasicTransform.java:602-640: the 2-D reverse of every matrix first, then the first axis (lvlR). */
+  @Override public double[][][] reverse(double[][][] spcHilb, int lvlP, int lvlQ, int lvlR) throws JWaveException {
+    check(spcHilb[0][0].length, lvlQ, "reverse");
+    check(spcHilb[0].length, lvlP, "reverse");
+    check(spcHilb.length, lvlR, "reverse");
+    return JwcNative.run3d(JwcNative.FWT3D_INVERSE, CudaContext.get(), spcHilb, lvlP, lvlQ, lvlR,
+        _wavelet.getScalingReConstruction(), _wavelet.getWaveletReConstruction(), 0);
+  }
+
   private void check(int length, int level, String dir) throws JWaveException {
     if (!isBinary(length))
       throw new JWaveFailure("FastWaveletTransform#" + dir + " - "

@@ -34,6 +34,10 @@ public final class JwcNative {
   private static final String[] NAMES_2D = {
       "jwc_fwt2d_forward", "jwc_fwt2d_inverse", "jwc_wpt2d_forward", "jwc_wpt2d_inverse" };
   public static final int FWT2D_FORWARD = 0, FWT2D_INVERSE = 1, WPT2D_FORWARD = 2, WPT2D_INVERSE = 3;
+  private static final MethodHandle[] TRANSFORMS_3D = new MethodHandle[4];
+  private static final String[] NAMES_3D = {
+      "jwc_fwt3d_forward", "jwc_fwt3d_inverse", "jwc_wpt3d_forward", "jwc_wpt3d_inverse" };
+  public static final int FWT3D_FORWARD = 0, FWT3D_INVERSE = 1, WPT3D_FORWARD = 2, WPT3D_INVERSE = 3;
   private static final MethodHandle WINDOWS;
   private static final MethodHandle[] TRANSFORMS_AED = new MethodHandle[4];
   private static final String[] NAMES_AED = {
@@ -65,6 +69,11 @@ public final class JwcNative {
     FunctionDescriptor t2 = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG,
         JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT);
     for (int i = 0; i < NAMES_2D.length; i++) TRANSFORMS_2D[i] = handle(NAMES_2D[i], t2);
+    // int f(jwc_ctx*, const double* in, double* out, int64 batch, int64 p, int64 q, int64 r, int lvlP, int lvlQ,
+    //       int lvlR, const double* lo, const double* hi, int L, unsigned flags)
+    FunctionDescriptor t3 = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG,
+        JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT);
+    for (int i = 0; i < NAMES_3D.length; i++) TRANSFORMS_3D[i] = handle(NAMES_3D[i], t3);
     // int f(jwc_ctx*, const double* in, double* out, int64 batch, int64 n, const double* lo, const double* hi, int L,
     //       unsigned flags)   -- n arbitrary (Ancient-Egyptian blocks)
     FunctionDescriptor ta = FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS,
@@ -181,6 +190,41 @@ public final class JwcNative {
       double[][] out = new double[rows][cols];
       for (int i = 0; i < rows; i++)
         MemorySegment.copy(so, JAVA_DOUBLE, (long) i * cols * Double.BYTES, out[i], 0, cols);
+      return out;
+    }
+  }
+
+  /** Spaces [batch][p][q][r] (BasicTransform.java:487-640), one native call. */
+  public static void run3d(int which, MemorySegment ctx, MemorySegment in, MemorySegment out, long batch, long p,
+      long q, long r, int lvlP, int lvlQ, int lvlR, double[] f0, double[] f1, int flags) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment s0 = a.allocateArray(JAVA_DOUBLE, f0);
+      MemorySegment s1 = a.allocateArray(JAVA_DOUBLE, f1);
+      int rc = (int) TRANSFORMS_3D[which].invokeExact(ctx, in, out, batch, p, q, r, lvlP, lvlQ, lvlR, s0, s1,
+          f0.length, flags);
+      if (rc != 0) throw new IllegalStateException(NAMES_3D[which] + " failed (" + rc + "): " + lastError());
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  /** double[][][] convenience: flatten, transform, un-flatten (the reference allocates a fresh space as well). */
+  public static double[][][] run3d(int which, MemorySegment ctx, double[][][] spc, int lvlP, int lvlQ, int lvlR,
+      double[] f0, double[] f1, int flags) {
+    int p = spc.length, q = spc[0].length, r = spc[0][0].length;
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment si = a.allocateArray(JAVA_DOUBLE, (long) p * q * r);
+      MemorySegment so = a.allocateArray(JAVA_DOUBLE, (long) p * q * r);
+      for (int i = 0; i < p; i++)
+        for (int j = 0; j < q; j++)
+          MemorySegment.copy(spc[i][j], 0, si, JAVA_DOUBLE, ((long) i * q + j) * r * Double.BYTES, r);
+      run3d(which, ctx, si, so, 1, p, q, r, lvlP, lvlQ, lvlR, f0, f1, flags);
+      double[][][] out = new double[p][q][r];
+      for (int i = 0; i < p; i++)
+        for (int j = 0; j < q; j++)
+          MemorySegment.copy(so, JAVA_DOUBLE, ((long) i * q + j) * r * Double.BYTES, out[i][j], 0, r);
       return out;
     }
   }

@@ -25,6 +25,7 @@ MAX_TAPS = 64
 _TRANSFORMS = ["modwt_forward", "modwt_inverse", "fwt_forward", "fwt_inverse", "wpt_forward", "wpt_inverse"]
 _TRANSFORMS_AED = ["fwt_aed_forward", "fwt_aed_inverse", "wpt_aed_forward", "wpt_aed_inverse"]
 _TRANSFORMS_2D = ["fwt2d_forward", "fwt2d_inverse", "wpt2d_forward", "wpt2d_inverse"]
+_TRANSFORMS_3D = ["fwt3d_forward", "fwt3d_inverse", "wpt3d_forward", "wpt3d_inverse"]
 SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal", "jwc_last_error", "jwc_version",
             "jwc_launch_count", "jwc_set_tuning", "jwc_get_tuning", "jwc_alloc_pinned", "jwc_free_pinned",
             "jwc_alloc_device", "jwc_free_device", "jwc_copy_to_device", "jwc_copy_to_host", "jwc_synchronize",
@@ -37,6 +38,7 @@ SYMBOLS = (["jwc_create", "jwc_destroy", "jwc_num_devices", "jwc_device_ordinal"
               "jwc_compress_magnitude_dev", "jwc_modwt_forward_windows_compress_dev"]
            + ["jwc_diag_dfma_tflops", "jwc_diag_copy_gbs"]
            + ["jwc_" + t for t in _TRANSFORMS_2D] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_2D]
+           + ["jwc_" + t for t in _TRANSFORMS_3D] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_3D]
            + ["jwc_" + t for t in _TRANSFORMS_AED] + ["jwc_" + t + "_dev" for t in _TRANSFORMS_AED])
 
 _lib = None
@@ -123,6 +125,13 @@ def load():
             fn.restype = _int
             fn = getattr(lib, "jwc_" + t + "_dev")
             fn.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _dp, _dp, _int, _u32]
+            fn.restype = _int
+        for t in _TRANSFORMS_3D:
+            fn = getattr(lib, "jwc_" + t)
+            fn.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _dp, _dp, _int, _u32]
+            fn.restype = _int
+            fn = getattr(lib, "jwc_" + t + "_dev")
+            fn.argtypes = [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _dp, _dp, _int, _u32]
             fn.restype = _int
         lib.jwc_diag_dfma_tflops.argtypes = [_vp, _int, _dp]
         lib.jwc_diag_dfma_tflops.restype = _int

@@ -39,6 +39,10 @@ enum class Op { ModwtFwd, ModwtInv, FwtFwd, FwtInv, WptFwd, WptInv };
 struct Dim2 {
   int64_t rows = 0;
   int lvl_m = 0;
+  // 3-D (BasicTransform.java:487-640): a unit is a space [depth][rows][n]; every [rows][n] matrix goes through the 2-D
+  // transform, then every line along the first axis through the 1-D transform with lvl_depth levels
+  int64_t depth = 0;
+  int lvl_depth = 0;
   bool aed = false;   // Ancient-Egyptian decomposition of arbitrary-length signals (levels ignored: full depth per block)
   int64_t hop = 0;    // > 0: forward MODWT of overlapping windows of ONE series; window b starts at b * hop
 };
@@ -58,6 +62,14 @@ int ilog2(int64_t n) {
 
 int validate(Op op, const void* in, const void* out, int64_t batch, int64_t n, int levels, const double* f0,
              const double* f1, int L, const Dim2& d2 = Dim2()) {
+  if (d2.depth != 0) {
+    JWC_REQUIRE(d2.rows != 0, "a space needs its matrix dimensions");
+    JWC_REQUIRE(is_pow2(d2.depth), "given space depth is not 2^p (got %lld)", (long long)d2.depth);
+    JWC_REQUIRE(d2.lvl_depth >= 0 && d2.lvl_depth <= ilog2(d2.depth),
+                "given level %d is out of range for given array of length %lld", d2.lvl_depth, (long long)d2.depth);
+    JWC_REQUIRE(d2.depth < ((int64_t)1 << 40) / (n > 0 ? n : 1) / (d2.rows > 0 ? d2.rows : 1), "space %lld x %lld x %lld too large",
+                (long long)d2.depth, (long long)d2.rows, (long long)n);
+  }
   if (d2.rows != 0) {
     JWC_REQUIRE(op != Op::ModwtFwd && op != Op::ModwtInv, "no 2-D MODWT");
     JWC_REQUIRE(is_pow2(d2.rows), "given matrix height is not 2^p (got %lld)", (long long)d2.rows);
@@ -127,6 +139,26 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
     }
     return JWC_OK;
   }
+  if (d2.depth != 0) {
+    // BasicTransform.java:509-565 forward(double[][][], lvlP, lvlQ, lvlR): the 2-D transform of every [rows][n] matrix,
+    // then every line along the first axis with lvlR levels; :602-640 reverse keeps that order (2-D reverse first).
+    // The first-axis pass is the 2-D column pass on the view [batch][depth][rows * n] -- in place on the row-major
+    // space, a warp's access is one contiguous row segment.
+    const bool tree = (op == Op::WptFwd || op == Op::WptInv);
+    const bool fwd = (op == Op::FwtFwd || op == Op::WptFwd);
+    Dim2 mat = d2;
+    mat.depth = 0;
+    mat.lvl_depth = 0;
+    if (dwt2d_column_steps(d2.depth, d2.lvl_depth) == 0)
+      return run_device(ctx, dev, st, op, d_in, d_out, batch * d2.depth, n, levels, fp, L, flags, mat);
+    Scratch ws(ctx, dev, st);
+    double* mid = ws.get((size_t)(batch * d2.depth * d2.rows * n));
+    if (!mid) { set_error("scratch allocation failed"); return JWC_ERR_NOMEM; }
+    const int rc = run_device(ctx, dev, st, op, d_in, mid, batch * d2.depth, n, levels, fp, L, flags, mat);
+    if (rc != JWC_OK) return rc;
+    return fwd ? dwt2d_columns_forward(ctx, dev, st, mid, d_out, batch, d2.depth, d2.rows * n, d2.lvl_depth, fp, L, tree, exact)
+               : dwt2d_columns_inverse(ctx, dev, st, mid, d_out, batch, d2.depth, d2.rows * n, d2.lvl_depth, fp, L, tree, exact);
+  }
   if (d2.rows != 0) {
     // BasicTransform.java:361-399 forward: rows (lvlN) then columns (lvlM); :436-474 reverse: columns, then rows.
     const bool tree = (op == Op::WptFwd || op == Op::WptInv);
@@ -184,7 +216,7 @@ int run_device(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, Op op, cons
 void io_sizes(Op op, int64_t n, int levels, int64_t* in_per, int64_t* out_per, const Dim2& d2 = Dim2()) {
   *in_per = n;
   *out_per = n;
-  if (d2.rows != 0) *in_per = *out_per = n * d2.rows;
+  if (d2.rows != 0) *in_per = *out_per = n * d2.rows * (d2.depth != 0 ? d2.depth : 1);
   // sliding windows: *in_per stays n (one window); consecutive windows start d2.hop apart (see in_step below)
   if (op == Op::ModwtFwd) *out_per = (int64_t)(levels + 1) * n;
   if (op == Op::ModwtInv) *in_per = (int64_t)(levels + 1) * n;
@@ -738,6 +770,28 @@ JWC_DEFINE(wpt_inverse, Op::WptInv)
     return run_dev(ctx, slot, stream, OP, d_in, d_out, batch, cols, lvl_n, f0, f1, L, flags, d2);                   \
   }
 
+// 3-D: spaces [batch][p][q][r]; the reference's argument order forward(spc, lvlP, lvlQ, lvlR) with ITS use of them: the 2-D
+// transform of every [q][r] matrix gets (lvlM, lvlN) = (lvlP, lvlQ), the lines along the first axis get lvlR
+#define JWC_DEFINE_3D(name, OP)                                                                                     \
+  JWC_API int jwc_##name(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int64_t p, int64_t q,         \
+                         int64_t r, int lvl_p, int lvl_q, int lvl_r, const double* f0, const double* f1, int L,     \
+                         unsigned flags) {                                                                          \
+    if (p < 1 || q < 1) { set_error("space dimensions must be >= 1 (got %lld x %lld)", (long long)p, (long long)q); return JWC_ERR_INVALID; } \
+    Dim2 d2;                                                                                                        \
+    d2.depth = p; d2.lvl_depth = lvl_r;                                                                             \
+    d2.rows = q; d2.lvl_m = lvl_p;                                                                                  \
+    return run_host(ctx, OP, in, out, batch, r, lvl_q, f0, f1, L, flags, d2);                                       \
+  }                                                                                                                 \
+  JWC_API int jwc_##name##_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,             \
+                               int64_t batch, int64_t p, int64_t q, int64_t r, int lvl_p, int lvl_q, int lvl_r,     \
+                               const double* f0, const double* f1, int L, unsigned flags) {                         \
+    if (p < 1 || q < 1) { set_error("space dimensions must be >= 1 (got %lld x %lld)", (long long)p, (long long)q); return JWC_ERR_INVALID; } \
+    Dim2 d2;                                                                                                        \
+    d2.depth = p; d2.lvl_depth = lvl_r;                                                                             \
+    d2.rows = q; d2.lvl_m = lvl_p;                                                                                  \
+    return run_dev(ctx, slot, stream, OP, d_in, d_out, batch, r, lvl_q, f0, f1, L, flags, d2);                      \
+  }
+
 // CompressorMagnitude.compress: out = in where |in| >= mean|in| * threshold, else 0; *magnitude = mean|in|
 JWC_API int jwc_compress_magnitude_dev(jwc_ctx* ctx, int slot, void* stream, const double* d_in, double* d_out,
                                        int64_t count, double threshold, double* d_magnitude) {
@@ -894,6 +948,11 @@ JWC_DEFINE_2D(fwt2d_forward, Op::FwtFwd)
 JWC_DEFINE_2D(fwt2d_inverse, Op::FwtInv)
 JWC_DEFINE_2D(wpt2d_forward, Op::WptFwd)
 JWC_DEFINE_2D(wpt2d_inverse, Op::WptInv)
+
+JWC_DEFINE_3D(fwt3d_forward, Op::FwtFwd)
+JWC_DEFINE_3D(fwt3d_inverse, Op::FwtInv)
+JWC_DEFINE_3D(wpt3d_forward, Op::WptFwd)
+JWC_DEFINE_3D(wpt3d_inverse, Op::WptInv)
 
 static int dwt_split_entry(jwc_ctx* ctx, bool inverse, bool tree, const double* const* d_in, double* const* d_out,
                            int64_t n, int levels, const double* lo, const double* hi, int L, unsigned flags) {

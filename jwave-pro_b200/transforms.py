@@ -106,9 +106,12 @@ class WaveletTransform(BasicTransform):
             raise RuntimeError("%s_dev failed (%d): %s" % (fn_name, rc, _native.last_error()))
 
     # ---- full-depth defaults (WaveletTransform.java:77-112) --------------------------------------------------
-    def forward(self, arrTime, level=None, lvlN=None):
+    def forward(self, arrTime, level=None, lvlN=None, lvlR=None):
         """1-D: forward(arrTime[, level]).  A 2-D array selects the reference's matrix overloads
-        forward(double[][]) / forward(double[][], lvlM, lvlN) (BasicTransform.java:330-399)."""
+        forward(double[][]) / forward(double[][], lvlM, lvlN) (BasicTransform.java:330-399), a 3-D array its space
+        overloads forward(double[][][]) / forward(double[][][], lvlP, lvlQ, lvlR) (:487-565)."""
+        if np.ndim(arrTime) == 3:
+            return self.forward3D(arrTime, level, lvlN, lvlR)
         if np.ndim(arrTime) == 2:
             return self.forward2D(arrTime, level, lvlN)
         if level is None:
@@ -119,7 +122,9 @@ class WaveletTransform(BasicTransform):
             level = self.calcExponent(len(arrTime))
         return self._forward_level(arrTime, level)
 
-    def reverse(self, arrHilb, level=None, lvlN=None):
+    def reverse(self, arrHilb, level=None, lvlN=None, lvlR=None):
+        if np.ndim(arrHilb) == 3:
+            return self.reverse3D(arrHilb, level, lvlN, lvlR)
         if np.ndim(arrHilb) == 2:
             return self.reverse2D(arrHilb, level, lvlN)
         if level is None:
@@ -240,6 +245,77 @@ class _CudaPyramidBase(WaveletTransform):
     def reverse2D(self, matHilb, lvlM=None, lvlN=None, flags=0):
         C = _as_f64(matHilb)
         return self.reverse2DBatch(C[None, :, :], lvlM, lvlN, flags)[0]
+
+    # ---- 3-D (BasicTransform.java:487-640) --------------------------------------------------------------------
+    def _levels3d(self, p, q, r, lvlP, lvlQ, lvlR, direction):
+        if lvlP is None:      # BasicTransform.java:490-493 / :582-585: the exponents of the three dimensions, in this order
+            lvlP = self.calcExponent(p)
+        if lvlQ is None:
+            lvlQ = self.calcExponent(q)
+        if lvlR is None:
+            lvlR = self.calcExponent(r)
+        # the reference hands (lvlP, lvlQ) to the 2-D transform of every [q][r] matrix -- rows of length r with lvlQ,
+        # columns of length q with lvlP -- and lvlR to the lines of length p along the first axis (:532, :555)
+        self._check(r, lvlQ, direction)
+        self._check(q, lvlP, direction)
+        self._check(p, lvlR, direction)
+        return lvlP, lvlQ, lvlR
+
+    def _call3d(self, fn_name, src, dst, batch, p, q, r, lvls, f0, f1, flags):
+        lib = _native.load()
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        rc = getattr(lib, fn_name)(self._context().handle, src.ctypes.data, dst.ctypes.data, batch, p, q, r, lvls[0],
+                                   lvls[1], lvls[2], _ptr(f0), _ptr(f1), len(f0), flags)
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (fn_name, rc, _native.last_error()))
+
+    def forward3DBatch(self, spcTime, lvlP=None, lvlQ=None, lvlR=None, flags=0, out=None):
+        """[batch][p][q][r] -> same shape; every space as forward(double[][][], lvlP, lvlQ, lvlR)."""
+        X = _as_f64(spcTime)
+        B, p, q, r = X.shape
+        lvls = self._levels3d(p, q, r, lvlP, lvlQ, lvlR, "forward")
+        out = _out_buffer(out, X.shape)
+        self._call3d(self._fn + "3d_forward", X, out, B, p, q, r, lvls, self._wavelet.getScalingDeComposition(),
+                     self._wavelet.getWaveletDeComposition(), flags)
+        return out
+
+    def reverse3DBatch(self, spcHilb, lvlP=None, lvlQ=None, lvlR=None, flags=0, out=None):
+        C = _as_f64(spcHilb)
+        B, p, q, r = C.shape
+        lvls = self._levels3d(p, q, r, lvlP, lvlQ, lvlR, "reverse")
+        out = _out_buffer(out, C.shape)
+        self._call3d(self._fn + "3d_inverse", C, out, B, p, q, r, lvls, self._wavelet.getScalingReConstruction(),
+                     self._wavelet.getWaveletReConstruction(), flags)
+        return out
+
+    def forward3D(self, spcTime, lvlP=None, lvlQ=None, lvlR=None, flags=0):
+        X = _as_f64(spcTime)
+        return self.forward3DBatch(X[None], lvlP, lvlQ, lvlR, flags)[0]
+
+    def reverse3D(self, spcHilb, lvlP=None, lvlQ=None, lvlR=None, flags=0):
+        C = _as_f64(spcHilb)
+        return self.reverse3DBatch(C[None], lvlP, lvlQ, lvlR, flags)[0]
+
+    def _call3d_dev(self, fn_name, d_src, d_dst, batch, p, q, r, lvls, f0, f1, flags, stream, slot):
+        lib = _native.load()
+        f0, f1 = _as_f64(f0), _as_f64(f1)
+        rc = getattr(lib, fn_name + "_dev")(self._context().handle, slot, ctypes.c_void_p(stream if stream else 1),
+                                            ctypes.c_void_p(d_src), ctypes.c_void_p(d_dst), batch, p, q, r, lvls[0],
+                                            lvls[1], lvls[2], _ptr(f0), _ptr(f1), len(f0), flags)
+        if rc != 0:
+            raise RuntimeError("%s_dev failed (%d): %s" % (fn_name, rc, _native.last_error()))
+
+    def forward3DDevice(self, d_in, d_out, batch, p, q, r, lvlP, lvlQ, lvlR, stream=0, flags=0, slot=0):
+        lvls = self._levels3d(p, q, r, lvlP, lvlQ, lvlR, "forward")
+        self._call3d_dev(self._fn + "3d_forward", d_in, d_out, batch, p, q, r, lvls,
+                         self._wavelet.getScalingDeComposition(), self._wavelet.getWaveletDeComposition(), flags,
+                         stream, slot)
+
+    def reverse3DDevice(self, d_in, d_out, batch, p, q, r, lvlP, lvlQ, lvlR, stream=0, flags=0, slot=0):
+        lvls = self._levels3d(p, q, r, lvlP, lvlQ, lvlR, "reverse")
+        self._call3d_dev(self._fn + "3d_inverse", d_in, d_out, batch, p, q, r, lvls,
+                         self._wavelet.getScalingReConstruction(), self._wavelet.getWaveletReConstruction(), flags,
+                         stream, slot)
 
     def _call2d_dev(self, fn_name, d_src, d_dst, batch, rows, cols, lvlM, lvlN, f0, f1, flags, stream, slot):
         lib = _native.load()

@@ -207,6 +207,20 @@ def batch2d(kind, x, lvl_m, lvl_n, f0, f1, reverse=False, nthreads=1):
     return along_rows(along_cols(x, lvl_m), lvl_n)
 
 
+def batch3d(kind, x, lvl_p, lvl_q, lvl_r, f0, f1, reverse=False, nthreads=1):
+    """3-D FWT / WPT of every space of x (batch, p, q, r), composed as the reference composes it:
+    transforms/BasicTransform.java:509-565 forward(double[][][], lvlP, lvlQ, lvlR) -- the 2-D forward(mat, lvlP, lvlQ) of
+    every matrix x[b][i] (so the rows of length r get lvlQ, the columns of length q get lvlP), then every line along the
+    first axis with lvlR -- and :602-640 reverse, which keeps that order (2-D reverse first, then the first axis)."""
+    x = _c(x)
+    B, P, Q, R = x.shape
+    op = kind + ("_rev" if reverse else "_fwd")
+    mats = batch2d(kind, x.reshape(B * P, Q, R), lvl_p, lvl_q, f0, f1, reverse=reverse, nthreads=nthreads)
+    lines = np.ascontiguousarray(mats.reshape(B, P, Q * R).transpose(0, 2, 1)).reshape(B * Q * R, P)
+    out = batch(op, lines, lvl_r, f0, f1, nthreads).reshape(B, Q * R, P)
+    return np.ascontiguousarray(out.transpose(0, 2, 1)).reshape(B, P, Q, R)
+
+
 def aed_blocks(n):
     """tools/MathToolKit.java:57-84 decompose(): exponents of the descending powers of two that sum to n (42 -> 5, 3, 1)."""
     assert n >= 1

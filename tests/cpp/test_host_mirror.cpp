@@ -99,6 +99,27 @@ int main() {
     try { fwt.forward(ramp, 4, 3); } catch (const JWaveFailure& e) { thrown = strstr(e.what(), "out of range") != nullptr; }
     CHECK(thrown);
   }
+  {  // 3-D overloads (BasicTransform.java:487-640): constant 8 x 8 x 8 cube -> sqrt(512) in the corner; round trips
+    CudaFastWaveletTransform fwt(make("Daubechies4"), ctx);
+    CudaWaveletPacketTransform wpt(make("Haar1"), ctx);
+    Space ones(8, Matrix(8, std::vector<double>(8, 1.0)));
+    Space h = fwt.forward(ones);
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 8; j++)
+        for (int k = 0; k < 8; k++) CHECK(std::fabs(h[i][j][k] - ((i + j + k == 0) ? std::sqrt(512.0) : 0.0)) < 1e-8);
+    Space wave(4, Matrix(8, std::vector<double>(16)));
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 8; j++)
+        for (int k = 0; k < 16; k++) wave[i][j][k] = std::cos(0.3 * i * i + 0.21 * j - 0.07 * k * k);
+    Space back = fwt.reverse(fwt.forward(wave, 3, 4, 2), 3, 4, 2);   // lvlP -> the 8-axis, lvlQ -> the 16-axis, lvlR -> the 4-axis
+    Space back2 = wpt.reverse(wpt.forward(wave, 1, 2, 1), 1, 2, 1);
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 8; j++)
+        for (int k = 0; k < 16; k++) { CHECK(std::fabs(back[i][j][k] - wave[i][j][k]) < 1e-10); CHECK(std::fabs(back2[i][j][k] - wave[i][j][k]) < 1e-10); }
+    bool thrown = false;
+    try { fwt.forward(wave); } catch (const JWaveFailure& e) { thrown = strstr(e.what(), "out of range") != nullptr; }   // lvlQ = log2(8) = 3 fits the 16-axis, lvlR = log2(16) = 4 > log2(4): as in the reference
+    CHECK(thrown);
+  }
   printf(fails ? "%d checks FAILED\n" : "host mirror ok\n", fails);
   return fails ? 1 : 0;
 }

@@ -145,6 +145,13 @@ def test_2d_and_window_argument_checks_need_no_gpu(jw):
         f.forward(np.zeros((8, 8)), 4, 3)
     with pytest.raises(jw.JWaveFailure, match="out of range"):
         f.reverse(np.zeros((8, 8)), 3, -1)
+    # 3-D overloads (BasicTransform.java:487-640): lvlP goes to the q axis, lvlQ to the r axis, lvlR to the p axis
+    with pytest.raises(jw.JWaveFailure, match=r"2\^p"):
+        f.forward(np.zeros((8, 6, 8)))
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        f.forward(np.zeros((32, 8, 8)))             # default levels (5, 3, 3): lvlP = 5 > log2(q) = 3, as in the reference
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        f.reverse(np.zeros((8, 8, 8)), 3, 3, 4)
     m = jw.CudaMODWTTransform(jw.wavelets.Haar1())
     with pytest.raises(jw.IllegalArgumentException):
         m.forwardMODWTWindows(np.zeros(100), 128, 16, 3)      # window longer than the series

@@ -208,6 +208,52 @@ def test_2d_composition_follows_the_reference_loops(W, oracle):
             assert np.max(np.abs(back - x)) <= 1e-10
 
 
+def test_3d_composition_follows_the_reference_loops(W, oracle):
+    """batch3d against a literal restatement of BasicTransform.java:509-565 / :602-640: the 2-D transform (itself the
+    literal loops of the test above, with the numpy 1-D oracle) of every matrix spc[i] with (lvlP, lvlQ), then every line
+    spc[:, j, k] with lvlR -- in that order for BOTH directions, as the reference has it."""
+    for kind, fwd1, rev1 in (("fwt", np_oracle.fwt_forward, np_oracle.fwt_reverse),
+                             ("wpt", np_oracle.wpt_forward, np_oracle.wpt_reverse)):
+        for cls, p, q, r, lp, lq, lr in (("Haar1", 4, 4, 4, 2, 2, 2), ("Daubechies4", 4, 8, 16, 2, 3, 1),
+                                         ("Symlet8", 8, 2, 4, 1, 2, 3), ("Coiflet2", 2, 16, 2, 4, 0, 1)):
+            w = W.create(cls)
+            s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+            sr, wr = w.getScalingReConstruction(), w.getWaveletReConstruction()
+            x = splitmix_uniform(11 + p + q, (p, q, r))
+
+            def mat2d(m, one, f0, f1, reverse):
+                o = m.copy()
+                if not reverse:
+                    for a in range(q):
+                        o[a, :] = one(o[a, :].copy(), lq, f0, f1)      # rows of the matrix: lvlN = lvlQ
+                    for b in range(r):
+                        o[:, b] = one(o[:, b].copy(), lp, f0, f1)      # its columns: lvlM = lvlP
+                else:
+                    for b in range(r):
+                        o[:, b] = one(o[:, b].copy(), lp, f0, f1)
+                    for a in range(q):
+                        o[a, :] = one(o[a, :].copy(), lq, f0, f1)
+                return o
+
+            hilb = np.empty_like(x)
+            for i in range(p):
+                hilb[i] = mat2d(x[i], fwd1, s, wv, False)
+            for j in range(q):
+                for k in range(r):
+                    hilb[:, j, k] = fwd1(hilb[:, j, k].copy(), lr, s, wv)
+            got = oracle.batch3d(kind, x[None], lp, lq, lr, s, wv)[0]
+            assert np.array_equal(got, hilb), (kind, cls)
+            time = np.empty_like(x)
+            for i in range(p):
+                time[i] = mat2d(hilb[i], rev1, sr, wr, True)
+            for j in range(q):
+                for k in range(r):
+                    time[:, j, k] = rev1(time[:, j, k].copy(), lr, sr, wr)
+            back = oracle.batch3d(kind, hilb[None], lp, lq, lr, sr, wr, reverse=True)[0]
+            assert np.array_equal(back, time), (kind, cls)
+            assert np.max(np.abs(back - x)) <= 1e-10
+
+
 def test_2d_all_ones_concentrates_in_one_coefficient(W, oracle):
     """2-D extension of the reference's all-ones ladders (SteppingTest.java:37-314): a constant rows x cols matrix
     transforms at full depth to sqrt(rows*cols) in the top-left corner and zeros elsewhere."""

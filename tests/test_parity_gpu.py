@@ -626,6 +626,72 @@ def test_2d_matches_oracle(jw, gpu_ctx, oracle, kind, cls, rows, cols, lvl_m, lv
     assert _maxerr(t.reverse2DBatch(got, lvl_m, lvl_n), X, X) <= PR_TOL
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# 3-D FWT / WPT: BasicTransform.java:487-640 -- the 2-D transform of every matrix, then the lines along the first axis
+# ----------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+@pytest.mark.parametrize("cls,p,q,r,lvls,batch", [
+    ("Haar1", 8, 8, 8, (3, 3, 3), 1),
+    ("Daubechies4", 16, 32, 64, (5, 6, 4), 2),      # lvlP goes to the q axis, lvlQ to the r axis, lvlR to the p axis
+    ("Daubechies4", 64, 64, 64, (6, 6, 6), 1),      # a cube at full depth: forward(double[][][])
+    ("Symlet8", 128, 16, 32, (2, 3, 7), 2),         # deep first-axis transform: fused column launches on 512 columns
+    ("Daubechies20", 4, 8, 16, (3, 4, 2), 3),       # filter longer than every dimension
+    ("Daubechies2", 1, 16, 16, (4, 4, 0), 2),       # a single matrix: the first-axis pass has nothing to do
+    ("Daubechies3", 256, 4, 8, (0, 0, 8), 1),       # only the first axis is transformed
+    ("Daubechies6", 32, 1, 64, (0, 6, 5), 2),       # a single row per matrix
+])
+def test_3d_matches_oracle(jw, gpu_ctx, oracle, kind, cls, p, q, r, lvls, batch):
+    w = jw.wavelets.create(cls)
+    T = jw.CudaFastWaveletTransform if kind == "fwt" else jw.CudaWaveletPacketTransform
+    t = T(w)
+    X = splitmix_uniform(4321 + p + q + r, (batch, p, q, r))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.batch3d(kind, X, lvls[0], lvls[1], lvls[2], s, wv, nthreads=8)
+    got = t.forward3DBatch(X, *lvls)
+    assert _maxerr(got, ref, X) <= TOL
+    assert np.array_equal(t.forward3DBatch(X, *lvls, flags=jw.FLAG_EXACT), ref)
+    rref = oracle.batch3d(kind, ref, lvls[0], lvls[1], lvls[2], w.getScalingReConstruction(),
+                          w.getWaveletReConstruction(), reverse=True, nthreads=8)
+    assert _maxerr(t.reverse3DBatch(ref, *lvls), rref, X) <= TOL
+    assert np.array_equal(t.reverse3DBatch(ref, *lvls, flags=jw.FLAG_EXACT), rref)
+    assert _maxerr(t.reverse3DBatch(got, *lvls), X, X) <= PR_TOL
+
+
+def test_3d_java_overloads_device_buffers_and_errors(jw, gpu_ctx, oracle):
+    """forward(double[][][]) = the exponents of the three dimensions (BasicTransform.java:490-493); device-resident
+    variant; errors as the 1-D calls (a non-cubic space at default depth fails like the reference: lvlP = log2(p) is
+    applied to the q axis)."""
+    import torch
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaFastWaveletTransform(w)
+    X = splitmix_uniform(7, (16, 16, 16))
+    s, wv = w.getScalingDeComposition(), w.getWaveletDeComposition()
+    ref = oracle.batch3d("fwt", X[None], 4, 4, 4, s, wv)[0]
+    assert _maxerr(t.forward(X), ref, X) <= TOL
+    assert _maxerr(t.forward(X, 4, 4, 4), ref, X) <= TOL
+    assert _maxerr(t.reverse(t.forward(X)), X, X) <= PR_TOL
+    assert _maxerr(t.reverse(t.forward(X, 1, 2, 3), 1, 2, 3), X, X) <= PR_TOL
+    with pytest.raises(jw.JWaveFailure, match="2\\^p"):
+        t.forward(np.zeros((16, 12, 16)))
+    with pytest.raises(jw.JWaveFailure, match="out of range"):
+        t.forward(np.zeros((32, 8, 8)))          # lvlP = 5 > log2(q) = 3, as in the reference
+    d_in = torch.from_numpy(np.ascontiguousarray(np.stack([X, -X]))).cuda()
+    d_out = torch.empty_like(d_in)
+    t.forward3DDevice(d_in.data_ptr(), d_out.data_ptr(), 2, 16, 16, 16, 4, 4, 4)
+    torch.cuda.synchronize()
+    assert _maxerr(d_out.cpu().numpy()[0], ref, X) <= TOL and _maxerr(d_out.cpu().numpy()[1], -ref, X) <= TOL
+    d_back = torch.empty_like(d_in)
+    t.reverse3DDevice(d_out.data_ptr(), d_back.data_ptr(), 2, 16, 16, 16, 4, 4, 4)
+    torch.cuda.synchronize()
+    assert _maxerr(d_back.cpu().numpy()[0], X, X) <= PR_TOL
+    lib = jw._native.load()
+    f = (ctypes.c_double * 2)(0.5, 0.5)
+    buf = np.zeros(512)
+    rc = lib.jwc_fwt3d_forward(gpu_ctx.handle, buf.ctypes.data, buf.ctypes.data, 1, 6, 8, 8, 1, 1, 1, f, f, 2, 0)
+    assert rc == -1 and b"2^p" in lib.jwc_last_error()
+
+
 def test_2d_java_overloads_and_errors(jw, gpu_ctx, oracle):
     """forward(double[][]) = full depth in both dimensions (BasicTransform.java:336-340); errors as the 1-D calls."""
     w = jw.wavelets.Daubechies4()
