@@ -13,6 +13,7 @@
 // Context constructor throws.
 #pragma once
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -94,6 +95,24 @@ class WaveletTransform : public BasicTransform {
   virtual std::vector<double> reverse(const std::vector<double>& arrHilb) {
     if (!isBinary((int64_t)arrHilb.size())) throw JWaveFailure("WaveletTransform#reverse - given array length is not 2^p | p E N ... = 1, 2, 4, 8, 16, 32, .. please use the Ancient Egyptian Decomposition for any other array length!");
     return reverse(arrHilb, calcExponent((int64_t)arrHilb.size()));
+  }
+  // BasicTransform.java:257-320 forward / reverse(Complex[]): N complex numbers as ONE real array of length 2N, real and
+  // imaginary parts interleaved, through the 1-D transform at full depth
+  std::vector<std::complex<double>> forward(const std::vector<std::complex<double>>& arrTime) {
+    std::vector<double> bulk(2 * arrTime.size());
+    for (size_t i = 0; i < arrTime.size(); i++) { bulk[2 * i] = arrTime[i].real(); bulk[2 * i + 1] = arrTime[i].imag(); }
+    const std::vector<double> h = forward(bulk);
+    std::vector<std::complex<double>> out(arrTime.size());
+    for (size_t i = 0; i < out.size(); i++) out[i] = {h[2 * i], h[2 * i + 1]};
+    return out;
+  }
+  std::vector<std::complex<double>> reverse(const std::vector<std::complex<double>>& arrHilb) {
+    std::vector<double> bulk(2 * arrHilb.size());
+    for (size_t i = 0; i < arrHilb.size(); i++) { bulk[2 * i] = arrHilb[i].real(); bulk[2 * i + 1] = arrHilb[i].imag(); }
+    const std::vector<double> t = reverse(bulk);
+    std::vector<std::complex<double>> out(arrHilb.size());
+    for (size_t i = 0; i < out.size(); i++) out[i] = {t[2 * i], t[2 * i + 1]};
+    return out;
   }
   // WaveletTransform.java:136-182
   std::vector<std::vector<double>> decompose(const std::vector<double>& arrTime) {
@@ -379,6 +398,15 @@ class CudaMODWTTransform : public WaveletTransform {
     for (size_t i = 0; i < g_.size(); i++) { g_[i] = g_[i] / s; h_[i] = h_[i] / s; }
   }
   static int getMaxDecompositionLevel() { return MAX_DECOMPOSITION_LEVEL; }
+  // MODWTTransform.java:148-153, :191-213: the reference switches its CPU loops between the direct and the FFT circular
+  // convolution; the device path has one arithmetic, so the setting (and the FFT threshold of the two-argument
+  // constructor) is stored for callers that read it back and changes nothing
+  enum class ConvolutionMethod { AUTO, DIRECT, FFT };
+  CudaMODWTTransform(Wavelet w, int fftThreshold, std::shared_ptr<Context> ctx = nullptr) : CudaMODWTTransform(std::move(w), std::move(ctx)) {
+    fftThreshold_ = fftThreshold;
+  }
+  void setConvolutionMethod(ConvolutionMethod m) { method_ = m; }
+  ConvolutionMethod getConvolutionMethod() const { return method_; }
 
   // MODWTTransform.java:256-306; rows W_1..W_J, V_J
   std::vector<std::vector<double>> forwardMODWT(const std::vector<double>& data, int maxLevel) const {
@@ -472,6 +500,8 @@ class CudaMODWTTransform : public WaveletTransform {
     return rows;
   }
   std::vector<double> g_, h_;
+  int fftThreshold_ = 4096;   // MODWTTransform.java:144
+  ConvolutionMethod method_ = ConvolutionMethod::AUTO;
 };
 
 }  // namespace jwave

@@ -110,6 +110,11 @@ class WaveletTransform(BasicTransform):
         """1-D: forward(arrTime[, level]).  A 2-D array selects the reference's matrix overloads
         forward(double[][]) / forward(double[][], lvlM, lvlN) (BasicTransform.java:330-399), a 3-D array its space
         overloads forward(double[][][]) / forward(double[][][], lvlP, lvlQ, lvlR) (:487-565)."""
+        if np.iscomplexobj(arrTime) and np.ndim(arrTime) == 1:
+            # BasicTransform.java:257-280 forward(Complex[]): the N complex numbers as ONE real array of length 2N,
+            # real and imaginary parts interleaved, through forward(double[]) at full depth, and back
+            bulk = np.ascontiguousarray(arrTime, dtype=np.complex128).view(np.float64)
+            return np.ascontiguousarray(self.forward(bulk)).view(np.complex128)
         if np.ndim(arrTime) == 3:
             return self.forward3D(arrTime, level, lvlN, lvlR)
         if np.ndim(arrTime) == 2:
@@ -123,6 +128,9 @@ class WaveletTransform(BasicTransform):
         return self._forward_level(arrTime, level)
 
     def reverse(self, arrHilb, level=None, lvlN=None, lvlR=None):
+        if np.iscomplexobj(arrHilb) and np.ndim(arrHilb) == 1:      # BasicTransform.java:297-320 reverse(Complex[])
+            bulk = np.ascontiguousarray(arrHilb, dtype=np.complex128).view(np.float64)
+            return np.ascontiguousarray(self.reverse(bulk)).view(np.complex128)
         if np.ndim(arrHilb) == 3:
             return self.reverse3D(arrHilb, level, lvlN, lvlR)
         if np.ndim(arrHilb) == 2:
@@ -557,17 +565,43 @@ class MODWTCoefficients:
         return self._backing
 
 
+class ConvolutionMethod:
+    """MODWTTransform.ConvolutionMethod (MODWTTransform.java:148-153).  The reference switches its CPU loops between the
+    direct O(N M) and the FFT O(N log N) circular convolution; the device path has one arithmetic (the direct sum, in
+    the reference's summation order), so the setting is kept for callers that read it back and changes nothing."""
+    AUTO = "AUTO"
+    DIRECT = "DIRECT"
+    FFT = "FFT"
+
+
 class CudaMODWTTransform(WaveletTransform):
     """Drop-in for transforms/MODWTTransform.java."""
 
     MAX_DECOMPOSITION_LEVEL = 13  # MODWTTransform.java:111
+    ConvolutionMethod = ConvolutionMethod
 
-    def __init__(self, wavelet, context=None):
+    def __init__(self, wavelet, fftThreshold=None, context=None):
+        # MODWTTransform.java:180-195: (wavelet) and (wavelet, fftThreshold); the threshold only steers the reference's
+        # AUTO choice between its two CPU convolutions and is recorded, not used
+        if fftThreshold is not None and not isinstance(fftThreshold, (int, np.integer)):
+            context, fftThreshold = fftThreshold, None      # CudaMODWTTransform(wavelet, context)
         super().__init__(wavelet, context)
         self._name = "MODWT"
         self._lock = threading.Lock()
         self._g = None
         self._h = None
+        self._fftThreshold = 4096 if fftThreshold is None else int(fftThreshold)   # MODWTTransform.java:128
+        self._convolutionMethod = ConvolutionMethod.AUTO
+
+    def setConvolutionMethod(self, method):
+        # MODWTTransform.java:202-204
+        if method not in (ConvolutionMethod.AUTO, ConvolutionMethod.DIRECT, ConvolutionMethod.FFT):
+            raise IllegalArgumentException("unknown convolution method %r" % (method,))
+        self._convolutionMethod = method
+
+    def getConvolutionMethod(self):
+        # MODWTTransform.java:211-213
+        return self._convolutionMethod
 
     @staticmethod
     def getMaxDecompositionLevel():

@@ -120,6 +120,22 @@ int main() {
     try { fwt.forward(wave); } catch (const JWaveFailure& e) { thrown = strstr(e.what(), "out of range") != nullptr; }   // lvlQ = log2(8) = 3 fits the 16-axis, lvlR = log2(16) = 4 > log2(4): as in the reference
     CHECK(thrown);
   }
+  {  // Complex[] overloads (BasicTransform.java:257-320) and the MODWT configuration accessors (MODWTTransform.java:191-213)
+    CudaFastWaveletTransform fwt(make("Daubechies4"), ctx);
+    std::vector<std::complex<double>> z(64);
+    for (size_t i = 0; i < z.size(); i++) z[i] = {std::sin(0.3 * (double)i), std::cos(0.11 * (double)(i * i))};
+    std::vector<double> bulk(128);
+    for (size_t i = 0; i < z.size(); i++) { bulk[2 * i] = z[i].real(); bulk[2 * i + 1] = z[i].imag(); }
+    const auto hz = fwt.forward(z);
+    const auto hb = fwt.forward(bulk);
+    for (size_t i = 0; i < z.size(); i++) { CHECK(hz[i].real() == hb[2 * i]); CHECK(hz[i].imag() == hb[2 * i + 1]); }
+    const auto back = fwt.reverse(hz);
+    for (size_t i = 0; i < z.size(); i++) CHECK(std::abs(back[i] - z[i]) < 1e-10);
+    CudaMODWTTransform m(make("Haar1"), 1024, ctx);
+    CHECK(m.getConvolutionMethod() == CudaMODWTTransform::ConvolutionMethod::AUTO);
+    m.setConvolutionMethod(CudaMODWTTransform::ConvolutionMethod::DIRECT);
+    CHECK(m.getConvolutionMethod() == CudaMODWTTransform::ConvolutionMethod::DIRECT);
+  }
   printf(fails ? "%d checks FAILED\n" : "host mirror ok\n", fails);
   return fails ? 1 : 0;
 }

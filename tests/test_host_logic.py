@@ -161,3 +161,18 @@ def test_2d_and_window_argument_checks_need_no_gpu(jw):
         m.forwardMODWTWindows(np.zeros(100), 32, 8, 6)        # J > log2(window)
     with pytest.raises(jw.JWaveFailure):
         jw.AncientEgyptianDecomposition(m)                     # only the pyramid transforms can be wrapped
+
+
+def test_modwt_constructor_variants_and_convolution_method(jw):
+    """MODWTTransform.java:180-213: (wavelet) / (wavelet, fftThreshold) constructors and the ConvolutionMethod accessors;
+    on the device there is one arithmetic, so the setting is stored and read back, nothing else."""
+    w = jw.wavelets.Daubechies4()
+    t = jw.CudaMODWTTransform(w)
+    assert t.getConvolutionMethod() == jw.ConvolutionMethod.AUTO and t.ConvolutionMethod is jw.ConvolutionMethod
+    t.setConvolutionMethod(jw.ConvolutionMethod.FFT)
+    assert t.getConvolutionMethod() == "FFT"
+    with pytest.raises(jw.IllegalArgumentException):
+        t.setConvolutionMethod("fastest")
+    assert jw.CudaMODWTTransform(w, 1024)._fftThreshold == 1024
+    assert jw.CudaMODWTTransform(w)._fftThreshold == 4096          # MODWTTransform.java:144
+    assert jw.CudaMODWTTransform.getMaxDecompositionLevel() == 13

@@ -692,6 +692,24 @@ def test_3d_java_overloads_device_buffers_and_errors(jw, gpu_ctx, oracle):
     assert rc == -1 and b"2^p" in lib.jwc_last_error()
 
 
+def test_complex_overloads(jw, gpu_ctx, oracle):
+    """BasicTransform.java:257-320 forward / reverse(Complex[]): N complex numbers = ONE real array of length 2N with
+    real and imaginary parts interleaved, through the 1-D transform at full depth."""
+    n = 256
+    z = splitmix_uniform(3, (n,)) + 1j * splitmix_uniform(4, (n,))
+    bulk = np.empty(2 * n)
+    bulk[0::2], bulk[1::2] = z.real, z.imag
+    for T, op in ((jw.CudaFastWaveletTransform, "fwt"), (jw.CudaWaveletPacketTransform, "wpt")):
+        w = jw.wavelets.Daubechies4()
+        t = T(w)
+        ref = oracle.batch(op + "_fwd", bulk[None], 9, w.getScalingDeComposition(), w.getWaveletDeComposition())[0]
+        got = t.forward(z)
+        assert got.dtype == np.complex128 and got.shape == (n,)
+        assert _maxerr(got.real, ref[0::2], bulk) <= TOL and _maxerr(got.imag, ref[1::2], bulk) <= TOL
+        back = t.reverse(got)
+        assert np.max(np.abs(back - z)) <= PR_TOL
+
+
 def test_2d_java_overloads_and_errors(jw, gpu_ctx, oracle):
     """forward(double[][]) = full depth in both dimensions (BasicTransform.java:336-340); errors as the 1-D calls."""
     w = jw.wavelets.Daubechies4()
