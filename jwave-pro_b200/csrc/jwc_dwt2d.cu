@@ -569,6 +569,134 @@ __global__ void __launch_bounds__(kStrip* kGroups) col_ana_tree2_kernel(const __
   }
 }
 
+// Three levels per launch (forward): the same scheme one level deeper -- T + 7 (L-2) staged rows give T/2 + 3 (L-2) rows
+// of the two level-1 children, T/4 + (L-2) rows of the four level-2 children (all in shared memory) and T/8 rows of each
+// of the eight leaves, which go to their eighths of the block.  The halo rows are recomputed by the neighbouring tile:
+// worth it for the short filters, whose column passes are HBM-bound (Haar: no halo at all).
+template <int L, int T>
+__global__ void __launch_bounds__(kStrip* kGroups) col_ana_tree3_kernel(const __grid_constant__ ColTreeArgs a,
+                                                                        const __grid_constant__ FilterPair f) {
+  extern __shared__ double sm[];
+  constexpr int H = L - 2;
+  constexpr int NA = T + 7 * H, N1 = T / 2 + 3 * H, N2 = T / 4 + H;
+  constexpr int ROWS_AC = (NA + kPad) > 4 * (N2 + kPad) ? (NA + kPad) : 4 * (N2 + kPad);
+  double* A = sm;                                   // the staged rows; later the four level-2 children
+  double* B = sm + ROWS_AC * kStrip;                // the two level-1 children, (N1 + kPad) rows each
+  unsigned id = blockIdx.x;
+  const unsigned strip = id & ((1u << a.lg_strips) - 1);
+  id >>= a.lg_strips;
+  const int64_t r0 = (int64_t)(id & ((1u << a.lg_tiles) - 1)) * T;
+  id >>= a.lg_tiles;
+  const int64_t p = id & ((1u << a.lg_blocks) - 1), b = id >> a.lg_blocks;
+  const int64_t c0 = (int64_t)strip * kStrip;
+  const int ncol = (int)((a.cols - c0 < kStrip) ? a.cols - c0 : kStrip);
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kStrip + tx;
+  {
+    const double* src = a.src + b * a.mat + p * a.h * a.ld + c0;
+    for (int idx = tid; idx < NA * (kStrip / 2); idx += kStrip * kGroups) {
+      const int row = idx / (kStrip / 2), seg = idx % (kStrip / 2);
+      if (2 * seg < ncol) ptx::cp_async16(&A[row * kStrip + 2 * seg], src + ((r0 + row) & (a.h - 1)) * a.ld + 2 * seg);
+    }
+    ptx::cp_async_commit_wait_all();
+  }
+  __syncthreads();
+  constexpr int W = L + 2 * kRun - 2;
+  // one analysis step on `np` parents of shared memory: parent q at in + q * in_stride, children 2q, 2q+1 at out + ...
+  auto level = [&](const double* in, int in_stride, double* out, int out_stride, int np, int nout) {
+    const int runs = (nout + kRun - 1) / kRun;
+    for (int w = ty; w < np * runs; w += kGroups) {
+      const int q = w / runs, i0 = (w - q * runs) * kRun;
+      const double* src = in + q * in_stride;
+      double win[W];
+#pragma unroll
+      for (int t = 0; t < W; t++) win[t] = src[(2 * i0 + t) * kStrip + tx];
+      double sl[kRun], sh[kRun];
+#pragma unroll
+      for (int u = 0; u < kRun; u++) sl[u] = sh[u] = 0.0;
+#pragma unroll
+      for (int m = 0; m < L; m++)
+#pragma unroll
+        for (int u = 0; u < kRun; u++) {
+          sl[u] = fma(win[2 * u + m], f.f0[m], sl[u]);
+          sh[u] = fma(win[2 * u + m], f.f1[m], sh[u]);
+        }
+      double* lo = out + (2 * q) * out_stride;
+      double* hi = lo + out_stride;
+#pragma unroll
+      for (int u = 0; u < kRun; u++)
+        if (i0 + u < nout) {
+          lo[(i0 + u) * kStrip + tx] = sl[u];
+          hi[(i0 + u) * kStrip + tx] = sh[u];
+        }
+    }
+  };
+  level(A, 0, B, (N1 + kPad) * kStrip, 1, N1);
+  __syncthreads();
+  level(B, (N1 + kPad) * kStrip, A, (N2 + kPad) * kStrip, 2, N2);
+  __syncthreads();
+  // level 3: T/8 rows of each leaf, straight to its eighth of the block
+  const int64_t eighth = a.h >> 3;
+  double* out = a.dst + b * a.mat + (p * a.h + (r0 >> 3)) * a.ld + c0 + tx;
+  constexpr int NE = T / 8;                         // multiple of kRun
+  for (int w = ty; w < 4 * (NE / kRun); w += kGroups) {
+    const int parent = w / (NE / kRun), i0 = (w - parent * (NE / kRun)) * kRun;
+    const double* in = A + parent * (N2 + kPad) * kStrip;
+    double win[W];
+#pragma unroll
+    for (int t = 0; t < W; t++) win[t] = in[(2 * i0 + t) * kStrip + tx];
+    double sl[kRun], sh[kRun];
+#pragma unroll
+    for (int u = 0; u < kRun; u++) sl[u] = sh[u] = 0.0;
+#pragma unroll
+    for (int m = 0; m < L; m++)
+#pragma unroll
+      for (int u = 0; u < kRun; u++) {
+        sl[u] = fma(win[2 * u + m], f.f0[m], sl[u]);
+        sh[u] = fma(win[2 * u + m], f.f1[m], sh[u]);
+      }
+    if (tx < ncol) {
+      double* lo = out + (int64_t)(2 * parent) * eighth * a.ld;
+      double* hi = out + (int64_t)(2 * parent + 1) * eighth * a.ld;
+#pragma unroll
+      for (int u = 0; u < kRun; u++) {
+        lo[(int64_t)(i0 + u) * a.ld] = sl[u];
+        hi[(int64_t)(i0 + u) * a.ld] = sh[u];
+      }
+    }
+  }
+}
+
+template <int L>
+int launch_tree3(jwc_ctx* ctx, cudaStream_t st, ColTreeArgs a, const FilterPair& f, int64_t batch) {
+  constexpr int T = 128;
+  constexpr int H = L - 2;
+  a.strips = (a.cols + kStrip - 1) / kStrip;
+  a.tiles = a.h / T;
+  a.lg_strips = ilog2_exact(a.strips);
+  a.lg_tiles = ilog2_exact(a.tiles);
+  a.lg_blocks = ilog2_exact(a.blocks);
+  if (a.lg_strips < 0 || a.lg_tiles < 0 || a.lg_blocks < 0) return JWC_ERR_UNSUPPORTED;
+  const int64_t ctas = a.strips * a.tiles * a.blocks * batch;
+  if (ctas > 0x7fffffffLL) return JWC_ERR_UNSUPPORTED;
+  constexpr int NA = T + 7 * H, N1 = T / 2 + 3 * H, N2 = T / 4 + H;
+  constexpr int ROWS_AC = (NA + kPad) > 4 * (N2 + kPad) ? (NA + kPad) : 4 * (N2 + kPad);
+  const size_t smem = (size_t)(ROWS_AC + 2 * (N1 + kPad)) * kStrip * sizeof(double);
+  JWC_CUDA_CHECK(allow_max_dynamic_smem(col_ana_tree3_kernel<L, T>));
+  col_ana_tree3_kernel<L, T><<<(unsigned)ctas, dim3(kStrip, kGroups), smem, st>>>(a, f);
+  count_launch(ctx);
+  JWC_CUDA_CHECK(cudaGetLastError());
+  return JWC_OK;
+}
+
+int run_tree3(jwc_ctx* ctx, cudaStream_t st, const ColTreeArgs& a, const FilterPair& f, int64_t batch, int L) {
+  switch (L) {
+#define X(LL) case LL: return launch_tree3<LL>(ctx, st, a, f, batch);
+    X(2) X(4) X(6) X(8) X(10)
+#undef X
+    default: return JWC_ERR_UNSUPPORTED;
+  }
+}
+
 template <int L>
 int launch_tree2(jwc_ctx* ctx, cudaStream_t st, ColTreeArgs a, const FilterPair& f, int64_t batch) {
   constexpr int T = 128;
@@ -798,8 +926,11 @@ int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
       // the fused launch stages its rows with 16-byte cp.async; the ping-pong makes every launch after the first read
       // either scratch (aligned) or the caller's d_out, so both caller pointers must be 16-byte aligned
       const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
-      const int k = (!exact && aligned && ctx->tune.wpt2d_fuse >= 0 && steps - l >= 2 && (rows >> l) >= 128 && !(cols & 1) &&
-                     L >= 2 && L <= 20 && !(L & 1)) ? 2 : 1;
+      int k = (!exact && aligned && ctx->tune.wpt2d_fuse >= 0 && steps - l >= 2 && (rows >> l) >= 128 && !(cols & 1) &&
+               L >= 2 && L <= 20 && !(L & 1)) ? 2 : 1;
+      // three levels per launch for the short filters (their halo rows are cheap to recompute, the pass is HBM-bound);
+      // wpt2d_fuse = 2 keeps the launches at two levels
+      if (k == 2 && steps - l >= 3 && L <= 10 && ctx->tune.wpt2d_fuse != 2 && steps - l != 4) k = 3;
       sched.push_back(k);
       l += k;
     }
@@ -813,10 +944,10 @@ int dwt2d_columns_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
     for (size_t i = 0; i < sched.size(); i++) {
       double* dst = (((sched.size() - 1 - i) & 1) == 0) ? d_out : tmp;
       int rc;
-      if (sched[i] == 2) {
+      if (sched[i] >= 2) {
         ColTreeArgs a{};
         a.src = src; a.dst = dst; a.mat = mat; a.ld = cols; a.cols = cols; a.h = h; a.blocks = rows / h;
-        rc = run_tree2(ctx, st, a, f, batch, L);
+        rc = sched[i] == 3 ? run_tree3(ctx, st, a, f, batch, L) : run_tree2(ctx, st, a, f, batch, L);
       } else {
         ColArgs a{};
         a.src_lo = src; a.src_lo_mat = mat; a.src_lo_blk = h * cols;
@@ -899,6 +1030,9 @@ int dwt2d_columns_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, 
       for (int done = 0; done < steps;) {
         const bool aligned = true;       // no 16-byte loads in the inverse kernel
         const int64_t h2 = h << 1;       // block height after two steps
+        // (three levels per launch, as in the forward pass, were built and measured for the inverse too: the eight
+        // leaves stream in through per-thread sliding windows, and at the two CTAs per SM the larger shared-memory
+        // footprint leaves their latency shows -- Daubechies4 5.33 ms against 5.07, Haar 6 levels 8.6 against 7.8)
         const int k = (!exact && aligned && ctx->tune.wpt2d_fuse >= 0 && steps - done >= 2 && h2 >= 128 &&
                        (h2 >> 2) >= inv_halo(L, 2, 2) && (h2 >> 2) >= L / 2 && L >= 2 && L <= 20 && !(L & 1)) ? 2 : 1;
         sched.push_back(k);
