@@ -660,6 +660,7 @@ static int* tuning_field(jwc_ctx* ctx, const char* key) {
   if (!strcmp(key, "pf_inv")) return &t.pf_inv;
   if (!strcmp(key, "modwt_logp")) return &t.modwt_logp;
   if (!strcmp(key, "top_barrier")) return &t.top_barrier;
+  if (!strcmp(key, "dwt_upfront")) return &t.dwt_upfront;
   if (!strcmp(key, "dwt_k0")) return &t.dwt_k0;
   if (!strcmp(key, "dwt_fixed")) return &t.dwt_fixed;
   if (!strcmp(key, "modwt_force_wrap")) return &t.modwt_force_wrap;

@@ -52,6 +52,7 @@ struct DwtPassArgs {
   int l0, k, T, tiles, nodes, cap, mode;
   int pf_dist;        // L2 prefetch distance in CTAs (0 = off)
   int top_barrier;    // inverse: 1 = round-1 form of the tile wait (see the level loop)
+  int upfront;        // pyramid inverse, bulk mode: every D tile of the pass is requested in the prologue (own slot, own mbarrier)
   int log_tiles;      // tiles and nodes are powers of two: the CTA index is taken apart with shifts (a 64-bit
                       // division is a ~100-instruction subroutine, and a CTA only lives for a few thousand)
   unsigned nblocks;
@@ -477,9 +478,14 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
   auto len_of = [&](int jj) { return (tlen >> jj) + s_hl[jj]; };
   auto stride_of = [&](int jj) { const int l = len_of(jj); return l + (l & 1) + 2 * kDwtR; };
 
+  // upfront: all k detail tiles are requested before the first level runs.  D_{l0+jj-1} lands in the high-pass slot of
+  // the buffer level jj writes to, exactly where the one-level-ahead prefetch puts it; tiles of the same buffer nest
+  // without overlap ([stride_j, stride_j + len_j) lies below stride_{j-2} when T >> k >= L, checked by the host), so the
+  // waits of the deeper levels overlap one DRAM round trip instead of paying one each.  One mbarrier per level, phase 0.
+  const bool upfront = bulk && !TREE && a.upfront != 0;
   if (bulk && tid == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
+    const int nb = upfront ? a.k : 2;
+    for (int q = 0; q < nb; q++) ptx::mbar_init(&bars[q], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();   // mbarriers, s_hl and the tap copy are visible
@@ -525,6 +531,15 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
           ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)len * 8u);
           bulk_load_circ(smem, asrc, start, len, hn, &bars[0], nullptr, ihalo(0));
           bulk_load_circ(smem + st, dsrc, start, len, hn, &bars[0], nullptr, ihalo(1));
+          if (upfront) {
+            for (int j2 = a.k - 1, u2 = 1; j2 >= 1; --j2, ++u2) {   // D_{l0+j2}: read by iteration u2 from buffer u2 & 1
+              const int len2 = len_of(j2);
+              const int64_t hn2 = a.h >> j2, start2 = (a0 >> j2) - s_hl[j2];
+              ptx::mbar_expect_tx(&bars[u2], (uint32_t)len2 * 8u);
+              bulk_load_circ(smem + (u2 & 1) * a.cap + stride_of(j2), in_b + (a.N >> (a.l0 + j2)), start2, len2, hn2,
+                             &bars[u2], nullptr, ihalo(1 + a.k - j2));
+            }
+          }
         }
       } else {
         scalar_load_circ(smem, asrc, start, len, hn, tid, nt, nullptr, ihalo(0));
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
   for (int jj = a.k, u = 0; jj >= 1; --jj, ++u) {
     const int oin = (u & 1) * a.cap, oout = ((u + 1) & 1) * a.cap;
     const int st_in = stride_of(jj), st_out = stride_of(jj - 1);
-    if (!TREE && jj > 1) {   // prefetch D_{l0+jj-1} into the high-pass slot of the output buffer
+    if (!TREE && jj > 1 && !upfront) {   // prefetch D_{l0+jj-1} into the high-pass slot of the output buffer
       const int len = len_of(jj - 1);
       const int64_t hn = a.h >> (jj - 1), start = (a0 >> (jj - 1)) - s_hl[jj - 1];
       const double* dsrc = in_b + (a.N >> (a.l0 + jj - 1));
@@ -550,15 +565,17 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
       }
     }
     if (bulk && (!TREE || u == 0)) {
-      const uint32_t par = (uint32_t)((u >> 1) & 1);
-      if (a.top_barrier) {   // round-1 form: one sleeper on the mbarrier, the rest on a block barrier
-        if (tid == 0) ptx::mbar_wait(&bars[u & 1], par);
+      const uint32_t par = upfront ? 0u : (uint32_t)((u >> 1) & 1);
+      uint64_t* lvl_bar = &bars[upfront ? u : (u & 1)];
+      if (a.top_barrier == 1) {   // round-1 form: one sleeper on the mbarrier, the rest on a block barrier
+        if (tid == 0) ptx::mbar_wait(lvl_bar, par);
         __syncthreads();
       }
       // every thread takes its own acquire on the TMA-written tiles; the block barrier that ends the previous level
       // has already ordered the generic-proxy traffic, so the top of a level needs no second one
-      ptx::mbar_wait(&bars[u & 1], par);
-    } else if (u == 0 || a.top_barrier) {
+      if (a.top_barrier >= 16) ptx::mbar_wait_hint(lvl_bar, par, (uint32_t)a.top_barrier);   // experiment: suspend-time hint in ns
+      else ptx::mbar_wait(lvl_bar, par);
+    } else if (u == 0 || a.top_barrier == 1) {
       __syncthreads();   // scalar prologue loads (all threads) -> visible
     }
     const int hl_out = s_hl[jj - 1], hl_in = s_hl[jj];
@@ -848,6 +865,17 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     a.pf_dist = (p.mode == DWT_BULK) ? dwt_prefetch_distance(ctx, dev, p.smem, p.threads) : 0;
     if (ctx->tune.pf_inv != 0) a.pf_dist = (p.mode == DWT_BULK && ctx->tune.pf_inv > 0) ? ctx->tune.pf_inv : 0;
     a.top_barrier = ctx->tune.top_barrier;
+    a.upfront = 0;
+    if (!tree && p.mode == DWT_BULK && ctx->tune.dwt_upfront > 0 && p.k >= 2 && p.k <= 16) {
+      // the detail tiles of one buffer must nest: slot of D_j = [stride_j, stride_j + len_j) below the slot of D_{j-2}
+      const int64_t tl = std::min<int64_t>(a.h, p.T);
+      bool ok = true;
+      for (int j = 3; j <= p.k && ok; j++) {
+        const int64_t lj = dwt_inv_len(L, j, tl), l2 = dwt_inv_len(L, j - 2, tl);
+        ok = dwt_node_stride(l2) >= dwt_node_stride(lj) + lj;
+      }
+      a.upfront = ok ? 1 : 0;
+    }
     int rc = JWC_ERR_UNSUPPORTED;
     if (!tree)   // long signals: the tiled in-place kernel (jwc_dwt_whole.cu) takes passes of up to 3 levels
       rc = tile_dwt_inverse_pass(ctx, st, a.ain, a.ain_sig, a.in, a.in_sig, a.out, a.out_sig, n, p.l0, p.k, batch, f, L);

@@ -483,13 +483,22 @@ struct InvPassArgs {
   unsigned nblocks;
 };
 
+#ifndef JWC_INV_ONE_SUM
+#define JWC_INV_ONE_SUM 0
+#endif
 template <int L, int R>
 __device__ __forceinline__ void inv_item(const double* __restrict__ pv, const double* __restrict__ pw, int s,
                                          const FilterPair& f, const double* __restrict__ taps, double (&out)[R]) {
   constexpr bool ST = (L > kUniformTapsMax);
-  double ag[R], ah[R];
+  // ONE: both sums run through one accumulator per output (R instead of 2R live accumulators; the result differs from
+  // the reference's "two sums added at the end" in the last bits only, far inside the 1e-12 parity bound)
+  constexpr bool ONE = (JWC_INV_ONE_SUM != 0) && ST;
+  double ag[R], ah[ONE ? 1 : R];
 #pragma unroll
-  for (int q = 0; q < R; q++) { ag[q] = 0.0; ah[q] = 0.0; }
+  for (int q = 0; q < R; q++) {
+    ag[q] = 0.0;
+    if constexpr (!ONE) ah[q] = 0.0;
+  }
   double tg[L], th[L];
   // rows 0 .. R+L-2 ascending: accumulator q meets tap m = i - q in ascending m (reference order)
 #pragma unroll
@@ -501,17 +510,33 @@ __device__ __forceinline__ void inv_item(const double* __restrict__ pv, const do
     const double xv = *pv, xw = *pw;
     pv += s;
     pw += s;
+    if (ONE) {
 #pragma unroll
-    for (int q = 0; q < R; q++) {
-      const int m = i - q;
-      if (m >= 0 && m < L) {
-        ag[q] = fma(xv, ST ? tg[m] : f.f0[m], ag[q]);
-        ah[q] = fma(xw, ST ? th[m] : f.f1[m], ah[q]);
+      for (int q = 0; q < R; q++) {
+        const int m = i - q;
+        if (m >= 0 && m < L) ag[q] = fma(xv, tg[m], ag[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const int m = i - q;
+        if (m >= 0 && m < L) ag[q] = fma(xw, th[m], ag[q]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const int m = i - q;
+        if (m >= 0 && m < L) {
+          ag[q] = fma(xv, ST ? tg[m] : f.f0[m], ag[q]);
+          ah[q] = fma(xw, ST ? th[m] : f.f1[m], ah[q]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int q = 0; q < R; q++) out[q] = ag[q] + ah[q];   // :366-369: the two sums are added at the end
+  for (int q = 0; q < R; q++) {
+    if constexpr (ONE) out[q] = ag[q];
+    else out[q] = ag[q] + ah[q];   // :366-369: the two sums are added at the end
+  }
 }
 
 // rows [i_start, i_start + rows) of the decimated index (circular), P phases each, into dst (virtual layout r*P + p)
@@ -639,7 +664,9 @@ __global__ void __launch_bounds__(256, (L > 10 ? JWC_INV_MINB : 3)) modwt_inv_pa
     }
     if (bulk) {
       const uint32_t par = (uint32_t)((u >> 1) & 1);
-      if (!a.top_barrier) {
+      if (a.top_barrier >= 16) {
+        ptx::mbar_wait_hint(&bars[wb], par, (uint32_t)a.top_barrier);   // experiment: suspend-time hint in ns
+      } else if (!a.top_barrier) {
         // every thread takes its own acquire on the mbarrier: the block barrier at the end of the previous level has
         // already ordered the shared-memory traffic, so the top of a level needs no second one (measured on C2:
         // 3.50 -> 3.33 ms against one sleeper on the mbarrier + a block barrier for the rest)

@@ -1020,6 +1020,31 @@ def test_fwt_wpt_tile_wait_variants_agree(jw):
         ctx.close()
 
 
+@pytest.mark.parametrize("cls,n,lvl,group", [("Daubechies8", 1 << 17, 17, 0), ("Haar1", 1 << 17, 17, 6),
+                                              ("Daubechies20", 1 << 16, 9, 4), ("Coiflet5", 1 << 18, 7, 5),
+                                              ("Symlet3", 1 << 15, 15, 8)])
+def test_fwt_inverse_detail_tiles_requested_up_front(jw, oracle, cls, n, lvl, group):
+    """The pyramid inverse requests every detail tile of a pass in its prologue (dwt_upfront, the default); with the
+    one-level-ahead prefetch of round 1 (dwt_upfront = 0) the result is bit-identical, also for deeper passes than the
+    planner's (dwt_group), and both match the oracle."""
+    X = _inputs(11, 3, n)
+    w = jw.wavelets.create(cls)
+    c = jw.CudaFastWaveletTransform(w).forwardBatch(X, lvl)
+    outs = []
+    for up in (1, 0):
+        ctx = jw.Context([0])
+        ctx.set_tuning("dwt_upfront", up)
+        if group:
+            ctx.set_tuning("dwt_group", group)
+        outs.append(jw.CudaFastWaveletTransform(w, context=ctx).reverseBatch(c, lvl))
+        ctx.close()
+    assert np.array_equal(outs[0], outs[1]), (cls, group)
+    rref = oracle.batch("fwt_rev", c, lvl, w.getScalingReConstruction(), w.getWaveletReConstruction(), nthreads=8)
+    assert _maxerr(outs[0], rref, X) <= TOL
+    # (no perfect-reconstruction bound here: the reference's Coiflet5 table reconstructs to 3e-8 only, oracle included)
+    assert _maxerr(outs[0], X, X) <= max(PR_TOL, 2.0 * _maxerr(rref, X, X))
+
+
 def test_workspace_arenas_under_concurrent_device_calls(jw, oracle):
     """Multi-pass transforms take their workspace from the context's per-stream arenas.  Six host threads enqueue 2-D
     FWTs and deep 1-D FWTs on ONE context at once -- three on the context's shared stream, three on private streams --
