@@ -74,6 +74,13 @@ struct DwtPassArgs {
 __device__ __forceinline__ void bulk_load_circ(double* dst, const double* base, int64_t start, int len, int64_t hn,
                                                uint64_t* bar, const double* hi = nullptr, const double* lo_end = nullptr) {
   const bool circ = (hi == nullptr && lo_end == nullptr);
+  // interior tile (all but the first / last of a node): one copy, no wrap logic.  The general path below costs the issuing
+  // thread 100-130 instructions per tile (ptxas turns its subtract loops into a division) -- with k + 1 tiles per CTA
+  // that was a serial prefix of 300-600 instructions in front of the CTA's first byte (profiles/r2_ncu_fwt_inverse.txt)
+  if (circ && start >= 0 && start + len <= hn) {
+    ptx::bulk_g2s(dst, base + start, (uint32_t)len * 8u, bar);
+    return;
+  }
   // no 64-bit modulo here: it would be a subroutine call inside the level loop of the inverse kernel, and everything
   // live across that call (accumulator / tap registers of the other threads' code path) pays for it.  |start| is at
   // most a halo (tens of samples), so the two loops run a handful of times for one thread.
@@ -489,23 +496,6 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
     ptx::fence_mbar_init();
   }
   __syncthreads();   // mbarriers, s_hl and the tap copy are visible
-  if (bulk && a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {   // one wave ahead into L2
-    const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
-    const int ti2 = (int)(nb & (unsigned)(a.tiles - 1));
-    const int p2 = (int)((nb >> a.log_tiles) & (unsigned)(a.nodes - 1));
-    const int64_t b2 = (int64_t)(nb >> (a.log_tiles + a.l0 * (a.nodes > 1 ? 1 : 0)));
-    const int64_t a2 = (int64_t)ti2 * tlen;
-    if (TREE) {
-      const int own = tlen >> a.k;
-      if (tid < (1 << a.k) && own >= 2)
-        ptx::bulk_prefetch_l2(a.in + b2 * a.in_sig + (int64_t)p2 * a.h + (int64_t)tid * (a.h >> a.k) + (a2 >> a.k), (uint32_t)own * 8u);
-    } else if (tid <= a.k) {
-      const int jj = tid == 0 ? a.k : tid;   // thread 0: A_{l0+k}; thread t: D_{l0+t}
-      const int own = tlen >> jj;
-      const double* src = tid == 0 ? (a.ain + b2 * a.ain_sig) : (a.in + b2 * a.in_sig + (a.N >> (a.l0 + jj)));
-      if (own >= 2) ptx::bulk_prefetch_l2(src + (a2 >> jj), (uint32_t)own * 8u);
-    }
-  }
   // ---- prologue: the depth-k set into buffer 0 ------------------------------------------------------------------------------
   {
     const int jj = a.k, len = len_of(jj), st = stride_of(jj);
@@ -531,20 +521,41 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
           ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)len * 8u);
           bulk_load_circ(smem, asrc, start, len, hn, &bars[0], nullptr, ihalo(0));
           bulk_load_circ(smem + st, dsrc, start, len, hn, &bars[0], nullptr, ihalo(1));
-          if (upfront) {
-            for (int j2 = a.k - 1, u2 = 1; j2 >= 1; --j2, ++u2) {   // D_{l0+j2}: read by iteration u2 from buffer u2 & 1
-              const int len2 = len_of(j2);
-              const int64_t hn2 = a.h >> j2, start2 = (a0 >> j2) - s_hl[j2];
-              ptx::mbar_expect_tx(&bars[u2], (uint32_t)len2 * 8u);
-              bulk_load_circ(smem + (u2 & 1) * a.cap + stride_of(j2), in_b + (a.N >> (a.l0 + j2)), start2, len2, hn2,
-                             &bars[u2], nullptr, ihalo(1 + a.k - j2));
-            }
+        }
+        if (upfront && (tid & 31) == 0) {
+          // D_{l0+j2} is read by iteration u2 = k - j2 from buffer u2 & 1.  Lane 0 of warp (u2 mod warps) requests it:
+          // the requests of the levels leave in parallel instead of queueing behind thread 0's address arithmetic
+          const int nw = nt >> 5;
+          for (int u2 = (tid >> 5) == 0 ? nw : (tid >> 5); u2 < a.k; u2 += nw) {
+            const int j2 = a.k - u2;
+            const int len2 = len_of(j2);
+            const int64_t hn2 = a.h >> j2, start2 = (a0 >> j2) - s_hl[j2];
+            ptx::mbar_expect_tx(&bars[u2], (uint32_t)len2 * 8u);
+            bulk_load_circ(smem + (u2 & 1) * a.cap + stride_of(j2), in_b + (a.N >> (a.l0 + j2)), start2, len2, hn2,
+                           &bars[u2], nullptr, ihalo(1 + a.k - j2));
           }
         }
       } else {
         scalar_load_circ(smem, asrc, start, len, hn, tid, nt, nullptr, ihalo(0));
         scalar_load_circ(smem + st, dsrc, start, len, hn, tid, nt, nullptr, ihalo(1));
       }
+    }
+  }
+  if (bulk && a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {   // one wave ahead into L2
+    const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
+    const int ti2 = (int)(nb & (unsigned)(a.tiles - 1));
+    const int p2 = (int)((nb >> a.log_tiles) & (unsigned)(a.nodes - 1));
+    const int64_t b2 = (int64_t)(nb >> (a.log_tiles + a.l0 * (a.nodes > 1 ? 1 : 0)));
+    const int64_t a2 = (int64_t)ti2 * tlen;
+    if (TREE) {
+      const int own = tlen >> a.k;
+      if (tid < (1 << a.k) && own >= 2)
+        ptx::bulk_prefetch_l2(a.in + b2 * a.in_sig + (int64_t)p2 * a.h + (int64_t)tid * (a.h >> a.k) + (a2 >> a.k), (uint32_t)own * 8u);
+    } else if (tid <= a.k) {
+      const int jj = tid == 0 ? a.k : tid;   // thread 0: A_{l0+k}; thread t: D_{l0+t}
+      const int own = tlen >> jj;
+      const double* src = tid == 0 ? (a.ain + b2 * a.ain_sig) : (a.in + b2 * a.in_sig + (a.N >> (a.l0 + jj)));
+      if (own >= 2) ptx::bulk_prefetch_l2(src + (a2 >> jj), (uint32_t)own * 8u);
     }
   }
   // ---- k synthesis levels: depth jj (buffer u&1) -> depth jj-1 (buffer (u+1)&1) ---------------------------------------
