@@ -494,6 +494,17 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
     const int nb = upfront ? a.k : 2;
     for (int q = 0; q < nb; q++) ptx::mbar_init(&bars[q], 1);
     ptx::fence_mbar_init();
+    if (!TREE) {
+      // the first two tiles (A_{l0+k}, D_{l0+k}) are requested before the block barrier below: thread 0 has just
+      // initialised the mbarrier itself, and the halo comes straight from the parameter bank (s_hl is not visible yet)
+      const int jj = a.k, hk = a.hl[a.k];
+      const int len = (tlen >> jj) + hk;
+      const int st = len + (len & 1) + 2 * kDwtR;
+      const int64_t hn = a.h >> jj, start = (a0 >> jj) - hk;
+      ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)len * 8u);
+      bulk_load_circ(smem, a.ain + b * a.ain_sig, start, len, hn, &bars[0], nullptr, ihalo(0));
+      bulk_load_circ(smem + st, in_b + (a.N >> (a.l0 + jj)), start, len, hn, &bars[0], nullptr, ihalo(1));
+    }
   }
   __syncthreads();   // mbarriers, s_hl and the tap copy are visible
   // ---- prologue: the depth-k set into buffer 0 ------------------------------------------------------------------------------
@@ -516,12 +527,7 @@ __global__ void __launch_bounds__(256, (TREE ? (L > 6 ? 2 : 3) : ((L >= 8 && L <
     } else {
       const double* asrc = a.ain + b * a.ain_sig;                 // A_{l0+k}
       const double* dsrc = in_b + (a.N >> (a.l0 + jj));           // D_{l0+k}
-      if (bulk) {
-        if (tid == 0) {
-          ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)len * 8u);
-          bulk_load_circ(smem, asrc, start, len, hn, &bars[0], nullptr, ihalo(0));
-          bulk_load_circ(smem + st, dsrc, start, len, hn, &bars[0], nullptr, ihalo(1));
-        }
+      if (bulk) {   // (A_{l0+k} and D_{l0+k} are on their way since the top of the kernel)
         if (upfront && (tid & 31) == 0) {
           // D_{l0+j2} is read by iteration u2 = k - j2 from buffer u2 & 1.  Lane 0 of warp (u2 mod warps) requests it:
           // the requests of the levels leave in parallel instead of queueing behind thread 0's address arithmetic

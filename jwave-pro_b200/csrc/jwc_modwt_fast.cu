@@ -634,6 +634,11 @@ __global__ void __launch_bounds__(256, (L > 10 ? JWC_INV_MINB : 3)) modwt_inv_pa
       ptx::mbar_init(&bars[0], 1);
       ptx::mbar_init(&bars[1], 1);
       ptx::fence_mbar_init();
+      // V_{j0+k} and W_{j0+k} are requested right here, before the block barrier that publishes the mbarriers
+      const int rows = tlen2 + halo(a.k);
+      ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)rows * 8u);
+      inv_issue_load<WRAP>(a, Vb(0), vin_b, i0, rows, ph0, &bars[0], tid, nt);
+      inv_issue_load<WRAP>(a, Wb(0), co_b + (int64_t)(a.j0 + a.k - 1) * a.N, i0, rows, ph0, &bars[0], tid, nt);
     }
     __syncthreads();
   }
@@ -647,10 +652,9 @@ __global__ void __launch_bounds__(256, (L > 10 ? JWC_INV_MINB : 3)) modwt_inv_pa
     const double* src = (tid == 0) ? (a.vin + b2 * a.vin_sig) : (a.coeffs + b2 * a.coeff_sig + (int64_t)(a.j0 + tid - 1) * a.N);
     ptx::bulk_prefetch_l2(src + i2, (uint32_t)l2 * 8u);
   }
-  // prologue: V_{j0+k} and W_{j0+k}
-  {
+  // prologue: V_{j0+k} and W_{j0+k} (bulk mode: already requested above)
+  if (!bulk) {
     const int rows = tlen2 + halo(a.k);
-    if (bulk && tid == 0) ptx::mbar_expect_tx(&bars[0], 2u * (uint32_t)rows * 8u);
     inv_issue_load<WRAP>(a, Vb(0), vin_b, i0, rows, ph0, &bars[0], tid, nt);
     inv_issue_load<WRAP>(a, Wb(0), co_b + (int64_t)(a.j0 + a.k - 1) * a.N, i0, rows, ph0, &bars[0], tid, nt);
   }
