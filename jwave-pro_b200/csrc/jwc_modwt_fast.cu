@@ -65,6 +65,22 @@ struct RowMap {
   }
 };
 
+// blockIdx / tiles without a division: the quotient of n < 2^31 by d is (umulhi(m, n) + n) >> l with l = ceil(log2 d),
+// m = floor(2^32 (2^l - d) / d) + 1 (Granlund-Montgomery; the sum cannot overflow for n < 2^31).  The run-time
+// division it replaces is ~22 dependent instructions (I2F, MUFU.RCP, F2I, fix-ups) at the very top of every CTA, in
+// front of its first tile request.
+struct FastDiv {
+  unsigned m;
+  int l;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+  FastDiv f{1u, 0};
+  while (((uint64_t)1 << f.l) < d) f.l++;
+  f.m = (unsigned)(((((uint64_t)1 << f.l) - d) << 32) / d + 1);
+  return f;
+}
+__device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv& f) { return (__umulhi(f.m, n) + n) >> f.l; }
+
 struct FwdPassArgs {
   const double* in;   // V_{j0}
   double* coeffs;     // coefficient block base
@@ -72,6 +88,8 @@ struct FwdPassArgs {
   int64_t in_sig, coeff_sig, vout_sig;
   int64_t N, Nd;
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
+  FastDiv tiles_div;   // division by tiles_i
+  int log_groups;      // groups is a power of two (cycles and phases per CTA are)
   int pf_dist;   // L2 prefetch distance in CTAs (0 = off): the tile of CTA blockIdx + pf_dist is pulled into L2
   unsigned nblocks;
   RowMap rm;     // address of a decimated row (cycle index) of a phase-split pass
@@ -174,12 +192,11 @@ __global__ void __launch_bounds__(JWC_FWD_MAXT, (L > 10 ? JWC_FWD_MINB : JWC_FWD
     }
   }
 
-  // CTA index taken apart with 32-bit divisions (nblocks < 2^31; a 64-bit division is a ~100-instruction subroutine)
-  unsigned bid = blockIdx.x;
-  const int ti = (int)(bid % (unsigned)a.tiles_i);
-  bid /= (unsigned)a.tiles_i;
-  const int pg = (int)(bid % (unsigned)a.groups);
-  const int64_t b = (int64_t)(bid / (unsigned)a.groups);
+  // CTA index taken apart without divisions (nblocks < 2^31): multiply-high by tiles_i's magic number, shifts for the groups
+  unsigned bid = fastdiv(blockIdx.x, a.tiles_div);
+  const int ti = (int)(blockIdx.x - bid * (unsigned)a.tiles_i);
+  const int pg = (int)(bid & (unsigned)(a.groups - 1));
+  const int64_t b = (int64_t)(bid >> a.log_groups);
   const int64_t i0 = (int64_t)ti * a.T2;
   const int tlen2 = (int)((a.Nd - i0 < a.T2) ? (a.Nd - i0) : a.T2);
   const int ph0 = pg << a.logP;
@@ -206,8 +223,9 @@ __global__ void __launch_bounds__(JWC_FWD_MAXT, (L > 10 ? JWC_FWD_MINB : JWC_FWD
       if (a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {
         // roughly one wave ahead: the CTA that will own tile blockIdx + pf_dist finds its input in L2
         const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
-        const int ti2 = (int)(nb % (unsigned)a.tiles_i);
-        const int64_t b2 = (int64_t)(nb / (unsigned)a.tiles_i);   // groups == 1 in bulk mode
+        const unsigned q2 = fastdiv(nb, a.tiles_div);
+        const int ti2 = (int)(nb - q2 * (unsigned)a.tiles_i);
+        const int64_t b2 = (int64_t)q2;   // groups == 1 in bulk mode
         const int64_t i2 = (int64_t)ti2 * a.T2;
         const int64_t l2 = (a.Nd - i2 < a.T2) ? (a.Nd - i2) : a.T2;
         ptx::bulk_prefetch_l2(a.in + b2 * a.in_sig + i2, (uint32_t)l2 * 8u);
@@ -443,6 +461,9 @@ int fast_modwt_forward(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     a.j0 = p.j0; a.k = p.k; a.logP = p.logP; a.T2 = p.T2; a.Hp = p.Hp;
     a.tiles_i = (int)((a.Nd + p.T2 - 1) / p.T2);
     a.groups = (int)(cycles >> p.logP);
+    a.tiles_div = make_fastdiv((unsigned)a.tiles_i);
+    a.log_groups = 0;
+    while ((1 << a.log_groups) < a.groups) a.log_groups++;
     a.rm.S0 = (int64_t)1 << p.j0; a.rm.N = n; a.rm.Sm = a.rm.S0 % n; a.rm.invN = 1.0 / (double)n;
     a.rm.wrap = (n % a.rm.S0) != 0 || (ctx->tune.modwt_force_wrap > 0 && p.j0 > 0);
     a.vcap = p.vcap; a.mode = p.mode;
@@ -477,6 +498,8 @@ struct InvPassArgs {
   int64_t vin_sig, coeff_sig, vout_sig;
   int64_t N, Nd;
   int j0, k, logP, T2, Hp, tiles_i, groups, vcap, mode;
+  FastDiv tiles_div;   // division by tiles_i
+  int log_groups;      // groups is a power of two (cycles and phases per CTA are)
   int pf_dist;
   RowMap rm;
   int top_barrier;   // 1 = round-1 form of the tile wait (one thread on the mbarrier, the rest on a block barrier)
@@ -613,12 +636,11 @@ __global__ void __launch_bounds__(256, (L > 10 ? JWC_INV_MINB : 3)) modwt_inv_pa
     }
   }
 
-  // CTA index taken apart with 32-bit divisions (nblocks < 2^31; a 64-bit division is a ~100-instruction subroutine)
-  unsigned bid = blockIdx.x;
-  const int ti = (int)(bid % (unsigned)a.tiles_i);
-  bid /= (unsigned)a.tiles_i;
-  const int pg = (int)(bid % (unsigned)a.groups);
-  const int64_t b = (int64_t)(bid / (unsigned)a.groups);
+  // CTA index taken apart without divisions (nblocks < 2^31): multiply-high by tiles_i's magic number, shifts for the groups
+  unsigned bid = fastdiv(blockIdx.x, a.tiles_div);
+  const int ti = (int)(blockIdx.x - bid * (unsigned)a.tiles_i);
+  const int pg = (int)(bid & (unsigned)(a.groups - 1));
+  const int64_t b = (int64_t)(bid >> a.log_groups);
   const int64_t i0 = (int64_t)ti * a.T2;
   const int tlen2 = (int)((a.Nd - i0 < a.T2) ? (a.Nd - i0) : a.T2);
   const int ph0 = pg << a.logP;
@@ -645,8 +667,9 @@ __global__ void __launch_bounds__(256, (L > 10 ? JWC_INV_MINB : 3)) modwt_inv_pa
   if (bulk && a.pf_dist > 0 && tid <= a.k && blockIdx.x + (unsigned)a.pf_dist < a.nblocks) {
     // one wave ahead: thread t pulls the W_{j0+t} tile (t = 1..k) resp. the V tile (t = 0) of CTA blockIdx + pf_dist into L2
     const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
-    const int ti2 = (int)(nb % (unsigned)a.tiles_i);
-    const int64_t b2 = (int64_t)(nb / (unsigned)a.tiles_i);
+    const unsigned q2 = fastdiv(nb, a.tiles_div);
+    const int ti2 = (int)(nb - q2 * (unsigned)a.tiles_i);
+    const int64_t b2 = (int64_t)q2;
     const int64_t i2 = (int64_t)ti2 * a.T2;
     const int64_t l2 = (a.Nd - i2 < a.T2) ? (a.Nd - i2) : a.T2;
     const double* src = (tid == 0) ? (a.vin + b2 * a.vin_sig) : (a.coeffs + b2 * a.coeff_sig + (int64_t)(a.j0 + tid - 1) * a.N);
@@ -791,6 +814,9 @@ int fast_modwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, con
     a.j0 = p.j0; a.k = p.k; a.logP = p.logP; a.T2 = p.T2; a.Hp = p.Hp;
     a.tiles_i = (int)((a.Nd + p.T2 - 1) / p.T2);
     a.groups = (int)(cycles >> p.logP);
+    a.tiles_div = make_fastdiv((unsigned)a.tiles_i);
+    a.log_groups = 0;
+    while ((1 << a.log_groups) < a.groups) a.log_groups++;
     a.rm.S0 = (int64_t)1 << p.j0; a.rm.N = n; a.rm.Sm = a.rm.S0 % n; a.rm.invN = 1.0 / (double)n;
     a.rm.wrap = (n % a.rm.S0) != 0 || (ctx->tune.modwt_force_wrap > 0 && p.j0 > 0);
     a.vcap = p.vcap; a.mode = p.mode;
