@@ -78,7 +78,8 @@ struct Tuning {
   int dwt_fixed = 0;        // > 0: per-pass fixed cost of the FWT planner's model, 0.01 ps per sample (experiments)
   int dwt_k0 = 0;           // > 0: levels fused by the first FWT / WPT pass (experiments; 0 = planner's choice)
   int dwt_upfront = 1;      // 1 = pyramid inverse requests every detail tile of a pass in the prologue (jwc_dwt_fast.cu); 0 = one level ahead (round 1)
-  int top_barrier = 0;      // 1 = inverse tile kernels wait for their TMA tiles with one thread + a block barrier (round-1 form)
+  int top_barrier = 0;      // 1 = inverse tile kernels wait for their TMA tiles with one thread + a block barrier (round-1 form);
+                            // >= 16 = per-thread wait with that suspend-time hint in ns (measured: no effect, r2_sweeps.txt call r7e)
   int modwt_logp = 0;       // phases per CTA (log2) of the phase-split MODWT passes: 0 = auto, 1 or 2 = forced
   int modwt_tile_deep = 0;  // tile override (decimated samples) of the phase-split MODWT passes only, 0 = auto
 };

@@ -65,22 +65,6 @@ struct RowMap {
   }
 };
 
-// blockIdx / tiles without a division: the quotient of n < 2^31 by d is (umulhi(m, n) + n) >> l with l = ceil(log2 d),
-// m = floor(2^32 (2^l - d) / d) + 1 (Granlund-Montgomery; the sum cannot overflow for n < 2^31).  The run-time
-// division it replaces is ~22 dependent instructions (I2F, MUFU.RCP, F2I, fix-ups) at the very top of every CTA, in
-// front of its first tile request.
-struct FastDiv {
-  unsigned m;
-  int l;
-};
-inline FastDiv make_fastdiv(unsigned d) {
-  FastDiv f{1u, 0};
-  while (((uint64_t)1 << f.l) < d) f.l++;
-  f.m = (unsigned)(((((uint64_t)1 << f.l) - d) << 32) / d + 1);
-  return f;
-}
-__device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv& f) { return (__umulhi(f.m, n) + n) >> f.l; }
-
 struct FwdPassArgs {
   const double* in;   // V_{j0}
   double* coeffs;     // coefficient block base

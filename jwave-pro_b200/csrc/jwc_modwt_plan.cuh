@@ -52,6 +52,28 @@ struct ModwtPlanInput {
   bool inverse;        // inverse needs (V ping-pong + W double buffer), forward (V ping-pong + W staging)
 };
 
+// blockIdx / tiles without a division: the quotient of n < 2^31 by d is (mulhi(m, n) + n) >> l with l = ceil(log2 d),
+// m = floor(2^32 (2^l - d) / d) + 1 (Granlund-Montgomery; the sum cannot overflow for n < 2^31).  The run-time
+// division it replaces is ~22 dependent instructions (I2F, MUFU.RCP, F2I, fix-ups) at the very top of every CTA, in
+// front of its first tile request (tests/test_plan_bounds.py::test_fastdiv checks it on the CPU).
+struct FastDiv {
+  unsigned m;
+  int l;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+  FastDiv f{1u, 0};
+  while (((uint64_t)1 << f.l) < d) f.l++;
+  f.m = (unsigned)(((((uint64_t)1 << f.l) - d) << 32) / d + 1);
+  return f;
+}
+JWC_HD inline unsigned fastdiv(unsigned n, const FastDiv& f) {
+#ifdef __CUDA_ARCH__
+  return (__umulhi(f.m, n) + n) >> f.l;
+#else
+  return ((unsigned)(((uint64_t)f.m * n) >> 32) + n) >> f.l;
+#endif
+}
+
 inline int64_t modwt_halo(int L, int k) { return (int64_t)(L - 1) * (((int64_t)1 << k) - 1); }
 
 // The walk t -> t + 2^j0 (mod n) on a circular signal splits it into G = gcd(2^j0, n) interleaved cycles of n / G

@@ -13,6 +13,23 @@ int main(int argc, char** argv) {
   const char* kind = argv[1];
   const int64_t n = atoll(argv[2]);
   const int levels = atoi(argv[3]), L = atoi(argv[4]), inverse = atoi(argv[5]), budget = atoi(argv[6]);
+  if (!strcmp(kind, "fastdiv")) {   // argv[2] = divisor: the multiply-high quotient against the real one
+    const unsigned d = (unsigned)n;
+    const FastDiv f = make_fastdiv(d);
+    unsigned long long bad = 0, checked = 0;
+    auto chk = [&](unsigned long long v) {
+      if (v >= (1ull << 31)) return;
+      checked++;
+      if (fastdiv((unsigned)v, f) != (unsigned)(v / d)) bad++;
+    };
+    for (unsigned long long v = 0; v < 300000; v++) chk(v);
+    for (unsigned long long q = 1; q < 200000; q++) { chk(q * d); chk(q * d - 1); chk(q * d + 1); }
+    for (unsigned long long v = (1ull << 31) - 300000; v < (1ull << 31); v++) chk(v);
+    unsigned long long x = 88172645463325252ull;
+    for (int i = 0; i < 2000000; i++) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; chk(x & 0x7fffffffull); }
+    printf("{\"ok\": %d, \"checked\": %llu, \"m\": %u, \"l\": %d}\n", bad == 0 ? 1 : 0, checked, f.m, f.l);
+    return 0;
+  }
   if (!strcmp(kind, "modwt")) {
     ModwtPlanInput in{};
     in.n = n; in.J = levels; in.L = L; in.aligned16 = true; in.smem_budget = budget; in.inverse = inverse != 0;

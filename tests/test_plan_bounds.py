@@ -142,3 +142,13 @@ def test_dwt_plan_bounds(dump, L, kind, n, levels, inverse, budget):
             assert (tlen >> k) % 2 == 0
         assert 2 * cap * 8 + 2 * 64 * 8 + 128 <= p["smem"] <= budget + 4096
     assert l == levels
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 7, 39, 40, 41, 64, 79, 512, 1000, 4095, 4096, 4097, 65535, 65536, 99999,
+                               (1 << 20) + 1, (1 << 30) - 1, 1 << 30, (1 << 31) - 1])
+def test_fastdiv(dump, d):
+    """The MODWT tile kernels take blockIdx apart with a multiply-high by the tile count's magic number
+    (jwc_modwt_plan.cuh::make_fastdiv / fastdiv): exact for every n < 2^31 the launcher allows -- small n, multiples
+    of d and their neighbours, the top of the range, 2 M pseudo-random values."""
+    r = dump("fastdiv", d, 0, 0, False, 0)
+    assert r["ok"] == 1 and r["checked"] > 2_000_000, r
