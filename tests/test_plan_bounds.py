@@ -152,3 +152,60 @@ def test_fastdiv(dump, d):
     of d and their neighbours, the top of the range, 2 M pseudo-random values."""
     r = dump("fastdiv", d, 0, 0, False, 0)
     assert r["ok"] == 1 and r["checked"] > 2_000_000, r
+
+
+@pytest.mark.parametrize("L", [2, 4, 8, 16, 20, 30, 40])
+@pytest.mark.parametrize("n,levels", [(1 << 20, 20), (65536, 16), (4096, 12), (1 << 18, 7), (1024, 10), (256, 8)])
+@pytest.mark.parametrize("group", [0, 4, 5, 8, 12])
+@pytest.mark.parametrize("budget", [45000, 113000])
+def test_fwt_inverse_upfront_tiles_nest(dump, L, n, levels, group, budget):
+    """Pyramid inverse with every detail tile of a pass requested in the prologue (jwc_dwt_fast.cu, `upfront`): whenever
+    the host-side condition of fast_dwt_inverse holds, the k + 1 TMA-written tiles and the low-pass arrays the levels
+    write never overlap while they are live, and every slot stays inside its buffer."""
+    exe_args = ["fwt", n, levels, L, True, budget]
+    import subprocess as sp
+    out = sp.run([EXE] + [str(int(a)) if not isinstance(a, str) else a for a in exe_args] + ([str(group)] if group else []),
+                 capture_output=True, text=True, check=True).stdout
+    plan = json.loads(out)
+    if not plan["ok"]:
+        pytest.skip("shape declined by the fused path")
+    R = plan["R"]
+
+    def stride(ln):
+        return ln + (ln & 1) + 2 * R
+
+    def halo(jj):
+        h = 0
+        for _ in range(jj):
+            h = (h + 1) // 2 + (L // 2 - 1)
+            h += h & 1
+        return h
+
+    checked = 0
+    for p in plan["passes"]:
+        k, cap = p["k"], p["cap"]
+        tlen = min(n >> p["l0"], p["T"])
+        ln = [(tlen >> j) + halo(j) for j in range(k + 1)]
+        if p["mode"] != 0 or k < 2 or k > 16:
+            continue
+        if not all(stride(ln[j - 2]) >= stride(ln[j]) + ln[j] for j in range(3, k + 1)):
+            continue   # the kernel keeps the one-level-ahead prefetch for this pass
+        checked += 1
+        # (buffer, lo, hi, first step, last step) of everything that holds data; step -1 = prologue, step u = level k - u
+        live = [(0, 0, ln[k], -1, 0), (0, stride(ln[k]), stride(ln[k]) + ln[k], -1, 0)]
+        for j in range(k - 1, 0, -1):
+            u = k - j
+            live.append((u & 1, stride(ln[j]), stride(ln[j]) + ln[j], -1, u))          # D_j, TMA-written, read by step u
+        for u in range(k):
+            j_out = k - u - 1
+            live.append(((u + 1) & 1, 0, ln[j_out], u, u + 1))                            # A_{j_out}, written by step u
+        for (b, lo, hi, _, _) in live:
+            assert 0 <= lo < hi <= cap, (p, b, lo, hi)
+        for x in range(len(live)):
+            for y in range(x + 1, len(live)):
+                bx, lx, hx, fx, tx = live[x]
+                by, ly, hy, fy, ty = live[y]
+                if bx == by and max(fx, fy) <= min(tx, ty) and max(lx, ly) < min(hx, hy):
+                    raise AssertionError(("overlap", p, live[x], live[y]))
+    if L <= 16 and n >= 65536 and budget == 45000:
+        assert checked > 0   # the shapes of the benchmark do take the up-front path
