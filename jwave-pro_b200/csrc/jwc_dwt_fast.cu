@@ -883,7 +883,8 @@ int fast_dwt_inverse(jwc_ctx* ctx, const DeviceSlot& dev, cudaStream_t st, const
     if (ctx->tune.pf_inv != 0) a.pf_dist = (p.mode == DWT_BULK && ctx->tune.pf_inv > 0) ? ctx->tune.pf_inv : 0;
     a.top_barrier = ctx->tune.top_barrier;
     a.upfront = 0;
-    if (!tree && p.mode == DWT_BULK && ctx->tune.dwt_upfront > 0 && p.k >= 2 && p.k <= 16) {
+    // (k <= 15: one mbarrier per level in 16 slots and the 16-entry halo table; whole warps: lane 0 of warp u requests tile u)
+    if (!tree && p.mode == DWT_BULK && ctx->tune.dwt_upfront > 0 && p.k >= 2 && p.k <= 15 && (p.threads & 31) == 0) {
       // the detail tiles of one buffer must nest: slot of D_j = [stride_j, stride_j + len_j) below the slot of D_{j-2}
       const int64_t tl = std::min<int64_t>(a.h, p.T);
       bool ok = true;
