@@ -66,3 +66,67 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "oracle" not in txt.lower(), "%s mentions the oracle" % f
+
+
+def test_java_ffm_descriptors_match_the_header():
+    """The Java drop-in cannot be compiled here (no JDK), so its Panama FunctionDescriptors are checked statically: every
+    symbol java/.../JwcNative.java binds must be declared in include/jwavecuda.h with the same return type and the
+    same argument kinds in the same order (pointer -> ADDRESS, int64_t / size_t -> JAVA_LONG, int / unsigned -> JAVA_INT)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "jwavecuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"JWC_API\s+([\w\s\*]+?)\s*\b(jwc_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
+
+        def kind(t):
+            t = t.strip()
+            if "*" in t:
+                return "ADDRESS"
+            base = re.sub(r"\b(const|unsigned|signed)\b", "", t).split()
+            word = base[0] if base else "int"           # "unsigned flags" -> int-sized
+            if "int64_t" in t or "size_t" in t or "uint64_t" in t:
+                return "JAVA_LONG"
+            if word in ("int", "flags") or t.startswith("unsigned") or "int" in t.split():
+                return "JAVA_INT"
+            if word == "double":
+                return "JAVA_DOUBLE"
+            if word == "void":
+                return "VOID"
+            raise AssertionError("unmapped C type %r in %s" % (t, name))
+        argl = [] if args.strip() in ("", "void") else [kind(a.rsplit(None, 1)[0] if "*" not in a.rsplit(None, 1)[-1] else a)
+                                                         for a in args.split(",")]
+        protos[name] = [kind(ret)] + argl
+    java = open(os.path.join(root, "java", "jwave", "transforms", "cuda", "JwcNative.java")).read()
+    java = re.sub(r"//[^\n]*", " ", java)
+
+    def parse_fd(text):
+        m = re.match(r"FunctionDescriptor\.(of|ofVoid)\s*\((.*)\)\s*$", text.strip(), flags=re.S)
+        assert m, text
+        parts = [p.strip() for p in m.group(2).split(",") if p.strip()]
+        return (["VOID"] + parts) if m.group(1) == "ofVoid" else parts
+
+    def balanced(s, start):   # text of the call whose '(' is at or after `start`, up to its matching ')'
+        i = s.index("(", start)
+        depth, j = 0, i
+        while True:
+            depth += s[j] == "("
+            depth -= s[j] == ")"
+            if depth == 0:
+                return s[start:j + 1]
+            j += 1
+    variables = {m.group(1): parse_fd(balanced(java, m.start(2)))
+                 for m in re.finditer(r"FunctionDescriptor\s+(\w+)\s*=\s*(FunctionDescriptor\.)", java)}
+    arrays = {m.group(1): re.findall(r'"(jwc_\w+)"', m.group(2))
+              for m in re.finditer(r"String\[\]\s+(\w+)\s*=\s*\{(.*?)\}", java, flags=re.S)}
+    bound = {}
+    for m in re.finditer(r'handle\(\s*"(jwc_\w+)"\s*,\s*(FunctionDescriptor\.)', java):
+        bound[m.group(1)] = parse_fd(balanced(java, m.start(2)))
+    for m in re.finditer(r"handle\(\s*(\w+)\[i\]\s*,\s*(\w+)\s*\)", java):
+        for name in arrays[m.group(1)]:
+            bound[name] = variables[m.group(2)]
+    assert len(bound) >= 20, sorted(bound)
+    for name, fd in sorted(bound.items()):
+        assert name in protos, "%s is bound in JwcNative.java but not declared in jwavecuda.h" % name
+        assert fd == protos[name], (name, fd, protos[name])
