@@ -71,6 +71,14 @@ def circular_convolve(x, f, adjoint=False):
     return out
 
 
+def fft(re, im=None, inverse=False):
+    """FastFourierTransform.java:130-163 (Cooley-Tukey for 2^p, Bluestein otherwise); returns (re, im)."""
+    r = _c(re).copy()
+    i = np.zeros_like(r) if im is None else _c(im).copy()
+    lib().jwo_fft(_p(r), _p(i), ctypes.c_int(len(r)), ctypes.c_int(1 if inverse else 0))
+    return r, i
+
+
 def modwt_forward(x, J, g, h, dense=False, fft=False):
     x, g, h = _c(x), _c(g), _c(h)
     N = len(x)

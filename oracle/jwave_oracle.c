@@ -322,6 +322,10 @@ static void fft_any(double* re, double* im, int n, int inverse) {
   else fft_bluestein(re, im, n, inverse);
 }
 
+/* exported for the known-answer tests: the reference's FFT fixtures (src/test/resources/testdata/fft_*.txt, checked by
+ * CrossValidationTest.java:119-154 through Transform.forward: forward unscaled, inverse 1/n) */
+JWO_API void jwo_fft(double* re, double* im, int n, int inverse) { fft_any(re, im, n, inverse); }
+
 /* transforms/MODWTTransform.java:729-741 (wrapFilterToSignalLength), :752-786 (circularConvolveFFT),
  * :798-837 (circularConvolveFFTAdjoint, conjugates the filter spectrum).  ws = 4*N doubles. */
 static void conv_fft(const double* x, int N, const double* f, int M, int adjoint, double* out, double* ws) {

@@ -7,6 +7,8 @@ tests read.  Sources (relative to /root/reference/src/test/):
   resources/testdata/filter_haar_{dec,rec}_{lo,hi}.txt           (java/jwave/transforms/CrossValidationTest.java:159-209)
   java/jwave/transforms/MODWTTransformTest.java:39-71              MODWT Haar level 1 of [1..8] (literals below)
   java/jwave/transforms/MODWTFFTAdjointVerificationTest.java:44-101  adjoint == transpose of the convolution matrix
+  resources/testdata/fft_{dc,impulse}_{input,output_real,output_imag}.txt   (CrossValidationTest.java:119-154)
+  resources/testdata/filter_db2_dec_lo.txt, filter_db4_dec_{lo,hi}.txt, haar_{constant,linear}_input.txt
 """
 import json
 import os
@@ -54,6 +56,26 @@ def main():
         "signal": sig, "filter": f,
         "direct": [sum(H[i][j] * sig[j] for j in range(N)) for i in range(N)],
         "adjoint": [sum(H[j][i] * sig[j] for j in range(N)) for i in range(N)],
+    }
+    # FFT fixtures (the FFT is only the CPU baseline's engine here, but the baseline should be the reference's FFT)
+    g["fft_fixtures"] = {
+        "source": "CrossValidationTest.java:119-154 (testFFTWithReferenceData), tolerance 1e-10",
+        "dc": {"input": read("fft_dc_input.txt"), "real": read("fft_dc_output_real.txt"),
+               "imag": read("fft_dc_output_imag.txt")},
+        "impulse": {"input": read("fft_impulse_input.txt"), "real": read("fft_impulse_output_real.txt"),
+                    "imag": read("fft_impulse_output_imag.txt")},
+        "sine_input": read("fft_sine_simple_input.txt"),
+    }
+    # filter fixtures the reference ships beside the Haar ones (PyWavelets naming: db2 = 2 taps = Haar1, db4 = 4 taps
+    # = JWave's Daubechies2); no reference test reads them, they pin the extracted tables to 17 digits
+    g["filter_fixtures"] = {
+        "source": "src/test/resources/testdata/filter_db2_dec_lo.txt, filter_db4_dec_{lo,hi}.txt",
+        "Haar1": {"dec_lo": read("filter_db2_dec_lo.txt")},
+        "Daubechies2": {"dec_lo": read("filter_db4_dec_lo.txt"), "dec_hi": read("filter_db4_dec_hi.txt")},
+    }
+    g["haar_more_inputs"] = {
+        "source": "src/test/resources/testdata/haar_constant_input.txt, haar_linear_input.txt (inputs only)",
+        "constant": read("haar_constant_input.txt"), "linear": read("haar_linear_input.txt"),
     }
     with open(os.path.join(HERE, "reference_kats.json"), "w") as fh:
         json.dump(g, fh, indent=1)
