@@ -490,6 +490,9 @@ struct InvPassArgs {
   unsigned nblocks;
 };
 
+// -DJWC_INV_ONE_SUM=1: experiment of round 2 (profiles/r2_sweeps.txt, calls r7a / r7b), NOT the shipped form: 84 instead of
+// 96 registers for the 40-tap filter, no gain with 128 or 256 threads, -4 % with 9-row items; the default keeps the
+// reference's two sums.
 #ifndef JWC_INV_ONE_SUM
 #define JWC_INV_ONE_SUM 0
 #endif
